@@ -1,0 +1,123 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the REFERENCE's own code.
+
+Run in the build container (where /root/reference exists):
+
+    make -C oracle ref && python oracle/gen_golden.py
+
+Every array under tests/golden/ is an input or an output of oracle/_ref/libmxref.so, i.e. of the
+reference's headers compiled in place (oracle/ref_harness.cc lists the functions). The fixtures are
+small (a few hundred KB) and travel with the repository, so the GPU box -- which has no
+/root/reference -- can still check both the oracle and the CUDA path against reference outputs.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import kvoracle as K  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def u(rng, *shape):
+    return rng.uniform(-1, 1, shape).astype(np.float32)
+
+
+def main():
+    r = K.ref()
+    assert r is not None, "build oracle/_ref first: make -C oracle ref"
+    os.makedirs(GOLD, exist_ok=True)
+    rng = np.random.default_rng(0xB200)
+
+    # ---- dense reduce, CommCPU association, 1..9 sources + a >BIGARRAY_BOUND threaded case ----
+    d = {}
+    for n in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+        srcs = [u(rng, 1031) for _ in range(n)]
+        d["n%d_src" % n] = np.stack(srcs)
+        d["n%d_out" % n] = r.reduce(srcs)
+    np.savez_compressed(os.path.join(GOLD, "reduce_local.npz"), **d)
+
+    # ---- optimizers ----
+    d = {}
+    n = 2053
+    hp = dict(lr=0.1, wd=1e-4, rescale=1.0 / 256, momentum=0.9)
+    for tag, clip in (("noclip", None), ("clip", 0.002)):
+        w, g, m = u(rng, n), u(rng, n), u(rng, n)
+        d["sgd_%s_in" % tag] = np.stack([w, g])
+        d["sgd_%s_out" % tag] = r.sgd_update(w.copy(), g, hp["lr"], hp["wd"], hp["rescale"], clip)
+        w2, m2 = w.copy(), m.copy()
+        r.sgd_mom_update(w2, g, m2, hp["lr"], hp["momentum"], hp["wd"], hp["rescale"], clip)
+        d["sgdmom_%s_in" % tag] = np.stack([w, g, m])
+        d["sgdmom_%s_out" % tag] = np.stack([w2, m2])
+        w2, m2 = w.copy(), m.copy()
+        r.multi_sgd_update([w2], [g], [m2], [hp["lr"]], [hp["wd"]], hp["momentum"], hp["rescale"],
+                           clip)
+        d["multisgdmom_%s_out" % tag] = np.stack([w2, m2])
+        w2 = w.copy()
+        r.multi_sgd_update([w2], [g], None, [hp["lr"]], [hp["wd"]], 0.0, hp["rescale"], clip)
+        d["multisgd_%s_out" % tag] = w2
+        v = np.abs(u(rng, n))
+        w2, m2, v2 = w.copy(), m.copy(), v.copy()
+        # five Adam steps with the python-side bias-corrected lr (optimizer.py:1617-1620)
+        outs = []
+        aclip = None if clip is None else 0.5
+        for t in range(1, 6):
+            lr_t = K.f32(K.adam_lr(1e-3, 0.9, 0.999, t))
+            r.adam_update(w2, g, m2, v2, lr_t, K.f32(0.9), K.f32(0.999), K.f32(1e-8), K.f32(0.01),
+                          1.0, aclip)
+            outs.append(np.stack([w2.copy(), m2.copy(), v2.copy()]))
+        d["adam_%s_in" % tag] = np.stack([w, g, m, v])
+        d["adam_%s_out" % tag] = np.stack(outs)
+        # fp16 mixed precision
+        w32 = u(rng, n)
+        w16 = w32.astype(np.float16).view(np.uint16)
+        g16 = u(rng, n).astype(np.float16).view(np.uint16)
+        a16, a32, am = w16.copy(), w32.copy(), m.copy()
+        r.multi_mp_sgd_update_f16([a16], [a32], [g16], [am], [hp["lr"]], [hp["wd"]],
+                                  hp["momentum"], hp["rescale"], clip)
+        d["mp_%s_in16" % tag] = np.stack([w16, g16])
+        d["mp_%s_in32" % tag] = np.stack([w32, m])
+        d["mpmom_%s_out16" % tag] = a16
+        d["mpmom_%s_out32" % tag] = np.stack([a32, am])
+        a16, a32 = w16.copy(), w32.copy()
+        r.mp_sgd_update_f16(a16, a32, g16, hp["lr"], hp["wd"], hp["rescale"], clip)
+        d["mpsgd_%s_out16" % tag] = a16
+        d["mpsgd_%s_out32" % tag] = a32
+    d["hp"] = np.array([hp["lr"], hp["wd"], hp["rescale"], hp["momentum"]], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "optimizers.npz"), **d)
+
+    # ---- lazy row_sparse updates ----
+    d = {}
+    R, L, nnr = 200, 24, 40
+    for tag, clip in (("noclip", None), ("clip", 0.3)):
+        w, m = u(rng, R, L), u(rng, R, L)
+        v = np.abs(u(rng, R, L))
+        gi = np.sort(rng.choice(R, nnr, replace=False)).astype(np.int64)
+        gv = u(rng, nnr, L)
+        d["rsp_%s_in" % tag] = np.stack([w, m, v])
+        d["rsp_%s_gidx" % tag] = gi
+        d["rsp_%s_gval" % tag] = gv
+        d["rsp_sgd_%s_out" % tag] = r.sgd_rsp_update(w.copy(), gi, gv, 0.1, 1e-3, 0.5, clip)
+        w2, m2 = w.copy(), m.copy()
+        r.sgd_mom_rsp_update(w2, m2, gi, gv, 0.1, 0.9, 1e-3, 0.5, clip)
+        d["rsp_sgdmom_%s_out" % tag] = np.stack([w2, m2])
+        w2, m2, v2 = w.copy(), m.copy(), v.copy()
+        r.adam_rsp_update(w2, m2, v2, gi, gv, 1e-3, wd=0.01, clip=clip)
+        d["rsp_adam_%s_out" % tag] = np.stack([w2, m2, v2])
+    np.savez_compressed(os.path.join(GOLD, "rowsparse_updates.npz"), **d)
+
+    # ---- 2-bit compression ----
+    g = u(rng, 1003)
+    res = np.zeros_like(g)
+    comp1 = r.quantize_2bit(g, res, 0.5)
+    res1 = res.copy()
+    comp2 = r.quantize_2bit(g, res, 0.5)
+    np.savez_compressed(os.path.join(GOLD, "twobit.npz"), grad=g, comp1=comp1, res1=res1,
+                        comp2=comp2, res2=res.copy(), deq1=r.dequantize_2bit(comp1, g.size, 0.5))
+    print("wrote", sorted(os.listdir(GOLD)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,466 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy front-end of the CPU oracle (oracle/kvoracle.c) and of the
+reference harness (oracle/_ref/libmxref.so, built from the reference's own headers).
+
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference legs.
+The product package (anand_mxnet_b200) never imports this module.
+
+Two objects are exported:
+  * ``oracle``  -- the plain-C restatement (always available; built on demand with gcc)
+  * ``ref()``   -- the reference harness or ``None`` when oracle/_ref/libmxref.so is absent
+
+plus a pure-numpy restatement of the host orchestration the reference performs around the
+arithmetic (key grouping, update counts, lr/wd multipliers, Adam bias correction), each citing the
+reference file:line it follows.
+"""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_F = ctypes.c_float
+_P = ctypes.c_void_p
+_SZ = ctypes.c_size_t
+_I = ctypes.c_int
+
+
+def build(ref=True):
+    """Compile oracle/libkvoracle.so (and oracle/_ref/libmxref.so when /root/reference exists)."""
+    subprocess.run(["make", "-s", "-C", _HERE, "oracle"], check=True)
+    if ref and os.path.isdir("/root/reference/src/kvstore"):
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr_array(arrs):
+    return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+class Oracle(object):
+    """numpy API over oracle/libkvoracle.so (the plain-C restatement)."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "libkvoracle.so")
+        src = os.path.join(_HERE, "kvoracle.c")
+        if (not os.path.exists(path)) or os.path.getmtime(path) < os.path.getmtime(src):
+            build(ref=False)
+        self.lib = ctypes.CDLL(path)
+        L = self.lib
+        L.kvo_half_to_float.restype = _F
+        L.kvo_half_to_float.argtypes = [ctypes.c_uint16, _I]
+        L.kvo_float_to_half.restype = ctypes.c_uint16
+        L.kvo_float_to_half.argtypes = [_F, _I]
+        L.kvo_unique_i64.restype = _SZ
+        L.kvo_rsp_reduce.restype = _SZ
+        L.kvo_reduce_local.argtypes = [_P, _I, _SZ, _P, _I]
+        L.kvo_reduce_device.argtypes = [_P, _I, _SZ, _P, _I]
+        L.kvo_sgd_update.argtypes = [_SZ, _P, _P, _P, _F, _F, _F, _F, _I]
+        L.kvo_sgd_mom_update.argtypes = [_SZ, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I]
+        L.kvo_multi_sgd_update.argtypes = [_SZ, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I]
+        L.kvo_adam_update.argtypes = [_SZ, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F, _I]
+        L.kvo_test_update.argtypes = [_SZ, _P, _P, _P, _F, _I]
+        L.kvo_mp_sgd_update.argtypes = [_SZ, _P, _P, _P, _I, _F, _F, _F, _F, _I]
+        L.kvo_mp_sgd_mom_update.argtypes = [_SZ, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _I]
+        L.kvo_multi_mp_sgd_update.argtypes = [_SZ, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _I]
+        L.kvo_unique_i64.argtypes = [_P, _SZ]
+        L.kvo_rsp_reduce.argtypes = [_I, _P, _P, _P, _SZ, _P, _P]
+        L.kvo_sparse_retain.argtypes = [_P, _SZ, _P, _SZ, _P, _SZ, _I, _P, _P]
+        L.kvo_sgd_rsp_update.argtypes = [_SZ, _SZ, _P, _P, _P, _F, _F, _F, _F]
+        L.kvo_sgd_mom_rsp_update.argtypes = [_SZ, _SZ, _P, _P, _P, _P, _F, _F, _F, _F, _F]
+        L.kvo_adam_rsp_update.argtypes = [_SZ, _SZ, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F]
+        L.kvo_quantize_2bit.argtypes = [_SZ, _P, _P, _P, _F]
+        L.kvo_dequantize_2bit.argtypes = [_SZ, _P, _P, _F]
+
+    # ---- dense reduce -------------------------------------------------------------------
+    def reduce(self, srcs, order="local", nthreads=1):
+        """Sum a list of equal-shape fp32 arrays in the reference's association order."""
+        srcs = [_f32(s).ravel() for s in srcs]
+        out = np.empty_like(srcs[0])
+        fn = self.lib.kvo_reduce_local if order == "local" else self.lib.kvo_reduce_device
+        fn(_ptr_array(srcs), len(srcs), srcs[0].size, _ptr(out), nthreads)
+        return out
+
+    # ---- optimizers (in place on w / states, returns w) ----------------------------------
+    @staticmethod
+    def _clip(c):
+        return -1.0 if (c is None or c is False) else float(c)
+
+    def sgd_update(self, w, g, lr, wd=0.0, rescale=1.0, clip=None, nthreads=1):
+        self.lib.kvo_sgd_update(w.size, _ptr(w), _ptr(w), _ptr(g), self._clip(clip), lr, wd,
+                                rescale, nthreads)
+        return w
+
+    def sgd_mom_update(self, w, g, mom, lr, momentum, wd=0.0, rescale=1.0, clip=None, nthreads=1):
+        self.lib.kvo_sgd_mom_update(w.size, _ptr(w), _ptr(mom), _ptr(w), _ptr(g), self._clip(clip),
+                                    momentum, lr, wd, rescale, nthreads)
+        return w
+
+    def multi_sgd_update(self, w, g, mom, lr, momentum=0.0, wd=0.0, rescale=1.0, clip=None,
+                         nthreads=1):
+        self.lib.kvo_multi_sgd_update(w.size, _ptr(w), _ptr(mom) if mom is not None else None,
+                                      _ptr(w), _ptr(g), self._clip(clip), momentum, lr, wd,
+                                      rescale, nthreads)
+        return w
+
+    def adam_update(self, w, g, mean, var, lr, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0,
+                    rescale=1.0, clip=None, nthreads=1):
+        self.lib.kvo_adam_update(w.size, _ptr(w), _ptr(mean), _ptr(var), _ptr(w), _ptr(g),
+                                 self._clip(clip), rescale, beta1, beta2, lr, wd, eps, nthreads)
+        return w
+
+    def test_update(self, w, g, rescale=1.0, nthreads=1):
+        self.lib.kvo_test_update(w.size, _ptr(w), _ptr(w), _ptr(g), rescale, nthreads)
+        return w
+
+    # ---- 16-bit -----------------------------------------------------------------------
+    def to_half(self, a, kind):
+        """fp32 -> uint16 bit patterns (kind 0 = fp16, 1 = bf16), round-to-nearest-even."""
+        a = _f32(a)
+        f = self.lib.kvo_float_to_half
+        return np.array([f(float(x), kind) for x in a.ravel()], dtype=np.uint16).reshape(a.shape) \
+            if a.size < 4096 else self._to_half_np(a, kind)
+
+    @staticmethod
+    def _to_half_np(a, kind):
+        if kind == 0:
+            return a.astype(np.float16).view(np.uint16)
+        x = a.view(np.uint32).astype(np.uint64)
+        x = x + 0x7fff + ((x >> 16) & 1)
+        return (x >> 16).astype(np.uint16)
+
+    @staticmethod
+    def from_half(h, kind):
+        h = np.ascontiguousarray(h, dtype=np.uint16)
+        if kind == 0:
+            return h.view(np.float16).astype(np.float32)
+        return (h.astype(np.uint32) << 16).view(np.float32)
+
+    def mp_sgd_update(self, w16, w32, g16, kind, lr, wd=0.0, rescale=1.0, clip=None, nthreads=1):
+        self.lib.kvo_mp_sgd_update(w32.size, _ptr(w16), _ptr(w32), _ptr(g16), kind,
+                                   self._clip(clip), lr, wd, rescale, nthreads)
+        return w16
+
+    def multi_mp_sgd_update(self, w16, w32, g16, mom, kind, lr, momentum=0.0, wd=0.0, rescale=1.0,
+                            clip=None, nthreads=1):
+        self.lib.kvo_multi_mp_sgd_update(w32.size, _ptr(w16),
+                                         _ptr(mom) if mom is not None else None, _ptr(w32),
+                                         _ptr(g16), kind, self._clip(clip), momentum, lr, wd,
+                                         rescale, nthreads)
+        return w16
+
+    # ---- row_sparse -------------------------------------------------------------------
+    def unique(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int64).ravel().copy()
+        n = self.lib.kvo_unique_i64(_ptr(ids), ids.size)
+        return ids[:n]
+
+    def rsp_reduce(self, idxs, vals):
+        """idxs: list of int64 [nnr_s]; vals: list of fp32 [nnr_s, row_len] -> (idx, val)."""
+        idxs = [np.ascontiguousarray(i, dtype=np.int64) for i in idxs]
+        vals = [_f32(v).reshape(len(i), -1) for i, v in zip(idxs, vals)]
+        row_len = vals[0].shape[1]
+        total = sum(len(i) for i in idxs)
+        out_idx = np.empty(max(total, 1), dtype=np.int64)
+        out_val = np.empty((max(total, 1), row_len), dtype=np.float32)
+        nrows = (ctypes.c_size_t * len(idxs))(*[len(i) for i in idxs])
+        nnr = self.lib.kvo_rsp_reduce(len(idxs), _ptr_array(idxs), nrows, _ptr_array(vals),
+                                      row_len, _ptr(out_idx), _ptr(out_val))
+        return out_idx[:nnr].copy(), out_val[:nnr].copy()
+
+    def sparse_retain(self, src_idx, src_val, ids, src_dense_rows=False):
+        src_idx = np.ascontiguousarray(src_idx, dtype=np.int64)
+        src_val = _f32(src_val)
+        src_val = src_val.reshape(src_val.shape[0], -1)
+        ids = np.ascontiguousarray(ids, dtype=np.int64).ravel()
+        out_idx = np.empty(ids.size, dtype=np.int64)
+        out_val = np.empty((ids.size, src_val.shape[1]), dtype=np.float32)
+        self.lib.kvo_sparse_retain(_ptr(src_idx), src_idx.size, _ptr(src_val), src_val.shape[1],
+                                   _ptr(ids), ids.size, int(bool(src_dense_rows)), _ptr(out_idx),
+                                   _ptr(out_val))
+        return out_idx, out_val
+
+    def sgd_rsp_update(self, w, gidx, gval, lr, wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        self.lib.kvo_sgd_rsp_update(gidx.size, w.shape[1], _ptr(w), _ptr(gidx), _ptr(gval),
+                                    self._clip(clip), lr, wd, rescale)
+        return w
+
+    def sgd_mom_rsp_update(self, w, mom, gidx, gval, lr, momentum, wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        self.lib.kvo_sgd_mom_rsp_update(gidx.size, w.shape[1], _ptr(w), _ptr(mom), _ptr(gidx),
+                                        _ptr(gval), self._clip(clip), momentum, lr, wd, rescale)
+        return w
+
+    def adam_rsp_update(self, w, mean, var, gidx, gval, lr, beta1=0.9, beta2=0.999, eps=1e-8,
+                        wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        self.lib.kvo_adam_rsp_update(gidx.size, w.shape[1], _ptr(w), _ptr(mean), _ptr(var),
+                                     _ptr(gidx), _ptr(gval), self._clip(clip), beta1, beta2, lr,
+                                     wd, eps, rescale)
+        return w
+
+    # ---- 2-bit ------------------------------------------------------------------------
+    def quantize_2bit(self, grad, residual, threshold):
+        grad = _f32(grad).ravel()
+        comp = np.zeros((grad.size + 15) // 16, dtype=np.uint32)
+        self.lib.kvo_quantize_2bit(grad.size, _ptr(comp), _ptr(grad), _ptr(residual), threshold)
+        return comp
+
+    def dequantize_2bit(self, comp, n, threshold):
+        out = np.empty(n, dtype=np.float32)
+        self.lib.kvo_dequantize_2bit(n, _ptr(out), _ptr(comp), threshold)
+        return out
+
+
+class Ref(object):
+    """numpy API over oracle/_ref/libmxref.so (the reference's own code, see ref_harness.cc)."""
+
+    def __init__(self, path):
+        self.lib = ctypes.CDLL(path)
+        L = self.lib
+        L.mxref_reduce_sum_cpu.argtypes = [_P, _I, _SZ]
+        L.mxref_reduce_sum_cpu_impl.argtypes = [_P, _I, _SZ, _I, _SZ]
+        L.mxref_sgd_update.argtypes = [_SZ, _P, _P, _P, _F, _F, _F, _F, _I]
+        L.mxref_sgd_mom_update.argtypes = [_SZ, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I]
+        L.mxref_mp_sgd_update_f16.argtypes = [_SZ, _P, _P, _P, _P, _F, _F, _F, _F, _I]
+        L.mxref_mp_sgd_mom_update_f16.argtypes = [_SZ, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I]
+        L.mxref_multi_sgd_update.argtypes = [_I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _I]
+        L.mxref_multi_mp_sgd_update_f16.argtypes = [_I, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F,
+                                                    _I]
+        L.mxref_adam_update.argtypes = [_SZ, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F, _I]
+        L.mxref_sgd_rsp_update.argtypes = [_SZ, ctypes.c_int64, _P, _P, _P, _P, _F, _F, _F, _F, _I]
+        L.mxref_sgd_mom_rsp_update.argtypes = [_SZ, ctypes.c_int64, _P, _P, _P, _P, _P, _F, _F, _F,
+                                               _F, _F, _I]
+        L.mxref_adam_rsp_update.argtypes = [_SZ, ctypes.c_int64, _P, _P, _P, _P, _P, _P, _F, _F, _F,
+                                            _F, _F, _F, _F, _I]
+        L.mxref_quantize_2bit.argtypes = [_SZ, _P, _P, _P, _F, _F]
+        L.mxref_dequantize_2bit.argtypes = [_SZ, _P, _P, _F, _F]
+
+    @staticmethod
+    def _clip(c):
+        return -1.0 if (c is None or c is False) else float(c)
+
+    def reduce(self, srcs, nthreads=1, bigarray_bound=1000 * 1000):
+        """CommCPU 'local' reduce; the result lands in a copy of srcs[0] (reference sums in place)."""
+        bufs = [_f32(s).ravel().copy() for s in srcs]
+        if nthreads <= 1:
+            self.lib.mxref_reduce_sum_cpu(_ptr_array(bufs), len(bufs), bufs[0].size)
+        else:
+            self.lib.mxref_reduce_sum_cpu_impl(_ptr_array(bufs), len(bufs), bufs[0].size, nthreads,
+                                               bigarray_bound)
+        return bufs[0]
+
+    def reduce_inplace(self, bufs, nthreads, bigarray_bound=1000 * 1000):
+        self.lib.mxref_reduce_sum_cpu_impl(_ptr_array(bufs), len(bufs), bufs[0].size, nthreads,
+                                           bigarray_bound)
+
+    def sgd_update(self, w, g, lr, wd=0.0, rescale=1.0, clip=None, nthreads=1):
+        self.lib.mxref_sgd_update(w.size, _ptr(w), _ptr(w), _ptr(g), self._clip(clip), lr, wd,
+                                  rescale, nthreads)
+        return w
+
+    def sgd_mom_update(self, w, g, mom, lr, momentum, wd=0.0, rescale=1.0, clip=None, nthreads=1):
+        self.lib.mxref_sgd_mom_update(w.size, _ptr(w), _ptr(mom), _ptr(w), _ptr(g),
+                                      self._clip(clip), momentum, lr, wd, rescale, nthreads)
+        return w
+
+    def multi_sgd_update(self, ws, gs, moms, lrs, wds, momentum=0.0, rescale=1.0, clip=None,
+                         nthreads=1):
+        n = len(ws)
+        sizes = (ctypes.c_size_t * n)(*[w.size for w in ws])
+        lrs_c = (ctypes.c_float * n)(*lrs)
+        wds_c = (ctypes.c_float * n)(*wds)
+        self.lib.mxref_multi_sgd_update(n, sizes, _ptr_array(ws), _ptr_array(gs),
+                                        _ptr_array(moms) if moms is not None else None,
+                                        _ptr_array(ws), lrs_c, wds_c, self._clip(clip), rescale,
+                                        momentum, nthreads)
+        return ws
+
+    def multi_mp_sgd_update_f16(self, w16s, w32s, g16s, moms, lrs, wds, momentum=0.0, rescale=1.0,
+                                clip=None, nthreads=1):
+        n = len(w16s)
+        sizes = (ctypes.c_size_t * n)(*[w.size for w in w16s])
+        lrs_c = (ctypes.c_float * n)(*lrs)
+        wds_c = (ctypes.c_float * n)(*wds)
+        self.lib.mxref_multi_mp_sgd_update_f16(n, sizes, _ptr_array(w16s), _ptr_array(g16s),
+                                               _ptr_array(moms) if moms is not None else None,
+                                               _ptr_array(w32s), _ptr_array(w16s), lrs_c, wds_c,
+                                               self._clip(clip), rescale, momentum, nthreads)
+        return w16s
+
+    def mp_sgd_update_f16(self, w16, w32, g16, lr, wd=0.0, rescale=1.0, clip=None, nthreads=1):
+        self.lib.mxref_mp_sgd_update_f16(w16.size, _ptr(w16), _ptr(w16), _ptr(g16), _ptr(w32),
+                                         self._clip(clip), lr, wd, rescale, nthreads)
+        return w16
+
+    def mp_sgd_mom_update_f16(self, w16, w32, g16, mom, lr, momentum, wd=0.0, rescale=1.0,
+                              clip=None, nthreads=1):
+        self.lib.mxref_mp_sgd_mom_update_f16(w16.size, _ptr(w16), _ptr(mom), _ptr(w16), _ptr(g16),
+                                             _ptr(w32), self._clip(clip), momentum, lr, wd,
+                                             rescale, nthreads)
+        return w16
+
+    def adam_update(self, w, g, mean, var, lr, beta1=0.9, beta2=0.999, eps=1e-8, wd=0.0,
+                    rescale=1.0, clip=None, nthreads=1):
+        self.lib.mxref_adam_update(w.size, _ptr(w), _ptr(mean), _ptr(var), _ptr(w), _ptr(g),
+                                   self._clip(clip), rescale, beta1, beta2, lr, wd, eps, nthreads)
+        return w
+
+    def sgd_rsp_update(self, w, gidx, gval, lr, wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        self.lib.mxref_sgd_rsp_update(gidx.size, w.shape[1], _ptr(w), _ptr(w), _ptr(gidx),
+                                      _ptr(gval), self._clip(clip), lr, wd, rescale, 1)
+        return w
+
+    def sgd_mom_rsp_update(self, w, mom, gidx, gval, lr, momentum, wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        self.lib.mxref_sgd_mom_rsp_update(gidx.size, w.shape[1], _ptr(w), _ptr(mom), _ptr(w),
+                                          _ptr(gidx), _ptr(gval), self._clip(clip), momentum, lr,
+                                          wd, rescale, 1)
+        return w
+
+    def adam_rsp_update(self, w, mean, var, gidx, gval, lr, beta1=0.9, beta2=0.999, eps=1e-8,
+                        wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        self.lib.mxref_adam_rsp_update(gidx.size, w.shape[1], _ptr(w), _ptr(mean), _ptr(var),
+                                       _ptr(w), _ptr(gidx), _ptr(gval), self._clip(clip), beta1,
+                                       beta2, lr, wd, eps, rescale, 1)
+        return w
+
+    def quantize_2bit(self, grad, residual, threshold):
+        grad = _f32(grad).ravel()
+        comp = np.zeros((grad.size + 15) // 16, dtype=np.float32)
+        self.lib.mxref_quantize_2bit(grad.size, _ptr(comp), _ptr(grad), _ptr(residual),
+                                     -1 * threshold, threshold)
+        return comp.view(np.uint32)
+
+    def dequantize_2bit(self, comp, n, threshold):
+        out = np.empty(n, dtype=np.float32)
+        comp = np.ascontiguousarray(comp).view(np.float32)
+        self.lib.mxref_dequantize_2bit(n, _ptr(out), _ptr(comp), -1 * threshold, threshold)
+        return out
+
+
+_oracle = None
+_ref = False
+
+
+def get_oracle():
+    global _oracle
+    if _oracle is None:
+        _oracle = Oracle()
+    return _oracle
+
+
+def ref():
+    """The reference harness, or None when oracle/_ref/libmxref.so has not been built."""
+    global _ref
+    if _ref is False:
+        path = os.path.join(_HERE, "_ref", "libmxref.so")
+        _ref = Ref(path) if os.path.exists(path) else None
+    return _ref
+
+
+# ------------------------------------------------------------------------------------------
+# Host orchestration restated in numpy/python (not header-callable in the reference)
+# ------------------------------------------------------------------------------------------
+
+def f32(x):
+    """Python double -> nearest float32 -> python float: the str()/dmlc float-parse hop every
+    hyper-parameter takes between python/mxnet/optimizer/optimizer.py and the C++ op parameters."""
+    return float(np.float32(x))
+
+
+def group_kv_pairs(keys, values):
+    """KVStoreLocal::GroupKVPairs, src/kvstore/kvstore_local.h:377-407: stable-by-key grouping;
+    returns (uniq_keys ascending, grouped values in call order)."""
+    order = sorted(range(len(keys)), key=lambda i: keys[i])  # python sort is stable
+    uniq, grouped = [], []
+    for i in order:
+        if not uniq or keys[i] != uniq[-1]:
+            uniq.append(keys[i])
+            grouped.append([values[i]])
+        else:
+            grouped[-1].append(values[i])
+    return uniq, grouped
+
+
+def adam_lr(lr, beta1, beta2, t):
+    """python/mxnet/optimizer/optimizer.py:1617-1620: bias-corrected step size in python double."""
+    coef1 = 1. - beta1 ** t
+    coef2 = 1. - beta2 ** t
+    return lr * math.sqrt(coef2) / coef1
+
+
+class LocalKVStoreModel(object):
+    """numpy model of kvstore('local') with an optional fused optimizer: the end-to-end checker.
+
+    Follows KVStoreLocal::PushImpl/PullImpl (src/kvstore/kvstore_local.h:208-261): push = reduce the
+    per-device values of a key (CommCPU association, comm.h:357-392, or 'device' left fold), then
+    either run the updater on (merged, stored) or replace the stored value by the merged one; pull =
+    copy of the stored value. The optimizer step follows python/mxnet/optimizer/optimizer.py
+    (SGD._update_impl :603-659 -> multi_sgd[_mom]_update for dense; Adam.update :1610-1629).
+    """
+
+    def __init__(self, order="local"):
+        self.order = order
+        self.store = {}
+        self.opt = None
+        self.state = {}
+        self.count = {}
+        self.o = get_oracle()
+
+    def init(self, key, value):
+        assert key not in self.store, "duplicate init of key %s" % key
+        self.store[key] = _f32(value).copy()
+
+    def set_optimizer(self, kind, lr=0.01, momentum=0.0, wd=0.0, rescale_grad=1.0,
+                      clip_gradient=None, beta1=0.9, beta2=0.999, epsilon=1e-8, lr_mult=None,
+                      wd_mult=None):
+        self.opt = dict(kind=kind, lr=lr, momentum=momentum, wd=wd, rescale=rescale_grad,
+                        clip=clip_gradient, beta1=beta1, beta2=beta2, eps=epsilon,
+                        lr_mult=lr_mult or {}, wd_mult=wd_mult or {})
+
+    def push(self, key, values):
+        values = values if isinstance(values, (list, tuple)) else [values]
+        shape = self.store[key].shape
+        merged = self.o.reduce(values, self.order).reshape(shape)
+        if self.opt is None:
+            self.store[key] = merged
+            return
+        p = self.opt
+        w = self.store[key]
+        self.count[key] = self.count.get(key, 0) + 1
+        lr = p['lr'] * p['lr_mult'].get(key, 1.0)
+        wd = p['wd'] * p['wd_mult'].get(key, 1.0)
+        clip = p['clip'] if p['clip'] else None  # optimizer.py:623-624 passes clip only if truthy
+        if p['kind'] == 'sgd':
+            mom = None
+            if p['momentum'] != 0.0:
+                mom = self.state.setdefault(key, np.zeros_like(w))
+            self.o.multi_sgd_update(w.reshape(-1), merged.reshape(-1),
+                                    mom.reshape(-1) if mom is not None else None, f32(lr),
+                                    f32(p['momentum']) if p['momentum'] > 0 else 0.0, f32(wd),
+                                    f32(p['rescale']), f32(clip) if clip else None)
+        elif p['kind'] == 'adam':
+            m, v = self.state.setdefault(key, (np.zeros_like(w), np.zeros_like(w)))
+            lr_t = adam_lr(lr, p['beta1'], p['beta2'], self.count[key])
+            self.o.adam_update(w.reshape(-1), merged.reshape(-1), m.reshape(-1), v.reshape(-1),
+                               f32(lr_t), f32(p['beta1']), f32(p['beta2']), f32(p['eps']), f32(wd),
+                               f32(p['rescale']), f32(clip) if clip else None)
+        elif p['kind'] == 'test':
+            self.o.test_update(w.reshape(-1), merged.reshape(-1), f32(p['rescale']))
+        else:
+            raise ValueError(p['kind'])
+
+    def pull(self, key):
+        return self.store[key].copy()

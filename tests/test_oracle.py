@@ -1,0 +1,233 @@
+"""Pins the CPU oracle (oracle/kvoracle.c) -- CPU-only tests.
+
+Three anchors, as SURVEY.md 8(c) lists them:
+  1. tests/golden/*.npz -- outputs of the reference's own headers (oracle/gen_golden.py), committed;
+  2. oracle/_ref/libmxref.so -- the same reference code, live, when it has been built here;
+  3. the reference's known-answer values and the exact small-integer identities its
+     unit tests use (tests/python/unittest/test_kvstore.py:49-51, tests/python/gpu/test_device.py).
+All comparisons are bit-exact.
+"""
+import numpy as np
+import pytest
+
+import kvoracle as K
+
+
+def eq(a, b):
+    return np.array_equal(np.asarray(a).view(np.uint8), np.asarray(b).view(np.uint8))
+
+
+HP = dict(lr=0.1, wd=1e-4, rescale=1.0 / 256, momentum=0.9)
+CLIPS = (("noclip", None), ("clip", 0.002))
+
+
+# ---------------------------------------------------------------- golden fixtures (reference outputs)
+def test_reduce_local_golden(oracle, golden):
+    g = golden("reduce_local")
+    for n in range(1, 10):
+        srcs = list(g["n%d_src" % n])
+        assert eq(oracle.reduce(srcs, "local"), g["n%d_out" % n]), n
+        assert eq(oracle.reduce(srcs, "local", nthreads=3), g["n%d_out" % n]), n
+        if n <= 2:  # 'device' (left fold) and 'local' agree bit-for-bit only up to 2 sources
+            assert eq(oracle.reduce(srcs, "device"), g["n%d_out" % n])
+
+
+@pytest.mark.parametrize("tag,clip", CLIPS)
+def test_optimizers_golden(oracle, golden, tag, clip):
+    g = golden("optimizers")
+    w, gr = g["sgd_%s_in" % tag]
+    assert eq(oracle.sgd_update(w.copy(), gr, HP["lr"], HP["wd"], HP["rescale"], clip),
+              g["sgd_%s_out" % tag])
+    w, gr, m = g["sgdmom_%s_in" % tag]
+    w2, m2 = w.copy(), m.copy()
+    oracle.sgd_mom_update(w2, gr, m2, HP["lr"], HP["momentum"], HP["wd"], HP["rescale"], clip)
+    assert eq(np.stack([w2, m2]), g["sgdmom_%s_out" % tag])
+    w2, m2 = w.copy(), m.copy()
+    oracle.multi_sgd_update(w2, gr, m2, HP["lr"], HP["momentum"], HP["wd"], HP["rescale"], clip)
+    assert eq(np.stack([w2, m2]), g["multisgdmom_%s_out" % tag])
+    w2 = w.copy()
+    oracle.multi_sgd_update(w2, gr, None, HP["lr"], 0.0, HP["wd"], HP["rescale"], clip)
+    assert eq(w2, g["multisgd_%s_out" % tag])
+
+
+@pytest.mark.parametrize("tag,clip", (("noclip", None), ("clip", 0.5)))
+def test_adam_golden(oracle, golden, tag, clip):
+    g = golden("optimizers")
+    w, gr, m, v = [x.copy() for x in g["adam_%s_in" % tag]]
+    for t in range(1, 6):
+        lr_t = K.f32(K.adam_lr(1e-3, 0.9, 0.999, t))
+        oracle.adam_update(w, gr, m, v, lr_t, K.f32(0.9), K.f32(0.999), K.f32(1e-8), K.f32(0.01),
+                           1.0, clip)
+        assert eq(np.stack([w, m, v]), g["adam_%s_out" % tag][t - 1]), t
+
+
+@pytest.mark.parametrize("tag,clip", CLIPS)
+def test_mixed_precision_golden(oracle, golden, tag, clip):
+    g = golden("optimizers")
+    w16, g16 = g["mp_%s_in16" % tag]
+    w32, m = g["mp_%s_in32" % tag]
+    a16, a32, am = w16.copy(), w32.copy(), m.copy()
+    oracle.multi_mp_sgd_update(a16, a32, g16, am, 0, HP["lr"], HP["momentum"], HP["wd"],
+                               HP["rescale"], clip)
+    assert eq(a16, g["mpmom_%s_out16" % tag])
+    assert eq(np.stack([a32, am]), g["mpmom_%s_out32" % tag])
+    a16, a32 = w16.copy(), w32.copy()
+    oracle.mp_sgd_update(a16, a32, g16, 0, HP["lr"], HP["wd"], HP["rescale"], clip)
+    assert eq(a16, g["mpsgd_%s_out16" % tag])
+    assert eq(a32, g["mpsgd_%s_out32" % tag])
+
+
+@pytest.mark.parametrize("tag,clip", (("noclip", None), ("clip", 0.3)))
+def test_rowsparse_updates_golden(oracle, golden, tag, clip):
+    g = golden("rowsparse_updates")
+    w, m, v = g["rsp_%s_in" % tag]
+    gi, gv = g["rsp_%s_gidx" % tag], g["rsp_%s_gval" % tag]
+    assert eq(oracle.sgd_rsp_update(w.copy(), gi, gv, 0.1, 1e-3, 0.5, clip),
+              g["rsp_sgd_%s_out" % tag])
+    w2, m2 = w.copy(), m.copy()
+    oracle.sgd_mom_rsp_update(w2, m2, gi, gv, 0.1, 0.9, 1e-3, 0.5, clip)
+    assert eq(np.stack([w2, m2]), g["rsp_sgdmom_%s_out" % tag])
+    w2, m2, v2 = w.copy(), m.copy(), v.copy()
+    oracle.adam_rsp_update(w2, m2, v2, gi, gv, 1e-3, wd=0.01, clip=clip)
+    assert eq(np.stack([w2, m2, v2]), g["rsp_adam_%s_out" % tag])
+
+
+def test_twobit_golden(oracle, golden):
+    g = golden("twobit")
+    res = np.zeros_like(g["grad"])
+    c1 = oracle.quantize_2bit(g["grad"], res, 0.5)
+    assert eq(c1, g["comp1"]) and eq(res, g["res1"])
+    c2 = oracle.quantize_2bit(g["grad"], res, 0.5)
+    assert eq(c2, g["comp2"]) and eq(res, g["res2"])
+    assert eq(oracle.dequantize_2bit(c1, g["grad"].size, 0.5), g["deq1"])
+
+
+# ---------------------------------------------------------------- known answers
+def test_known_answers(oracle):
+    w = np.array([1, 2, 3, 4], np.float32)
+    g = np.array([.1, .2, .3, .4], np.float32)
+    o = oracle.sgd_update(np.array([1, 4], np.float32), np.array([.1, .4], np.float32),
+                          K.f32(.1), K.f32(.01))
+    assert o[0] == np.float32(0.989000022) and o[1] == np.float32(3.95600009)
+    m, v = np.zeros(4, np.float32), np.zeros(4, np.float32)
+    o = oracle.adam_update(w.copy(), g, m, v, K.f32(1e-3), wd=K.f32(.01))
+    assert o[0] == np.float32(0.996837735) and o[3] == np.float32(3.99683762)
+    mom = np.full(4, .5, np.float32)
+    o = oracle.multi_sgd_update(w.copy(), g, mom, K.f32(.1), K.f32(.9), K.f32(1e-4),
+                                K.f32(1 / 256))
+    assert o[0] == np.float32(1.44995093) and o[3] == np.float32(4.44980383)
+    assert mom[0] == np.float32(0.449950904)
+    grad = np.array([(i % 3 - 1) * 0.6 for i in range(16)], np.float32)
+    assert oracle.quantize_2bit(grad, np.zeros(16, np.float32), .5)[0] == 0x8ee3388e
+    # 8 inputs of 0.1*(i+1) through the CommCPU association -> 3.5999999
+    srcs = [np.full(3, np.float32(0.1 * (i + 1)), np.float32) for i in range(8)]
+    assert oracle.reduce(srcs, "local")[0] == np.float32(3.5999999)
+
+
+def test_small_integer_identities(oracle):
+    # tests/python/gpu/test_device.py:38-71: ones over n devices == n, for both associations
+    for n in range(1, 9):
+        for shape in ((10,), (100, 50), (2, 3, 4, 5, 6, 7, 8)):
+            srcs = [np.ones(shape, np.float32) for _ in range(n)]
+            for order in ("local", "device"):
+                assert np.all(oracle.reduce(srcs, order) == n)
+    # tests/python/unittest/test_kvstore.py:227-279: updater `local += recv`, four pushes of
+    # ones over 4 devices -> stored == 1 + 4*4 per push chain
+    m = K.LocalKVStoreModel()
+    m.init(3, np.ones((4, 4), np.float32))
+    m.set_optimizer('test', rescale_grad=1.0)
+    for _ in range(4):
+        m.push(3, [np.ones((4, 4), np.float32)] * 4)
+    assert np.all(m.pull(3) == 17)
+
+
+def test_half_conversions(oracle):
+    allh = np.arange(0x7c00, dtype=np.uint16)  # every finite non-negative fp16
+    f = oracle.from_half(allh, 0)
+    back = np.array([oracle.lib.kvo_float_to_half(float(x), 0) for x in f], dtype=np.uint16)
+    assert eq(back, allh)
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-70000, 70000, 4000), rng.uniform(-1e-4, 1e-4, 4000),
+                        rng.uniform(-1e-7, 1e-7, 2000)]).astype(np.float32)
+    mine = np.array([oracle.lib.kvo_float_to_half(float(t), 0) for t in x], dtype=np.uint16)
+    assert eq(mine, x.astype(np.float16).view(np.uint16))
+    # bf16: round-to-nearest-even on the upper 16 bits
+    import torch
+    tb = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    mine = np.array([oracle.lib.kvo_float_to_half(float(t), 1) for t in x], dtype=np.uint16)
+    assert eq(mine, tb)
+    assert eq(oracle.to_half(x, 1), tb) and eq(oracle.to_half(x, 0), x.astype(np.float16).view(np.uint16))
+
+
+def test_rowsparse_reduce_unique_retain(oracle):
+    rng = np.random.default_rng(2)
+    R, L = 64, 5
+    idxs, vals = [], []
+    for s in range(4):
+        i = np.sort(rng.choice(R, 20, replace=False)).astype(np.int64)
+        idxs.append(i)
+        vals.append(rng.integers(-3, 4, (20, L)).astype(np.float32))
+    oi, ov = oracle.rsp_reduce(idxs, vals)
+    dense = np.zeros((R, L), np.float32)
+    for i, v in zip(idxs, vals):
+        dense[i] += v
+    assert np.array_equal(oi, np.unique(np.concatenate(idxs)))
+    assert np.array_equal(ov, dense[oi])  # small integers: exact (test_kvstore.py:178-227)
+    # unique: unsorted + duplicates -> ascending unique (kvstore_utils.cc:32-44)
+    ids = rng.integers(0, R, 100)
+    assert np.array_equal(oracle.unique(ids), np.unique(ids))
+    assert oracle.unique(np.array([], np.int64)).size == 0
+    # retain: every requested id is emitted; missing rows are zero (sparse_retain-inl.h:121-150)
+    req = np.unique(rng.integers(0, R, 30)).astype(np.int64)
+    ri, rv = oracle.sparse_retain(oi, ov, req)
+    assert np.array_equal(ri, req)
+    present = np.isin(req, oi)
+    assert np.array_equal(rv[present], dense[req[present]])
+    assert np.all(rv[~present] == 0)
+    # dense-source fast path: idx used as the row position
+    full_i = np.arange(R, dtype=np.int64)
+    ri, rv = oracle.sparse_retain(full_i, dense, req, src_dense_rows=True)
+    assert np.array_equal(rv, dense[req])
+
+
+# ---------------------------------------------------------------- live reference (when built here)
+needs_ref = pytest.mark.skipif(K.ref() is None, reason="oracle/_ref/libmxref.so not built")
+
+
+@needs_ref
+def test_reduce_vs_reference_live(oracle):
+    r = K.ref()
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 4, 5, 6, 7, 8, 9, 13, 16):
+        srcs = [rng.uniform(-1, 1, 3001).astype(np.float32) for _ in range(n)]
+        assert eq(oracle.reduce(srcs, "local"), r.reduce(srcs)), n
+    # above MXNET_KVSTORE_BIGARRAY_BOUND: 4 threads x 4096-element tasks (comm.h:394-410)
+    srcs = [rng.uniform(-1, 1, 1200007).astype(np.float32) for _ in range(8)]
+    assert eq(oracle.reduce(srcs, "local", nthreads=4), r.reduce(srcs, nthreads=4))
+
+
+@needs_ref
+@pytest.mark.parametrize("clip", (None, 0.5, 0.002))
+def test_optimizers_vs_reference_live(oracle, clip):
+    r = K.ref()
+    rng = np.random.default_rng(4)
+    n = 10007
+
+    def mk():
+        return [rng.uniform(-1, 1, n).astype(np.float32) for _ in range(4)]
+    w, g, m, v = mk()
+    assert eq(oracle.sgd_update(w.copy(), g, .1, 1e-4, 1 / 256, clip),
+              r.sgd_update(w.copy(), g, .1, 1e-4, 1 / 256, clip))
+    a, b = [w.copy(), m.copy()], [w.copy(), m.copy()]
+    oracle.sgd_mom_update(a[0], g, a[1], .1, .9, 1e-4, 1 / 256, clip)
+    r.sgd_mom_update(b[0], g, b[1], .1, .9, 1e-4, 1 / 256, clip)
+    assert eq(a[0], b[0]) and eq(a[1], b[1])
+    a, b = [w.copy(), m.copy()], [w.copy(), m.copy()]
+    oracle.multi_sgd_update(a[0], g, a[1], .1, .9, 1e-4, 1 / 256, clip)
+    r.multi_sgd_update([b[0]], [g], [b[1]], [.1], [1e-4], .9, 1 / 256, clip)
+    assert eq(a[0], b[0]) and eq(a[1], b[1])
+    v = np.abs(v)
+    a, b = [w.copy(), m.copy(), v.copy()], [w.copy(), m.copy(), v.copy()]
+    oracle.adam_update(a[0], g, a[1], a[2], 1e-3, wd=.01, clip=clip)
+    r.adam_update(b[0], g, b[1], b[2], 1e-3, wd=.01, clip=clip)
+    assert all(eq(x, y) for x, y in zip(a, b))
