@@ -1,0 +1,118 @@
+// engine.h -- the stream/event scheduler that stands in for MXNet's dependency engine on this path.
+//
+// Reference contract (include/mxnet/engine.h:95-112,204-275; src/engine/threaded_engine_perdevice.cc):
+// every operation declares the arrays it reads and the arrays it mutates; the engine guarantees
+// read-after-write / write-after-read / write-after-write order per array, runs independent work
+// concurrently, and lets the caller block with WaitForVar / WaitForAll. The reference realises that
+// with worker threads that each own one CUDA stream and `cudaStreamSynchronize` after every op.
+//
+// B200 design: no worker threads and no per-op host synchronisation. Each GPU has ONE in-order
+// stream (the library's own, or a caller-provided one -- B200KVEngineSetStream -- so KVStore work
+// is ordered with the framework that produced the gradients). An array carries the tags
+// (device, sequence-number) of its last writer and last readers; same-device order is stream
+// order, cross-device order is a cudaStreamWaitEvent on an event recorded lazily -- only when some
+// other stream (or the host) actually has to wait. Host waits are cudaEventSynchronize.
+#pragma once
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.h"
+
+namespace b200kv {
+
+struct Tag {
+  int dev = -1;      // -1: no pending device work
+  uint64_t seq = 0;  // position in that device's issue order
+};
+
+// Per-array dependency record (the reference's engine::Var).
+struct Var {
+  Tag writer;
+  uint64_t reader_seq[kMaxDevices] = {0};  // last read issued on each device
+  bool has_readers = false;
+};
+
+class Engine {
+ public:
+  static Engine* Get();
+
+  int NumDevices();
+  cudaStream_t Stream(int dev);
+  void SetStream(int dev, cudaStream_t s);  // nullptr restores the library-owned stream
+
+  // ---- dependency protocol: call BeginRead/BeginWrite before enqueueing an op on `dev`, then
+  // Issue(dev) once the op is enqueued and Mark* the arrays with the returned sequence number.
+  void BeginRead(int dev, const Var& v);   // stream[dev] waits for v's writer
+  void BeginWrite(int dev, const Var& v);  // ... and for every reader
+  uint64_t Issue(int dev);
+  void MarkRead(int dev, uint64_t seq, Var* v);
+  void MarkWrite(int dev, uint64_t seq, Var* v);
+
+  void StreamWait(int dev, Tag t);  // stream[dev] waits for device work `t`
+  void HostWait(Tag t);             // calling thread waits for device work `t`
+  void WaitToRead(const Var& v);
+  void WaitToWrite(const Var& v);
+  void WaitAll();
+  // Full barrier among the streams of `devs`: everything issued so far on any of them completes
+  // before anything issued afterwards on any of them starts (2N event ops, not N^2).
+  void JoinStreams(const std::vector<int>& devs);
+
+  // ---- memory (pooled: blocks are cached per device and size class, never returned to the driver
+  // before shutdown; the reference's GPUPooledStorageManager plays the same role)
+  void* Alloc(int dev, size_t bytes);
+  void Free(int dev, void* p, size_t bytes);
+  void* AllocPinned(size_t bytes);
+  void FreePinned(void* p, size_t bytes);
+  size_t BytesAllocated(int dev);
+
+  // src/kvstore/comm.h:715-757 (EnableP2P): returns the number of ordered pairs enabled
+  int EnablePeerAccess(const std::vector<int>& devs);
+  bool PeerEnabled(int a, int b);
+
+  std::recursive_mutex& mutex() { return mu_; }
+  void Shutdown();
+
+  // launch accounting (bench.py's gpu_launches, tests)
+  void CountLaunch(const char* name, uint64_t algorithmic_bytes);
+  uint64_t launch_count = 0;
+  const char* last_kernel = "";
+  uint64_t last_kernel_bytes = 0;
+
+ private:
+  Engine();
+  void Init();
+  cudaEvent_t RecordLatest(int dev);
+  static size_t RoundSize(size_t bytes);
+
+  struct Dev {
+    cudaStream_t own = nullptr, cur = nullptr;
+    std::vector<cudaEvent_t> ring;
+    size_t ring_pos = 0;
+    cudaEvent_t latest = nullptr;
+    uint64_t issued = 0, recorded = 0, completed = 0;
+    uint64_t waited[kMaxDevices] = {0};  // waited[e]: this stream already waits for e's seq <= value
+    std::multimap<size_t, void*> pool;
+    size_t bytes = 0;
+  };
+  std::vector<Dev> devs_;
+  std::multimap<size_t, void*> pinned_pool_;
+  bool peer_[kMaxDevices][kMaxDevices] = {{false}};
+  bool inited_ = false;
+  std::recursive_mutex mu_;
+};
+
+// RAII: switch the calling thread's current CUDA device.
+struct DeviceGuard {
+  explicit DeviceGuard(int dev) {
+    KV_CUDA(cudaGetDevice(&prev_));
+    if (prev_ != dev) KV_CUDA(cudaSetDevice(dev));
+    dev_ = dev;
+  }
+  ~DeviceGuard() {
+    if (prev_ != dev_) cudaSetDevice(prev_);
+  }
+  int prev_ = 0, dev_ = 0;
+};
+
+}  // namespace b200kv

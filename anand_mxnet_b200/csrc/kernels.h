@@ -1,0 +1,126 @@
+// kernels.h -- host-side launch interface of the hand-written sm_100a kernels (plain structs, no
+// CUDA types beyond cudaStream_t) so the runtime (.cc) and the kernels (.cu) compile separately.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace b200kv {
+
+constexpr int kMaxSrc = 16;  // values of one key per push (devices / ranks)
+constexpr int kMaxDst = 16;  // outs of one key per pull
+constexpr int kChunkElems = 4096;   // work item: <= 4096 consecutive elements of one key
+constexpr int kBlockElems = 32768;  // ownership stripe in the store-global element space
+constexpr int kKeyAlignElems = 128; // every key starts on a 128-element boundary of that space
+
+// What the update step computes from (w, merged gradient, state). Expression trees are the
+// reference's, see dense_kernels.cu.
+enum OptKind : int {
+  kOptAssign = 0,     // stored = merged            (push without updater, kvstore_local.h:237-243)
+  kOptSGD = 1,        // multi_sgd[_mom]_update     (optimizer_op-inl.h:225-258)
+  kOptSGDSingle = 2,  // sgd_update / mp_sgd_update (optimizer_op-inl.h:388-397, 661-674)
+  kOptAdam = 3,       // adam_update                (optimizer_op-inl.h:1302-1312)
+  kOptTest = 4,       // mx.optimizer.Test          (optimizer.py:2044-2046)
+  kOptPullOnly = 5,   // no gradient: broadcast the stored value
+};
+
+enum SumOrder : int {
+  kOrderDevice = 0,  // left fold             (ndarray_function-inl.h:402-431, CommDevice)
+  kOrderLocal = 1,   // g0 + groups of four   (comm.h:357-392, CommCPU)
+};
+
+// One key of a fused launch, as seen by ONE device. 16-byte aligned so it can be fetched as uint4.
+struct alignas(16) KeyDesc {
+  const void* src[kMaxSrc];  // gradient of every source (local or peer-mapped), dtype = key dtype
+  void* out[kMaxDst];        // pull targets (local or peer-mapped), dtype = key dtype
+  void* w;                   // stored value on this device (key dtype)
+  float* w32;                // fp32 master weights (16-bit keys under multi_precision) or null
+  float* s1;                 // momentum / Adam mean (fp32) or null
+  float* s2;                 // Adam var (fp32) or null
+  float lr_unused;           // per-key (lr, wd) travel in DenseLaunch::hyper so a plan's tables
+  float wd_unused;           // stay constant across steps
+  int32_t n_src;
+  int32_t n_out;
+  uint32_t vec_ok;           // all pointers 16-byte aligned -> vector path
+  uint32_t pad_[3];
+};
+
+struct alignas(16) ChunkDesc {
+  uint32_t key;  // index into the KeyDesc table
+  uint32_t off;  // first element (multiple of kKeyAlignElems unless the key is unaligned)
+  uint32_t len;  // 1..kChunkElems
+  uint32_t pad_;
+};
+
+struct DenseLaunch {
+  const KeyDesc* keys = nullptr;      // device memory
+  const ChunkDesc* chunks = nullptr;  // device memory
+  const float* hyper = nullptr;       // device memory: (lr, wd) float pairs, one per key
+  int n_chunks = 0;
+  int max_src = 0;     // max n_src over the keys (selects the unroll variant)
+  int dtype = 0;       // key dtype: kFloat32 / kFloat16 / kBfloat16
+  int opt = kOptAssign;
+  int order = kOrderDevice;
+  float momentum = 0.f, rescale = 1.f, clip = -1.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
+  // cross-process launches (one rank per GPU): signal pads for the in-kernel start/end barriers
+  uint32_t* const* signal_pads = nullptr;  // device array [world] of peer-mapped pads, or null
+  int rank = 0, world = 1;
+  uint32_t epoch = 0;
+};
+
+// Fused reduce (+scale/clip +optimizer step) (+broadcast) over a list of chunks, one CTA per chunk.
+void LaunchDenseFused(const DenseLaunch& p, cudaStream_t stream);
+
+// ---- small elementwise helpers for the imperative-op surface (updaters written in Python) ----
+enum EwOp : int { kEwCopy = 0, kEwAdd, kEwSub, kEwMul, kEwAddScalar, kEwMulScalar, kEwFill };
+void LaunchElementwise(int op, int dtype, void* out, const void* a, const void* b, float scalar,
+                       size_t n, cudaStream_t stream);
+void LaunchCast(void* out, int out_dtype, const void* in, int in_dtype, size_t n, cudaStream_t stream);
+
+// ---- row_sparse (rowsparse_kernels.cu) ----
+// lazy row updates over the rows listed in a row_sparse gradient (optimizer_op-inl.h:426-450,
+// 776-801, 1383-1408); opt is kOptSGDSingle (sgd_update), kOptSGD (sgd_mom_update), kOptAdam
+struct RspUpdateLaunch {
+  float* w = nullptr; float* s1 = nullptr; float* s2 = nullptr;
+  const int64_t* gidx = nullptr; const float* gval = nullptr;
+  int64_t nrows = 0, row_len = 0;
+  int opt = kOptSGDSingle;
+  float lr = 0.f, wd = 0.f, momentum = 0.f, rescale = 1.f, clip = -1.f, beta1 = 0.9f,
+        beta2 = 0.999f, eps = 1e-8f;
+};
+void LaunchRspUpdate(const RspUpdateLaunch& p, cudaStream_t stream);
+
+// union of row ids + in-order accumulation (ndarray_function.cc:59-175 semantics).
+// Phase 1 (device): sorted unique union of all source ids -> out_idx, count -> *d_nnr.
+size_t RspUnionWorkspaceBytes(int64_t total_ids);
+void LaunchRspUnion(const int64_t* const* d_src_idx, const int64_t* h_src_nrows, int nsrc,
+                    int64_t total_ids, int64_t* out_idx, int64_t* d_nnr, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream);
+// Phase 2: out_val[r] = 0.0f + sum over sources in list order of the rows whose id == out_idx[r]
+struct RspSumLaunch {
+  const int64_t* const* src_idx = nullptr;  // device array [nsrc] of device pointers
+  const float* const* src_val = nullptr;    // device array [nsrc]
+  const int64_t* src_nrows = nullptr;       // device array [nsrc]
+  int nsrc = 0;
+  const int64_t* out_idx = nullptr; float* out_val = nullptr;
+  int64_t nnr = 0, row_len = 0;
+};
+void LaunchRspSum(const RspSumLaunch& p, cudaStream_t stream);
+// sort + unique of int64 ids (kvstore_utils.cu:43-97 semantics); count -> *d_count
+size_t UniqueWorkspaceBytes(int64_t n);
+void LaunchUnique(const int64_t* ids, int64_t n, int64_t* out, int64_t* d_count, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream);
+// sparse_retain (sparse_retain-inl.h:121-150,262-323): out_idx = ids verbatim, rows gathered
+struct RetainLaunch {
+  const int64_t* src_idx = nullptr; const float* src_val = nullptr; int64_t src_nnr = 0;
+  int src_dense_rows = 0;  // the source holds every row: id is the row position
+  const int64_t* ids = nullptr; int64_t nids = 0; int64_t row_len = 0;
+  int64_t* out_idx = nullptr; float* out_val = nullptr;
+};
+void LaunchRetain(const RetainLaunch& p, cudaStream_t stream);
+
+// ---- TMA bulk-copy packing of many small arrays into one fusion buffer (pack_kernels.cu) ----
+struct PackItem { const void* src; void* dst; uint64_t bytes; };
+void LaunchPackBulk(const PackItem* d_items, int n_items, uint64_t max_bytes, cudaStream_t stream);
+
+}  // namespace b200kv

@@ -1,0 +1,172 @@
+// kvstore.h -- the store behind MXKVStore*: key table, value grouping, placement, the fused
+// optimizer's host state and the launch plans of the dense path.
+//
+// Reference roles covered (and replaced): KVStoreLocal (src/kvstore/kvstore_local.h:69-490),
+// CommCPU / CommDevice (src/kvstore/comm.h:103-797), the Python Updater + Optimizer bookkeeping
+// for SGD / Adam (python/mxnet/optimizer/optimizer.py:104-140,400-509,603-659,1610-1629,2079-2128).
+//
+// Placement (B200 design, replaces CommDevice::InitMergeBuffer's per-key owner GPU): every key
+// gets an offset in a store-global element space (aligned to 128 elements); that space is cut into
+// stripes of 32768 elements owned round-robin by the participating GPUs. Each GPU reduces, updates
+// and broadcasts the stripes it owns (reduce-scatter + update + all-gather in ONE kernel per GPU,
+// peers' gradients read and peers' weights written through NVLink-mapped pointers), and keeps the
+// optimizer state of exactly those stripes. With one GPU this degenerates to one fused kernel.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+#include "ndarray.h"
+
+namespace b200kv {
+
+typedef void (*UpdaterFn)(int key, void* recv, void* local, void* handle);
+typedef void (*StrUpdaterFn)(const char* key, void* recv, void* local, void* handle);
+
+struct OptConfig {
+  bool enabled = false;
+  int kind = kOptAssign;  // kOptSGD / kOptAdam / kOptTest
+  double lr = 0.01, wd = 0.0, momentum = 0.0, rescale = 1.0, clip = 0.0 /* falsy: no clipping */;
+  double beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
+  bool multi_precision = false;
+  bool lazy_update = true;
+  int begin_num_update = 0;
+  int num_update = 0;
+  std::unordered_map<int, double> lr_mult, wd_mult;
+  std::unordered_map<int, int> count;  // Optimizer._index_update_count
+};
+
+struct DevState {
+  NDArray w;    // stored value replica (key dtype)
+  NDArray w32;  // fp32 master (16-bit keys + multi_precision)
+  NDArray s1;   // momentum / Adam mean
+  NDArray s2;   // Adam var
+};
+
+struct KeyEntry {
+  int key = 0;
+  std::vector<int64_t> shape;
+  int dtype = kFloat32;
+  int stype = kDefaultStorage;
+  size_t size = 0;
+  uint64_t goff = 0;    // offset in the store-global element space
+  NDArray host;         // value as initialised, pinned host (kvstore_local.h:202) until first GPU use
+  int home = -1;        // GPU holding the whole authoritative value (-1: still on host)
+  bool striped = false; // authoritative value is striped over the store's device set
+  std::map<int, DevState> dev;
+  NDArray merged;       // reduce target of the updater-callback path (on `home`)
+  NDArray rsp;          // row_sparse stored value (on `home` or host)
+  std::vector<NDArray> stage_src, stage_out;  // device staging of host-resident values / outs
+};
+
+struct DenseOp {
+  KeyEntry* e = nullptr;
+  std::vector<NDArray> srcs;  // empty: pull only
+  std::vector<NDArray> outs;  // empty: push only
+};
+
+// Device-resident descriptor tables of one fused launch, cached by call signature.
+struct Plan {
+  struct PerDev {
+    int dev = -1;
+    void* d_keys = nullptr;
+    void* d_chunks = nullptr;
+    void* d_hyper = nullptr;
+    int n_chunks = 0;
+    std::vector<float> hyper;  // last uploaded (lr, wd) per key
+    size_t bytes_keys = 0, bytes_chunks = 0, bytes_hyper = 0;
+  };
+  std::vector<PerDev> per_dev;
+  int n_keys = 0;
+  int max_src = 0;
+  uint64_t algorithmic_bytes = 0;
+  ~Plan();
+};
+
+class KVStore {
+ public:
+  explicit KVStore(const std::string& type);
+  ~KVStore();
+
+  const std::string& type() const { return type_; }
+  int rank() const { return 0; }
+  int group_size() const { return 1; }
+
+  void Init(const std::vector<int>& keys, const std::vector<NDArray>& values);
+  void InitStr(const std::vector<std::string>& keys, const std::vector<NDArray>& values);
+  void Push(const std::vector<int>& keys, const std::vector<NDArray>& values, int priority);
+  void Pull(const std::vector<int>& keys, const std::vector<NDArray>& outs, int priority,
+            bool ignore_sparse);
+  void PushPull(const std::vector<int>& vkeys, const std::vector<int>& okeys,
+                const std::vector<NDArray>& values, const std::vector<NDArray>& outs, int priority);
+  void PullRowSparse(const std::vector<int>& keys, const std::vector<NDArray>& outs,
+                     const std::vector<NDArray>& row_ids, int priority);
+  std::vector<int> LookupKeys(const std::vector<std::string>& str_keys);
+  void SetKeyTypeInt();
+  void SetKeyTypeStr();
+
+  void SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle);
+  void SetGradientCompression(const std::vector<std::pair<std::string, std::string>>& kw);
+
+  // ---- fused optimizer (B200 extension)
+  void SetOptimizer(const std::string& name,
+                    const std::vector<std::pair<std::string, std::string>>& kw);
+  OptConfig& opt() { return opt_; }
+  NDArray GetOptimizerState(int key, int state_id);
+  void SetOptimizerState(int key, int state_id, const NDArray& v);
+  void Flush() {}
+  std::string DescribePlan(const std::vector<int>& keys, int num_devices);
+
+ private:
+  KeyEntry& Entry(int key);
+  void InitImpl(const std::vector<int>& keys, const std::vector<NDArray>& values);
+  void PushImpl(const std::vector<int>& keys, const std::vector<NDArray>& values,
+                const std::vector<int>* okeys, const std::vector<NDArray>* outs);
+  void PullImpl(const std::vector<int>& keys, const std::vector<NDArray>& outs, bool ignore_sparse);
+
+  // dense machinery
+  void ExecDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stripe = true);
+  void ExecCallbackPush(KeyEntry& e, const std::vector<NDArray>& srcs);
+  void EnsureOnDevice(KeyEntry& e, int dev);            // HOST -> WHOLE(dev)
+  void EnsureStriped(KeyEntry& e);                      // WHOLE -> STRIPED(devset_)
+  void EnsureWhole(KeyEntry& e, int dev);               // STRIPED -> WHOLE(dev)
+  DevState& StateOn(KeyEntry& e, int dev, int opt_kind);
+  int OwnerOf(const KeyEntry& e, uint64_t global_elem) const;
+  void SetDeviceSet(const std::vector<int>& devs);
+  NDArray StageSrc(KeyEntry& e, size_t slot, const NDArray& host_src, int dev);
+  NDArray StageOut(KeyEntry& e, size_t slot, const NDArray& host_out, int dev);
+  void KeyHyper(const KeyEntry& e, int opt_kind, float* lr, float* wd);
+  std::shared_ptr<Plan> GetPlan(const std::vector<DenseOp>& ops, int opt_kind,
+                                const std::vector<int>& devs, bool striped);
+
+  // row_sparse machinery (rowsparse.cc)
+  void PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs);
+  void PullRowSparseOne(KeyEntry& e, const NDArray& out, const NDArray& row_ids);
+  NDArray UniqueRowIds(const NDArray& row_ids, int dev, int64_t* count);
+
+  std::string type_;
+  bool order_local_ = true;   // 'local' => CommCPU association, 'device' => left fold
+  int key_type_ = -1;         // -1 undefined, 0 string, 1 int (kvstore_local.h:60-64)
+  std::unordered_map<int, std::unique_ptr<KeyEntry>> local_;
+  std::unordered_map<std::string, int> str_key_dict_;
+  std::unordered_map<int, std::string> reverse_str_key_dict_;
+  int next_str_key_ = 0;
+  std::unordered_set<int> warnings_printed_;
+  uint64_t next_goff_ = 0;
+  std::vector<int> devset_;   // GPUs the striped values live on, in first-push order
+  UpdaterFn updater_ = nullptr;
+  StrUpdaterFn str_updater_ = nullptr;
+  void* updater_handle_ = nullptr;
+  OptConfig opt_;
+  std::unordered_map<uint64_t, std::shared_ptr<Plan>> plans_;
+  std::string gc_type_ = "none";
+  friend struct PlanBuilder;
+};
+
+}  // namespace b200kv

@@ -1,0 +1,229 @@
+// ndarray.cc -- see ndarray.h.
+#include "ndarray.h"
+
+#include <cstring>
+
+namespace b200kv {
+
+Storage::~Storage() {
+  if (external) {
+    if (deleter) deleter();
+    return;
+  }
+  Engine* e = Engine::Get();
+  try {
+    if (ctx.is_gpu()) {
+      e->Free(ctx.dev_id, dptr, bytes);
+      e->Free(ctx.dev_id, aux, aux_bytes);
+    } else {
+      // a pinned host block may still be the target/source of an in-flight async copy
+      e->WaitToWrite(var);
+      e->FreePinned(dptr, bytes);
+      e->FreePinned(aux, aux_bytes);
+    }
+  } catch (...) {
+  }
+}
+
+static size_t Prod(const std::vector<int64_t>& s, size_t from = 0) {
+  size_t n = 1;
+  for (size_t i = from; i < s.size(); ++i) n *= static_cast<size_t>(s[i]);
+  return n;
+}
+
+static void* AllocOn(Context ctx, size_t bytes) {
+  Engine* e = Engine::Get();
+  if (ctx.is_gpu()) return e->Alloc(ctx.dev_id, bytes);
+  return e->AllocPinned(bytes);  // every host-side array is pinned so H2D/D2H copies are async DMA
+}
+
+NDArray::NDArray(const std::vector<int64_t>& shape, Context ctx, int dtype, bool delay_alloc)
+    : shape_(shape), dtype_(dtype), stype_(kDefaultStorage) {
+  for (auto d : shape) KV_CHECK(d >= 0) << "negative dimension in shape";
+  st_ = std::make_shared<Storage>();
+  st_->ctx = ctx;
+  if (ctx.is_gpu()) {
+    KV_CHECK(ctx.dev_id >= 0 && ctx.dev_id < Engine::Get()->NumDevices())
+        << "invalid gpu id " << ctx.dev_id;
+  }
+  if (!delay_alloc) Alloc();
+}
+
+NDArray NDArray::RowSparse(const std::vector<int64_t>& shape, Context ctx, int dtype) {
+  KV_CHECK(shape.size() >= 1) << "row_sparse needs at least 1 dimension";
+  NDArray a;
+  a.shape_ = shape;
+  a.dtype_ = dtype;
+  a.stype_ = kRowSparseStorage;
+  a.st_ = std::make_shared<Storage>();
+  a.st_->ctx = ctx;
+  a.st_->nnr = 0;
+  return a;
+}
+
+size_t NDArray::Size() const { return Prod(shape_); }
+size_t NDArray::RowLength() const { return Prod(shape_, 1); }
+
+void NDArray::Alloc() const {
+  if (st_->dptr != nullptr || stype_ != kDefaultStorage) return;
+  size_t bytes = ByteSize();
+  if (bytes == 0) return;
+  st_->dptr = AllocOn(st_->ctx, bytes);
+  st_->bytes = bytes;
+}
+
+void* NDArray::data() const {
+  if (aux_view_) return st_->aux;
+  if (stype_ == kDefaultStorage) Alloc();
+  return static_cast<char*>(st_->dptr) + byte_offset_;
+}
+
+void NDArray::CheckAndAllocRows(int64_t nnr) const {
+  KV_CHECK_EQ(stype_, kRowSparseStorage);
+  KV_CHECK(!st_->external) << "cannot re-allocate an external row_sparse array";
+  Engine* e = Engine::Get();
+  size_t need = static_cast<size_t>(nnr) * RowLength() * DTypeSize(dtype_);
+  size_t need_aux = static_cast<size_t>(nnr) * sizeof(int64_t);
+  if (need > st_->bytes) {
+    if (st_->ctx.is_gpu()) e->Free(st_->ctx.dev_id, st_->dptr, st_->bytes);
+    else { e->WaitToWrite(st_->var); e->FreePinned(st_->dptr, st_->bytes); }
+    st_->dptr = AllocOn(st_->ctx, need);
+    st_->bytes = need;
+  }
+  if (need_aux > st_->aux_bytes) {
+    if (st_->ctx.is_gpu()) e->Free(st_->ctx.dev_id, st_->aux, st_->aux_bytes);
+    else { e->WaitToWrite(st_->var); e->FreePinned(st_->aux, st_->aux_bytes); }
+    st_->aux = AllocOn(st_->ctx, need_aux);
+    st_->aux_bytes = need_aux;
+  }
+  st_->nnr = nnr;
+}
+
+NDArray NDArray::DataView() const {
+  NDArray v = *this;
+  v.stype_ = kDefaultStorage;
+  if (stype_ == kRowSparseStorage) {
+    v.shape_ = shape_;
+    v.shape_[0] = st_->nnr;
+  }
+  return v;
+}
+
+NDArray NDArray::AuxView() const {
+  KV_CHECK_EQ(stype_, kRowSparseStorage) << "only row_sparse arrays have aux data";
+  NDArray v = *this;
+  v.stype_ = kDefaultStorage;
+  v.dtype_ = kInt64;
+  v.shape_ = {st_->nnr};
+  v.aux_view_ = true;
+  return v;
+}
+
+NDArray NDArray::Reshaped(const std::vector<int64_t>& shape) const {
+  KV_CHECK_EQ(Prod(shape), Size()) << "reshape size mismatch";
+  NDArray v = *this;
+  v.shape_ = shape;
+  return v;
+}
+
+NDArray NDArray::FromDLPack(DLManagedTensorABI* t, bool transient) {
+  const DLTensorABI& d = t->dl_tensor;
+  NDArray a;
+  a.st_ = std::make_shared<Storage>();
+  KV_CHECK(d.ctx.device_type == 1 || d.ctx.device_type == 2 || d.ctx.device_type == 3)
+      << "unsupported DLPack device type " << d.ctx.device_type;
+  a.st_->ctx = d.ctx.device_type == 2 ? Context::GPU(d.ctx.device_id)
+                                       : Context{d.ctx.device_type == 3 ? kCPUPinned : kCPU, 0};
+  KV_CHECK_EQ(d.dtype.lanes, 1);
+  int dt = -1;
+  if (d.dtype.code == 2 && d.dtype.bits == 32) dt = kFloat32;
+  else if (d.dtype.code == 2 && d.dtype.bits == 64) dt = kFloat64;
+  else if (d.dtype.code == 2 && d.dtype.bits == 16) dt = kFloat16;
+  else if (d.dtype.code == 4 && d.dtype.bits == 16) dt = kBfloat16;
+  else if (d.dtype.code == 0 && d.dtype.bits == 32) dt = kInt32;
+  else if (d.dtype.code == 0 && d.dtype.bits == 64) dt = kInt64;
+  else if (d.dtype.code == 0 && d.dtype.bits == 8) dt = kInt8;
+  else if (d.dtype.code == 1 && d.dtype.bits == 8) dt = kUint8;
+  KV_CHECK(dt >= 0) << "unsupported DLPack dtype code " << int(d.dtype.code) << " bits "
+                    << int(d.dtype.bits);
+  a.dtype_ = dt;
+  a.shape_.assign(d.shape, d.shape + d.ndim);
+  if (d.strides != nullptr) {  // must be compact row-major
+    int64_t expect = 1;
+    for (int i = d.ndim - 1; i >= 0; --i) {
+      KV_CHECK(d.shape[i] <= 1 || d.strides[i] == expect) << "DLPack tensor is not contiguous";
+      expect *= d.shape[i];
+    }
+  }
+  a.st_->dptr = static_cast<char*>(d.data) + d.byte_offset;
+  a.st_->bytes = a.ByteSize();
+  a.st_->external = true;
+  if (!transient) a.st_->deleter = [t]() { if (t->deleter) t->deleter(t); };
+  return a;
+}
+
+NDArray NDArray::Copy(Context ctx) const {
+  NDArray out = stype_ == kRowSparseStorage ? RowSparse(shape_, ctx, dtype_)
+                                            : NDArray(shape_, ctx, dtype_);
+  CopyFromTo(*this, out);
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+void RawCopy(void* dst, Context dctx, Var* dvar, const void* src, Context sctx, Var* svar,
+             size_t bytes) {
+  if (bytes == 0 || dst == src) return;
+  Engine* e = Engine::Get();
+  Var none;
+  if (dvar == nullptr) dvar = &none;
+  if (svar == nullptr) svar = &none;
+  if (!dctx.is_gpu() && !sctx.is_gpu()) {
+    e->WaitToRead(*svar);
+    e->WaitToWrite(*dvar);
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  // the copy runs on the destination GPU's stream (or the source's for device -> host)
+  const int dev = dctx.is_gpu() ? dctx.dev_id : sctx.dev_id;
+  cudaStream_t s = e->Stream(dev);
+  e->BeginRead(dev, *svar);
+  e->BeginWrite(dev, *dvar);
+  DeviceGuard g(dev);
+  if (dctx.is_gpu() && sctx.is_gpu() && dctx.dev_id != sctx.dev_id) {
+    KV_CUDA(cudaMemcpyPeerAsync(dst, dctx.dev_id, src, sctx.dev_id, bytes, s));
+  } else {
+    KV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+  }
+  uint64_t seq = e->Issue(dev);
+  e->MarkRead(dev, seq, svar);
+  e->MarkWrite(dev, seq, dvar);
+}
+
+void CopyFromTo(const NDArray& from, const NDArray& to) {
+  KV_CHECK(!from.is_none() && !to.is_none()) << "copy of an empty NDArray";
+  if (from.SameStorage(to)) return;  // ndarray.cc:1199-1203
+  KV_CHECK_EQ(from.dtype(), to.dtype()) << "CopyFromTo: dtype mismatch";
+  KV_CHECK_EQ(from.stype(), to.stype())
+      << "CopyFromTo: storage type conversion is not on the KVStore path";
+  if (from.stype() == kDefaultStorage) {
+    KV_CHECK_EQ(from.Size(), to.Size()) << "CopyFromTo: operands shape mismatch";
+    if (from.Size() == 0) return;
+    RawCopy(to.data(), to.ctx(), to.var(), from.data(), from.ctx(), from.var(), from.ByteSize());
+    return;
+  }
+  // row_sparse (CopyFromToRspImpl, ndarray.cc:1076-1093)
+  KV_CHECK(from.shape() == to.shape()) << "CopyFromTo: row_sparse shape mismatch";
+  if (!from.storage_initialized()) {
+    Engine::Get()->WaitToWrite(*to.var());
+    to.SetNnr(0);
+    return;
+  }
+  const int64_t nnr = from.nnr();
+  to.CheckAndAllocRows(nnr);
+  RawCopy(to.data(), to.ctx(), to.var(), from.data(), from.ctx(), from.var(),
+          static_cast<size_t>(nnr) * from.RowLength() * DTypeSize(from.dtype()));
+  RawCopy(to.row_ids(), to.ctx(), to.var(), from.row_ids(), from.ctx(), from.var(),
+          static_cast<size_t>(nnr) * sizeof(int64_t));
+}
+
+}  // namespace b200kv

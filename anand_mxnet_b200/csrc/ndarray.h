@@ -1,0 +1,97 @@
+// ndarray.h -- the minimal NDArray the KVStore path needs: a ref-counted device (or pinned-host)
+// buffer + shape/dtype/context/storage-type, with row_sparse support (values + int64 row ids).
+// Mirrors the observable contract of include/mxnet/ndarray.h (Chunk sharing between handle copies,
+// storage_initialized(), aux_shape) without any of its operator/autograd machinery.
+#pragma once
+#include <functional>
+#include <memory>
+#include <vector>
+
+#include "common.h"
+#include "engine.h"
+
+namespace b200kv {
+
+// DLPack ABI (3rdparty/dlpack/include/dlpack/dlpack.h, v0.2 layout -- stable across versions).
+struct DLContextABI { int device_type; int device_id; };
+struct DLDataTypeABI { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensorABI {
+  void* data; DLContextABI ctx; int ndim; DLDataTypeABI dtype; int64_t* shape; int64_t* strides;
+  uint64_t byte_offset;
+};
+struct DLManagedTensorABI {
+  DLTensorABI dl_tensor; void* manager_ctx; void (*deleter)(DLManagedTensorABI*);
+};
+
+// Shared by every NDArray handle that aliases one value (the reference's NDArray::Chunk).
+struct Storage {
+  Context ctx;
+  void* dptr = nullptr;
+  size_t bytes = 0;
+  void* aux = nullptr;  // row_sparse: int64 row ids, ascending & unique
+  size_t aux_bytes = 0;
+  int64_t nnr = 0;      // row_sparse: rows stored; 0 == storage not initialised == all zeros
+  bool external = false;
+  std::function<void()> deleter;
+  Var var;
+  ~Storage();
+};
+
+class NDArray {
+ public:
+  NDArray() {}
+  // dense
+  NDArray(const std::vector<int64_t>& shape, Context ctx, int dtype, bool delay_alloc = false);
+  // row_sparse (always delay-allocated: no rows until CheckAndAllocRows)
+  static NDArray RowSparse(const std::vector<int64_t>& shape, Context ctx, int dtype);
+  static NDArray FromDLPack(DLManagedTensorABI* t, bool transient);
+
+  bool is_none() const { return st_ == nullptr; }
+  const std::vector<int64_t>& shape() const { return shape_; }
+  int dtype() const { return dtype_; }
+  int stype() const { return stype_; }
+  Context ctx() const { return st_ ? st_->ctx : Context(); }
+  int dev() const { return st_->ctx.dev_id; }
+  bool on_gpu() const { return st_ && st_->ctx.is_gpu(); }
+  size_t Size() const;        // product of shape
+  size_t RowLength() const;   // product of shape[1:]
+  size_t ByteSize() const { return Size() * DTypeSize(dtype_); }
+  Var* var() const { return &st_->var; }
+  Storage* storage() const { return st_.get(); }
+  bool SameStorage(const NDArray& o) const { return st_ == o.st_; }
+
+  void Alloc() const;  // dense: allocate if delayed
+  void* data() const;  // dense values / row_sparse value rows
+  int64_t* row_ids() const { return static_cast<int64_t*>(st_->aux); }
+  int64_t nnr() const { return st_->nnr; }
+  bool storage_initialized() const { return stype_ == kDefaultStorage ? true : st_->nnr > 0; }
+  // row_sparse: make room for `nnr` rows (contents undefined) and set aux_shape = nnr
+  void CheckAndAllocRows(int64_t nnr) const;
+  void SetNnr(int64_t nnr) const { st_->nnr = nnr; }
+
+  // views used by MXNDArrayGetDataNDArray / GetAuxNDArray: dense arrays aliasing the blobs
+  NDArray DataView() const;
+  NDArray AuxView() const;
+  NDArray Reshaped(const std::vector<int64_t>& shape) const;
+
+  // Deep copy into a fresh array on ctx (NDArray::Copy, src/ndarray/ndarray.cc:...)
+  NDArray Copy(Context ctx) const;
+
+ private:
+  std::shared_ptr<Storage> st_;
+  std::vector<int64_t> shape_;
+  int dtype_ = kFloat32;
+  int stype_ = kDefaultStorage;
+  size_t byte_offset_ = 0;
+  bool aux_view_ = false;
+};
+
+// CopyFromTo (src/ndarray/ndarray.cc:1198-1296): asynchronous copy as an engine op; self-copy and
+// zero-size copies are skipped; handles every CPU/pinned/GPU/peer combination, dense and row_sparse.
+void CopyFromTo(const NDArray& from, const NDArray& to);
+// Raw async copy of `bytes` between two contexts on the right stream; used by CopyFromTo and the
+// host<->device staging of MXNDArraySyncCopy*.
+void RawCopy(void* dst, Context dctx, Var* dvar, const void* src, Context sctx, Var* svar,
+             size_t bytes);
+
+}  // namespace b200kv

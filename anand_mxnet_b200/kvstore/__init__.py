@@ -1,0 +1,5 @@
+"""mx.kv / mx.kvstore namespace (python/mxnet/kvstore/__init__.py)."""
+from .base import KVStoreBase, TestStore, create
+from .kvstore import KVStore
+
+__all__ = ['KVStoreBase', 'KVStore', 'TestStore', 'create']

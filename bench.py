@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- KVStore push+pull throughput on the ResNet-50 gradient set (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ...]
+
+One "step" = one pass of the hot path over the synthetic gradient set: push the gradients of all
+157 ResNet-50 tensors (25 549 486 fp32 elements, uniform [-1,1)), reduce them, apply SGD with
+momentum ON THE STORE, and pull the new weights back -- one grouped MXKVStorePushPull call, which
+the library turns into ONE fused kernel launch per GPU.
+
+Printed JSON (one line, rank 0):
+  value      GB/s of ALGORITHMIC bytes (24 B/element for SGD-momentum at N=1; the
+             all-reduce bus-bandwidth formula of tools/bandwidth/measure.py:137-138 at N>=2), inputs
+             and outputs resident in HBM, timed with CUDA events on the launching stream
+  e2e        same metric through the same C-ABI call with HOST buffers (pinned CPU-context
+             NDArrays): the H2D copy of the gradients and the D2H copy of the weights are inside
+             the timed region
+  roofline   dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events)
+             against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline   the reference's CPU kvstore('local') arithmetic (oracle/_ref, else the oracle
+             port) on this box's host cores, bounded sample
+`--impl reference` times that CPU path as the whole job (the driver's reference arm).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "kvstore_push_pull_GBps"
+UNIT = "GB/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def resnet50_shapes():
+    """Gradient tensors of the reference's ResNet-50 symbol (example/image-classification/symbols/
+    resnet.py, num_layers=50: units [3,4,6,3], filters [64,256,512,1024,2048], bottleneck, 1000
+    classes): 157 arrays, 25 549 486 elements."""
+    shapes = [(3,), (3,), (64, 3, 7, 7), (64,), (64,)]  # bn_data gamma/beta, conv0, bn0
+    filters = [64, 256, 512, 1024, 2048]
+    units = [3, 4, 6, 3]
+    for stage in range(4):
+        nf = filters[stage + 1]
+        for u in range(units[stage]):
+            cin = filters[stage] if u == 0 else nf
+            q = nf // 4
+            shapes += [(cin,), (cin,), (q, cin, 1, 1), (q,), (q,), (q, q, 3, 3), (q,), (q,),
+                       (nf, q, 1, 1)]
+            if u == 0:
+                shapes.append((nf, cin, 1, 1))  # projection shortcut
+    shapes += [(2048,), (2048,), (1000, 2048), (1000,)]
+    return shapes
+
+
+def bert_base_shapes():
+    """BERT-base parameter set: 199 arrays, 109 482 240 elements."""
+    H, L, FF, V = 768, 12, 3072, 30522
+    shapes = [(V, H), (512, H), (2, H), (H,), (H,)]
+    for _ in range(L):
+        shapes += [(H, H), (H,)] * 4 + [(H,), (H,), (FF, H), (FF,), (H, FF), (H,), (H,), (H,)]
+    shapes += [(H, H), (H,)]
+    return shapes
+
+
+WORKLOADS = {
+    "resnet50_sgd": dict(shapes=resnet50_shapes, opt="sgd", bytes_per_elem=24,
+                         desc="ResNet-50 gradient set, 157 fp32 tensors / 25549486 elements, "
+                              "SGD momentum fused on the store"),
+    "bert_adam": dict(shapes=bert_base_shapes, opt="adam", bytes_per_elem=32,
+                      desc="BERT-base gradient set, 199 fp32 tensors / 109482240 elements, Adam "
+                           "fused on the store"),
+}
+
+SGD_KW = dict(learning_rate=0.1, momentum=0.9, wd=1e-4)
+ADAM_KW = dict(learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, wd=0.01)
+
+
+def algorithmic_bytes(workload, n_gpus):
+    n_elem = sum(int(np.prod(s)) for s in WORKLOADS[workload]["shapes"]())
+    if n_gpus == 1:
+        return n_elem * WORKLOADS[workload]["bytes_per_elem"]
+    # all-reduce bus bandwidth, per GPU (tools/bandwidth/measure.py:137-138)
+    return int(n_elem * 4 * 2 * (n_gpus - 1) / n_gpus)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline
+# ------------------------------------------------------------------------------------------------
+def cpu_kvstore_step_fn(workload, n_src):
+    """One kvstore('local') step on host cores: CommCPU reduce of n_src gradient buffers per key
+    (comm.h:357-410), then the optimizer kernel per key (one updater call per key, OMP inside, as
+    the reference's callback path does), then the copy to n_src outputs (comm.h:209-224)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kvoracle as K
+    ref = K.ref()
+    o = K.get_oracle()
+    cores = os.cpu_count() or 1
+    shapes = WORKLOADS[workload]["shapes"]()
+    rng = np.random.default_rng(0xB200)
+    sizes = [int(np.prod(s)) for s in shapes]
+    W = [rng.uniform(-1, 1, n).astype(np.float32) for n in sizes]
+    G = [[rng.uniform(-1, 1, n).astype(np.float32) for _ in range(n_src)] for n in sizes]
+    M = [np.zeros(n, np.float32) for n in sizes]
+    V = [np.zeros(n, np.float32) for n in sizes]
+    OUT = [[np.empty(n, np.float32) for _ in range(n_src)] for n in sizes]
+    kind = "reference" if ref is not None else "port"
+    sp, f32 = K.scalar_param, K.f32
+    opt = WORKLOADS[workload]["opt"]
+    state = {"t": 0}
+
+    def step():
+        state["t"] += 1
+        t = state["t"]
+        for k in range(len(sizes)):
+            if n_src > 1:
+                bufs = [g for g in G[k]]
+                if ref is not None:
+                    merged_bufs = [bufs[0].copy()] + bufs[1:]      # CopyFromTo(src[0] -> merged)
+                    ref.reduce_inplace(merged_bufs, 4)             # MXNET_KVSTORE_REDUCTION_NTHREADS=4
+                    merged = merged_bufs[0]
+                else:
+                    merged = o.reduce(bufs, "local", 4)
+            else:
+                merged = G[k][0]
+            if opt == "sgd":
+                if ref is not None:
+                    ref.multi_sgd_update([W[k]], [merged], [M[k]], [f32(0.1)], [f32(1e-4)],
+                                         sp(0.9), sp(1.0 / 256), None, cores)
+                else:
+                    o.multi_sgd_update(W[k], merged, M[k], f32(0.1), sp(0.9), f32(1e-4),
+                                       sp(1.0 / 256), None, cores)
+            else:
+                lr_t = sp(K.adam_lr(1e-3, 0.9, 0.999, t))
+                fn = ref.adam_update if ref is not None else o.adam_update
+                fn(W[k], merged, M[k], V[k], lr_t, sp(0.9), sp(0.999), sp(1e-8), sp(0.01), 1.0,
+                   None, cores)
+            for out in OUT[k]:
+                np.copyto(out, W[k])
+    return step, kind, cores
+
+
+def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path on this box's cores."""
+    n_src = max(1, args.gpus)
+    step, kind, cores = cpu_kvstore_step_fn(args.workload, n_src)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    nbytes = algorithmic_bytes(args.workload, n_src) * (n_src if n_src > 1 else 1)
+    value = nbytes / dt / 1e9
+    sample = "%d full steps of %s with %d host gradient buffers per key" % (
+        args.steps, args.workload, n_src)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload]["desc"], "store": "kvstore('local') on CPU",
+                       "values_per_key": n_src},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def make_optimizer(mx, workload, n_gpus):
+    if WORKLOADS[workload]["opt"] == "sgd":
+        return mx.optimizer.SGD(rescale_grad=1.0 / (256 * n_gpus), **SGD_KW)
+    return mx.optimizer.Adam(rescale_grad=1.0, **ADAM_KW)
+
+
+def run_single_gpu(args):
+    import torch
+    import anand_mxnet_b200 as mx
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    mx.base.set_stream(0, stream.cuda_stream)   # library work is issued on torch's stream
+    shapes = WORKLOADS[args.workload]["shapes"]()
+    keys = list(range(len(shapes)))
+    n_elem = sum(int(np.prod(s)) for s in shapes)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0xB200)
+
+    def urand(s):
+        return torch.rand(s, device=dev, generator=gen) * 2 - 1
+
+    # ---- device-resident arm
+    kv = mx.kv.create("device")
+    kv.init(keys, [mx.nd.from_torch(urand(s)) for s in shapes])
+    kv.set_optimizer(make_optimizer(mx, args.workload, 1))
+    grads_t = [urand(s) for s in shapes]
+    outs_t = [torch.empty(s, device=dev) for s in shapes]
+    grads = [mx.nd.from_torch(t) for t in grads_t]
+    outs = [mx.nd.from_torch(t) for t in outs_t]
+    torch.cuda.synchronize()
+
+    def step():
+        kv.pushpull(keys, grads, out=outs)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    mx.base.reset_kernel_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_all0.record(stream)
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        step()
+        ev[i][1].record(stream)
+    t_all1.record(stream)
+    torch.cuda.synchronize()
+    launches = mx.base.kernel_launch_count()
+    clocks = sampler.stop()
+    ms_total = t_all0.elapsed_time(t_all1)
+    ms_step = ms_total / args.steps
+    ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    alg = algorithmic_bytes(args.workload, 1)
+    value = alg / (ms_step * 1e-3) / 1e9
+    peaks, peak_src = measured_peaks()
+    achieved = alg / (ms_kernel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": _ncu_traffic(), "kernel":
+                "dense_fused_kernel<float,1,SGD>" if WORKLOADS[args.workload]["opt"] == "sgd"
+                else "dense_fused_kernel<float,1,Adam>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_kernel}
+
+    # ---- end-to-end arm: same C-ABI call, HOST (pinned) gradient and weight buffers
+    kv2 = mx.kv.create("device")
+    kv2.init(keys, [mx.nd.array(np.zeros(s, np.float32), mx.cpu()) for s in shapes])
+    kv2.set_optimizer(make_optimizer(mx, args.workload, 1))
+    rng = np.random.default_rng(0xB200)
+    hgrads = [mx.nd.array(rng.uniform(-1, 1, s).astype(np.float32), mx.cpu()) for s in shapes]
+    houts = [mx.nd.empty(s, mx.cpu()) for s in shapes]
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        kv2.pushpull(keys, hgrads, out=houts)
+    mx.nd.waitall()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        kv2.pushpull(keys, hgrads, out=houts)
+    e1.record(stream)
+    mx.nd.waitall()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    e2e = {"value": alg / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_elem * 4,
+           "d2h_bytes_per_step": n_elem * 4, "ms_per_step": e2e_ms, "steps": e2e_steps}
+
+    # ---- cpu baseline (bounded sample, rank 0, N=1)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cstep, kind, cores = cpu_kvstore_step_fn(args.workload, 1)
+        cstep()
+        t0 = time.perf_counter()
+        n = 0
+        while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 200):
+            cstep()
+            n += 1
+        cdt = (time.perf_counter() - t0) / n
+        cpu = {"value": alg / cdt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "%d full steps of %s (reduce of 1 value + optimizer + copy-out per key), "
+                         "%.1f ms/step" % (n, args.workload, cdt * 1e3)}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload]["desc"], "store": "kvstore('device')",
+                       "call": "one grouped MXKVStorePushPull over all keys per step",
+                       "l2": "working set %.0f MB per step > 126 MB L2, no flush needed" % (alg / 1e6),
+                       "optimizer": SGD_KW if WORKLOADS[args.workload]["opt"] == "sgd" else ADAM_KW},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks}
+    print(json.dumps(line))
+
+
+def _ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "r01_dense_fused_traffic.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="resnet50_sgd", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        run_single_gpu(args)
+        return
+    from bench_multi import run_multi_gpu
+    run_multi_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

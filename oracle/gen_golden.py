@@ -63,10 +63,10 @@ def main():
         # five Adam steps with the python-side bias-corrected lr (optimizer.py:1617-1620)
         outs = []
         aclip = None if clip is None else 0.5
+        sp = lambda x: r.dmlc_stof(repr(float(x)))  # noqa: E731  the reference's own scalar parse
         for t in range(1, 6):
-            lr_t = K.f32(K.adam_lr(1e-3, 0.9, 0.999, t))
-            r.adam_update(w2, g, m2, v2, lr_t, K.f32(0.9), K.f32(0.999), K.f32(1e-8), K.f32(0.01),
-                          1.0, aclip)
+            lr_t = sp(K.adam_lr(1e-3, 0.9, 0.999, t))
+            r.adam_update(w2, g, m2, v2, lr_t, sp(0.9), sp(0.999), sp(1e-8), sp(0.01), 1.0, aclip)
             outs.append(np.stack([w2.copy(), m2.copy(), v2.copy()]))
         d["adam_%s_in" % tag] = np.stack([w, g, m, v])
         d["adam_%s_out" % tag] = np.stack(outs)
@@ -116,6 +116,24 @@ def main():
     comp2 = r.quantize_2bit(g, res, 0.5)
     np.savez_compressed(os.path.join(GOLD, "twobit.npz"), grad=g, comp1=comp1, res1=res1,
                         comp2=comp2, res2=res.copy(), deq1=r.dequantize_2bit(comp1, g.size, 0.5))
+
+    # ---- scalar plumbing: python repr -> dmlc::stof, on values a training run produces ----
+    import random
+    random.seed(0xB200)
+    vals = [0.1, 0.01, 1e-4, 1e-5, 2.5e-5, 1.2345e-5, 0.9, 0.999, 1e-8, 1 / 256, 1 / 2048, 5.0, 2.5]
+    for _ in range(3000):
+        k = random.random()
+        if k < 0.3:
+            vals.append(random.uniform(0, 1))
+        elif k < 0.6:
+            vals.append(10 ** random.uniform(-9, 3))
+        elif k < 0.8:
+            vals.append(0.1 * 0.97 ** random.randint(0, 300))
+        else:
+            vals.append(K.adam_lr(1e-3, 0.9, 0.999, random.randint(1, 5000)))
+    vals = np.array(vals, dtype=np.float64)
+    parsed = np.array([r.dmlc_stof(repr(float(v))) for v in vals], dtype=np.float32)
+    np.savez_compressed(os.path.join(GOLD, "scalar_parse.npz"), values=vals, parsed=parsed)
     print("wrote", sorted(os.listdir(GOLD)))
 
 

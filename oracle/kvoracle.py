@@ -244,10 +244,16 @@ class Ref(object):
                                             _F, _F, _F, _F, _I]
         L.mxref_quantize_2bit.argtypes = [_SZ, _P, _P, _P, _F, _F]
         L.mxref_dequantize_2bit.argtypes = [_SZ, _P, _P, _F, _F]
+        L.mxref_dmlc_stof.restype = _F
+        L.mxref_dmlc_stof.argtypes = [ctypes.c_char_p]
 
     @staticmethod
     def _clip(c):
         return -1.0 if (c is None or c is False) else float(c)
+
+    def dmlc_stof(self, s):
+        """the reference's own dmlc::stof"""
+        return float(self.lib.mxref_dmlc_stof(s.encode()))
 
     def reduce(self, srcs, nthreads=1, bigarray_bound=1000 * 1000):
         """CommCPU 'local' reduce; the result lands in a copy of srcs[0] (reference sums in place)."""
@@ -375,9 +381,69 @@ def ref():
 # ------------------------------------------------------------------------------------------
 
 def f32(x):
-    """Python double -> nearest float32 -> python float: the str()/dmlc float-parse hop every
-    hyper-parameter takes between python/mxnet/optimizer/optimizer.py and the C++ op parameters."""
+    """Python double -> nearest float32 -> python float: how TUPLE op parameters (lrs, wds of the
+    multi_* ops) arrive -- str(tuple) parsed by std::istream >> float (include/mxnet/tuple.h),
+    which is correctly rounded."""
     return float(np.float32(x))
+
+
+def dmlc_stof(s):
+    """dmlc::stof == ParseFloat<float> (3rdparty/dmlc-core/include/dmlc/strtonum.h:99-254) restated
+    with numpy float32 arithmetic: float(int part) + float(double(frac digits)/double(10^k)), then
+    scaled by powers of ten IN FLOAT. Not a correctly rounded conversion -- and it is what every
+    SCALAR op parameter (lr, wd, rescale_grad, momentum, clip_gradient, beta1, ...) goes through."""
+    F = np.float32
+    p = s.strip()
+    sign = 1.0
+    if p[:1] in '+-':
+        sign = -1.0 if p[0] == '-' else 1.0
+        p = p[1:]
+    low = p.lower()
+    if low in ('inf', 'infinity'):
+        return float(F(sign * np.inf))
+    if low.startswith('nan'):
+        return float('nan')
+    i = 0
+    predec = 0
+    while i < len(p) and p[i].isdigit():
+        predec = predec * 10 + int(p[i])
+        i += 1
+    value = F(predec)
+    if i < len(p) and p[i] == '.':
+        i += 1
+        val2, pow10, cnt = 0, 1, 0
+        while i < len(p) and p[i].isdigit():
+            if cnt < 19:
+                val2 = val2 * 10 + int(p[i])
+                pow10 *= 10
+            cnt += 1
+            i += 1
+        value = F(value + F(float(val2) / float(pow10)))
+    if i < len(p) and p[i] in 'eE':
+        i += 1
+        frac = False
+        if i < len(p) and p[i] in '+-':
+            frac = p[i] == '-'
+            i += 1
+        expon = 0
+        while i < len(p) and p[i].isdigit():
+            expon = expon * 10 + int(p[i])
+            i += 1
+        scale = F(1.0)
+        while expon >= 8:
+            scale = F(scale * F(1e8))
+            expon -= 8
+        while expon > 0:
+            scale = F(scale * F(10.0))
+            expon -= 1
+        value = F(value / scale) if frac else F(value * scale)
+    assert i == len(p) or p[i:] in ('f', 'F'), "cannot parse %r" % s
+    return float(F(sign) * value)
+
+
+def scalar_param(v):
+    """python float -> str() -> dmlc::stof: the value a scalar operator parameter really takes."""
+    return dmlc_stof(repr(float(v)))
 
 
 def group_kv_pairs(keys, values):
@@ -443,22 +509,27 @@ class LocalKVStoreModel(object):
         lr = p['lr'] * p['lr_mult'].get(key, 1.0)
         wd = p['wd'] * p['wd_mult'].get(key, 1.0)
         clip = p['clip'] if p['clip'] else None  # optimizer.py:623-624 passes clip only if truthy
+        sp = scalar_param
         if p['kind'] == 'sgd':
+            # multi_sgd[_mom]_update: lrs/wds are tuple parameters (nearest float32), the rest are
+            # scalar parameters (dmlc::stof); momentum is only passed when > 0 (optimizer.py:618-621)
             mom = None
             if p['momentum'] != 0.0:
                 mom = self.state.setdefault(key, np.zeros_like(w))
             self.o.multi_sgd_update(w.reshape(-1), merged.reshape(-1),
                                     mom.reshape(-1) if mom is not None else None, f32(lr),
-                                    f32(p['momentum']) if p['momentum'] > 0 else 0.0, f32(wd),
-                                    f32(p['rescale']), f32(clip) if clip else None)
+                                    sp(p['momentum']) if p['momentum'] > 0 else 0.0, f32(wd),
+                                    sp(p['rescale']), sp(clip) if clip else None)
         elif p['kind'] == 'adam':
+            # adam_update: every hyper-parameter is a scalar parameter
             m, v = self.state.setdefault(key, (np.zeros_like(w), np.zeros_like(w)))
             lr_t = adam_lr(lr, p['beta1'], p['beta2'], self.count[key])
             self.o.adam_update(w.reshape(-1), merged.reshape(-1), m.reshape(-1), v.reshape(-1),
-                               f32(lr_t), f32(p['beta1']), f32(p['beta2']), f32(p['eps']), f32(wd),
-                               f32(p['rescale']), f32(clip) if clip else None)
+                               sp(lr_t), sp(p['beta1']), sp(p['beta2']), sp(p['eps']), sp(wd),
+                               sp(p['rescale']), sp(clip) if clip else None)
         elif p['kind'] == 'test':
-            self.o.test_update(w.reshape(-1), merged.reshape(-1), f32(p['rescale']))
+            # grad * rescale_grad -> _mul_scalar(scalar=str(rescale_grad))
+            self.o.test_update(w.reshape(-1), merged.reshape(-1), sp(p['rescale']))
         else:
             raise ValueError(p['kind'])
 

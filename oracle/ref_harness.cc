@@ -69,6 +69,10 @@ extern "C" {
 
 int mxref_abi_version() { return 1; }
 
+// dmlc::stof (3rdparty/dmlc-core/include/dmlc/strtonum.h:467): how FieldEntry<float>::Set parses
+// every scalar op parameter (lr, wd, rescale_grad, ...). Pins csrc/scalar_parse.cc.
+float mxref_dmlc_stof(const char* s) { return dmlc::stof(std::string(s)); }
+
 // CommCPU::ReduceSumCPU<float>: sums n buffers of `size` floats into ptrs[0], reference association.
 void mxref_reduce_sum_cpu(float** ptrs, int n, size_t size) {
   std::vector<float*> d(ptrs, ptrs + n);

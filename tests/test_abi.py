@@ -1,0 +1,107 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/b200kv_c_api.h declares, fails loudly without a GPU (no CPU fallback), and its host-only
+pieces (chunk planner, plugin registry, front-end bookkeeping) behave."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module")
+def mx():
+    import anand_mxnet_b200 as mx
+    return mx
+
+
+def test_library_exports_every_declared_symbol(mx):
+    hdr = open(os.path.join(ROOT, "include", "b200kv_c_api.h")).read()
+    names = set(re.findall(r"B200KV_DLL\s+[\w\s\*]+?\b((?:MX|NN|B200KV)\w+)\s*\(", hdr))
+    assert len(names) > 70, len(names)
+    # the KVStore entry points of the reference's C API that python/mxnet/kvstore/kvstore.py binds
+    for required in ("MXKVStoreCreate", "MXKVStoreFree", "MXKVStoreInit", "MXKVStoreInitEx",
+                     "MXKVStorePush", "MXKVStorePushEx", "MXKVStorePullWithSparse",
+                     "MXKVStorePullWithSparseEx", "MXKVStorePushPull", "MXKVStorePushPullEx",
+                     "MXKVStorePullRowSparse", "MXKVStorePullRowSparseEx", "MXKVStoreSetUpdaterEx",
+                     "MXKVStoreSetGradientCompression", "MXKVStoreGetType", "MXKVStoreGetRank",
+                     "MXKVStoreGetGroupSize", "MXKVStoreIsWorkerNode", "MXKVStoreBarrier",
+                     "MXKVStoreSendCommmandToServers", "MXGetLastError"):
+        assert required in names
+    lib = ctypes.CDLL(os.path.join(ROOT, "anand_mxnet_b200", "libb200kv.so"))
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_fails_loudly_without_gpu(mx):
+    with pytest.raises(mx.MXNetError, match="no CPU fallback"):
+        mx.kv.create('device')
+    with pytest.raises(mx.MXNetError, match="needs a CUDA device"):
+        mx.nd.zeros((2, 2))
+
+
+def test_error_convention(mx):
+    lib = mx.base._LIB
+    h = ctypes.c_void_p()
+    assert lib.NNGetOpHandle(b"Convolution", ctypes.byref(h)) == -1
+    assert b"not registered" in lib.MXGetLastError()
+    assert lib.NNGetOpHandle(b"sgd_mom_update", ctypes.byref(h)) == 0
+    v = ctypes.c_int()
+    assert lib.MXGetVersion(ctypes.byref(v)) == 0 and v.value == 10600
+    for fn in (lib.MXKVStoreIsWorkerNode, lib.MXKVStoreIsServerNode, lib.MXKVStoreIsSchedulerNode):
+        assert fn(ctypes.byref(v)) == 0
+    assert lib.MXKVStoreIsWorkerNode(ctypes.byref(v)) == 0 and v.value == 1
+
+
+def test_chunk_planner(mx):
+    """Host-only planner: every element of every key lands in exactly one chunk of <= 4096
+    elements; stripes of 32768 elements rotate over the devices; balance within one stripe/key."""
+    from bench import resnet50_shapes, bert_base_shapes
+    lib = mx.base._LIB
+    for shapes in (resnet50_shapes(), bert_base_shapes(), [(3,), (1,), (4097,), (32768 * 3 + 5,)]):
+        sizes = [int(np.prod(s)) for s in shapes]
+        arr = (ctypes.c_uint64 * len(sizes))(*sizes)
+        for ndev in (1, 2, 4, 8):
+            counts = (ctypes.c_uint64 * ndev)()
+            elems = (ctypes.c_uint64 * ndev)()
+            assert lib.B200KVTestPlanChunks(arr, len(sizes), ndev, counts, elems) == 0
+            assert sum(elems) == sum(sizes)
+            if sum(sizes) > 64 * 32768 * ndev:
+                share = sum(sizes) / ndev
+                assert max(elems) - min(elems) <= 0.05 * share, (ndev, list(elems))
+
+
+def test_registry_and_teststore(mx):
+    # python/mxnet/kvstore/base.py:221-245,441-455: registry first, native factory otherwise
+    @mx.kv.KVStoreBase.register
+    class MyStore(mx.kv.KVStoreBase):
+        pass
+    assert isinstance(mx.kv.create('MyStore'), MyStore)
+    assert mx.kv.create('teststore').type == 'teststore'
+    assert mx.kv.TestStore.is_capable('optimizer') is False
+    assert mx.kv.KVStore.is_capable('optimizer') is True
+    with pytest.raises(TypeError):
+        mx.kv.create(3)
+
+
+def test_optimizer_bookkeeping(mx):
+    """lr / wd multipliers and update counts (optimizer.py:412-509), no device work involved."""
+    opt = mx.optimizer.SGD(learning_rate=0.1, wd=0.01, param_idx2name={0: 'fc_weight', 1: 'fc_bias'})
+    opt.set_lr_mult({'fc_bias': 2.0})
+    assert opt._get_lrs([0, 1]) == [0.1, 0.2]
+    assert opt._get_wds([0, 1]) == [0.01, 0.0]          # biases get wd_mult 0 by name
+    opt._update_count([0, 1])
+    opt._update_count(0)
+    assert opt.num_update == 2 and opt._index_update_count == {0: 2, 1: 1}
+    assert mx.optimizer.create('adam', learning_rate=3e-4).lr == 3e-4

@@ -54,11 +54,36 @@ def test_optimizers_golden(oracle, golden, tag, clip):
 def test_adam_golden(oracle, golden, tag, clip):
     g = golden("optimizers")
     w, gr, m, v = [x.copy() for x in g["adam_%s_in" % tag]]
+    sp = K.scalar_param
     for t in range(1, 6):
-        lr_t = K.f32(K.adam_lr(1e-3, 0.9, 0.999, t))
-        oracle.adam_update(w, gr, m, v, lr_t, K.f32(0.9), K.f32(0.999), K.f32(1e-8), K.f32(0.01),
-                           1.0, clip)
+        lr_t = sp(K.adam_lr(1e-3, 0.9, 0.999, t))
+        oracle.adam_update(w, gr, m, v, lr_t, sp(0.9), sp(0.999), sp(1e-8), sp(0.01), 1.0, clip)
         assert eq(np.stack([w, m, v]), g["adam_%s_out" % tag][t - 1]), t
+
+
+def test_scalar_parse_golden(golden):
+    """python repr -> dmlc::stof, the hop every scalar hyper-parameter takes: the oracle's
+    restatement AND the product library's (csrc/scalar_parse.cc, host-only test hooks) must both
+    reproduce the reference's values -- which differ from nearest-float32 for ~6% of inputs."""
+    import ctypes
+    import anand_mxnet_b200 as mx
+    lib = mx.base._LIB
+    g = golden("scalar_parse")
+    buf = ctypes.create_string_buffer(64)
+    out = ctypes.c_float()
+    n_not_nearest = 0
+    for v, want in zip(g["values"], g["parsed"]):
+        v = float(v)
+        assert np.float32(K.dmlc_stof(repr(v))) == want, v
+        assert lib.B200KVTestPyFloatRepr(ctypes.c_double(v), buf, 64) == 0
+        assert buf.value.decode() == repr(v)
+        assert lib.B200KVTestDmlcStof(repr(v).encode(), ctypes.byref(out)) == 0
+        assert np.float32(out.value) == want, v
+        n_not_nearest += int(np.float32(v) != want)
+    assert n_not_nearest > 0   # the quirk is real: a correctly rounded parse would NOT be bit-exact
+    for v in (0.0, -0.0, 1e16, 1e22, 123456789.125, 5e-324, 1.7976931348623157e308, 1e-5, 0.0001):
+        assert lib.B200KVTestPyFloatRepr(ctypes.c_double(v), buf, 64) == 0
+        assert buf.value.decode() == repr(v)
 
 
 @pytest.mark.parametrize("tag,clip", CLIPS)
@@ -204,6 +229,17 @@ def test_reduce_vs_reference_live(oracle):
     # above MXNET_KVSTORE_BIGARRAY_BOUND: 4 threads x 4096-element tasks (comm.h:394-410)
     srcs = [rng.uniform(-1, 1, 1200007).astype(np.float32) for _ in range(8)]
     assert eq(oracle.reduce(srcs, "local", nthreads=4), r.reduce(srcs, nthreads=4))
+
+
+@needs_ref
+def test_dmlc_stof_vs_reference_live():
+    import random
+    r = K.ref()
+    random.seed(7)
+    for _ in range(5000):
+        v = random.choice([random.uniform(0, 2), 10 ** random.uniform(-12, 6),
+                           0.1 * 0.97 ** random.randint(0, 500), -random.uniform(0, 1e-3)])
+        assert np.float32(K.dmlc_stof(repr(v))) == np.float32(r.dmlc_stof(repr(v))), v
 
 
 @needs_ref
