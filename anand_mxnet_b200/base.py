@@ -57,7 +57,7 @@ def c_array(ctype, values):
 
 def c_handle_array(objs):
     arr = (ctypes.c_void_p * len(objs))()
-    arr[:] = [o.handle.value if isinstance(o.handle, ctypes.c_void_p) else o.handle for o in objs]
+    arr[:] = [o._hv for o in objs]
     return arr
 
 

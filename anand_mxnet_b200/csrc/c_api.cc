@@ -564,12 +564,14 @@ int B200KVStoreSetOptimizer(KVStoreHandle handle, const char* name, mx_uint num_
 int B200KVStoreSetLearningRate(KVStoreHandle handle, double lr) {
   API_BEGIN();
   KV(handle).opt().lr = lr;
+  KV(handle).TouchOpt();
   API_END();
 }
 
 int B200KVStoreSetRescaleGrad(KVStoreHandle handle, double rescale_grad) {
   API_BEGIN();
   KV(handle).opt().rescale = rescale_grad;
+  KV(handle).TouchOpt();
   API_END();
 }
 
@@ -581,6 +583,7 @@ int B200KVStoreSetKeyMultipliers(KVStoreHandle handle, mx_uint num, const int* k
     if (lr_mult) o.lr_mult[keys[i]] = lr_mult[i];
     if (wd_mult) o.wd_mult[keys[i]] = wd_mult[i];
   }
+  KV(handle).TouchOpt();
   API_END();
 }
 
@@ -615,6 +618,7 @@ int B200KVStoreSetUpdateCount(KVStoreHandle handle, int key, int count) {
   OptConfig& o = KV(handle).opt();
   o.count[key] = count;
   o.num_update = std::max(o.num_update, count);
+  KV(handle).TouchOpt();
   API_END();
 }
 

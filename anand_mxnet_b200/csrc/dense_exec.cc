@@ -1,0 +1,289 @@
+// dense_exec.cc -- prepare / run split of the fused dense launch and the call-level cache.
+//
+// A training loop repeats the same C call every step (same keys, same arrays). Everything that
+// does not change between steps -- grouping, validation, placement, state allocation, descriptor
+// tables on the device, the list of arrays whose dependencies are tracked -- is computed once
+// (PrepareDense) and cached by the call's signature; a repeated call only replays RunPrepared:
+// staging copies (host-resident operands), update counts, (lr, wd) refresh when a hyper-parameter
+// changed, dependency bookkeeping, ONE kernel launch per owner GPU. This is what keeps the host
+// cost of a 157-key pushpull in the microseconds, below the ~90 us the kernel itself takes.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <set>
+
+#include "kvstore.h"
+#include "scalar_parse.h"
+
+namespace b200kv {
+
+static uint64_t Mix(uint64_t h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+  return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// call-level cache
+// ---------------------------------------------------------------------------------------------
+bool KVStore::CallSignature(int tag, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
+                            const std::vector<int>* okeys, const std::vector<NDArray>* outs,
+                            std::vector<uint64_t>* sig) {
+  sig->clear();
+  sig->reserve(4 + 2 * vkeys.size() + (okeys ? 2 * okeys->size() : 0));
+  sig->push_back(static_cast<uint64_t>(tag));
+  sig->push_back(vkeys.size());
+  for (size_t i = 0; i < vkeys.size(); ++i) {
+    const NDArray& a = values[i];
+    if (a.is_none() || a.stype() != kDefaultStorage) return false;  // row_sparse: slow path
+    sig->push_back(static_cast<uint64_t>(static_cast<int64_t>(vkeys[i])));
+    sig->push_back(reinterpret_cast<uint64_t>(a.storage()) ^ (reinterpret_cast<uint64_t>(a.data()) << 1));
+  }
+  sig->push_back(0xfeedULL);
+  if (okeys != nullptr) {
+    for (size_t i = 0; i < okeys->size(); ++i) {
+      const NDArray& a = (*outs)[i];
+      if (a.is_none() || a.stype() != kDefaultStorage) return false;
+      sig->push_back(static_cast<uint64_t>(static_cast<int64_t>((*okeys)[i])));
+      sig->push_back(reinterpret_cast<uint64_t>(a.storage()) ^ (reinterpret_cast<uint64_t>(a.data()) << 1));
+    }
+  }
+  return true;
+}
+
+static uint64_t HashSig(const std::vector<uint64_t>& sig) {
+  uint64_t h = 0x51ed270b;
+  for (uint64_t v : sig) h = Mix(h, v);
+  return h;
+}
+
+bool KVStore::RunCachedCall(const std::vector<uint64_t>& sig) {
+  auto it = call_cache_.find(HashSig(sig));
+  if (it == call_cache_.end()) return false;
+  CachedCall& c = *it->second;
+  if (c.epoch != layout_epoch_ || c.sig != sig) {
+    call_cache_.erase(it);
+    return false;
+  }
+  for (auto& p : c.launches) RunPrepared(p);
+  return true;
+}
+
+void KVStore::StoreCachedCall(const std::vector<uint64_t>& sig, std::vector<Prepared>&& launches) {
+  if (call_cache_.size() > 64) call_cache_.clear();
+  auto c = std::make_shared<CachedCall>();
+  c->sig = sig;
+  c->launches = std::move(launches);
+  c->epoch = layout_epoch_;
+  call_cache_[HashSig(sig)] = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prepare: placement, staging buffers, state, plan
+// ---------------------------------------------------------------------------------------------
+void KVStore::ExecDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stripe) {
+  std::vector<Prepared> launches;
+  PrepareDense(ops, opt_kind, allow_stripe, &launches);
+  for (auto& p : launches) RunPrepared(p);
+}
+
+void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stripe,
+                           std::vector<Prepared>* out) {
+  if (ops.empty()) return;
+  const bool is_push = opt_kind != kOptPullOnly;
+  // ---- 1. device set: a push with values on >= 2 GPUs (re)defines the stripe owners
+  if (is_push && allow_stripe) {
+    std::vector<int> devs;
+    for (auto& s : ops[0].srcs) {
+      if (s.on_gpu() && std::find(devs.begin(), devs.end(), s.dev()) == devs.end()) devs.push_back(s.dev());
+    }
+    if (devs.size() >= 2) SetDeviceSet(devs);
+  }
+  // ---- 2. placement of every key; host-resident operands get device staging buffers
+  // Launch groups: (dtype, striped?, home, bucket). Host-resident operands are staged through the
+  // GPU; such a group is cut into buckets of ~8 MB of staged bytes so the H2D copy of bucket b+1,
+  // the kernel of bucket b and the D2H copy of bucket b-1 run concurrently on the three lanes.
+  static const size_t kStageBucketBytes = []() {
+    const char* s = std::getenv("B200KV_STAGE_BUCKET_MB");
+    return static_cast<size_t>(s ? std::max(1, std::atoi(s)) : 8) << 20;
+  }();
+  std::map<std::tuple<int, int, int, int>, Prepared> groups;
+  std::map<std::tuple<int, int, int>, std::pair<int, size_t>> bucket_of;  // -> (bucket, bytes)
+  for (auto& op : ops) {
+    KeyEntry& e = *op.e;
+    std::vector<int> sdev;
+    for (auto& s : op.srcs) {
+      if (s.on_gpu() && std::find(sdev.begin(), sdev.end(), s.dev()) == sdev.end()) sdev.push_back(s.dev());
+    }
+    if (is_push && allow_stripe && sdev.size() >= 2) {
+      KV_CHECK(sdev == devset_) << "key " << e.key << ": values live on a different GPU list than "
+                                << "the other keys of this push";
+      EnsureStriped(e);
+    } else if (!e.striped && e.home < 0) {
+      int pick = -1;
+      for (auto& s : op.srcs) if (pick < 0 && s.on_gpu()) pick = s.dev();
+      for (auto& o : op.outs) if (pick < 0 && o.on_gpu()) pick = o.dev();
+      if (pick < 0) pick = devset_.empty() ? 0 : devset_[0];
+      EnsureOnDevice(e, pick);
+    }
+    KV_CHECK(op.outs.size() <= static_cast<size_t>(kMaxDst)) << "at most " << kMaxDst << " outs per key";
+    const auto gkey = std::make_tuple(e.dtype, e.striped ? 1 : 0, e.striped ? -1 : e.home);
+    size_t staged = 0;
+    for (auto& s : op.srcs) if (!s.on_gpu()) staged += s.ByteSize();
+    for (auto& o : op.outs) if (!o.on_gpu()) staged += o.ByteSize();
+    auto& bk = bucket_of[gkey];
+    if (staged > 0 && bk.second > 0 && bk.second + staged > kStageBucketBytes) {
+      ++bk.first;
+      bk.second = 0;
+    }
+    bk.second += staged;
+    Prepared& P = groups[std::make_tuple(std::get<0>(gkey), std::get<1>(gkey), std::get<2>(gkey), bk.first)];
+    const int stage_dev = e.striped ? devset_[0] : e.home;
+    DenseOp dop = op;
+    for (size_t i = 0; i < dop.srcs.size(); ++i) {
+      if (!dop.srcs[i].on_gpu()) {
+        NDArray st = StageSrc(e, i, dop.srcs[i], stage_dev);
+        P.stage_in.emplace_back(dop.srcs[i], st);
+        dop.srcs[i] = st;
+      }
+    }
+    for (size_t i = 0; i < dop.outs.size(); ++i) {
+      KV_CHECK_EQ(dop.outs[i].Size(), e.size) << "pull: shape mismatch for key " << e.key;
+      KV_CHECK_EQ(dop.outs[i].dtype(), e.dtype) << "pull: dtype mismatch for key " << e.key;
+      if (!dop.outs[i].on_gpu()) {
+        NDArray st = StageOut(e, i, dop.outs[i], stage_dev);
+        P.stage_out.emplace_back(st, dop.outs[i]);
+        dop.outs[i] = st;
+      }
+    }
+    P.ops.push_back(std::move(dop));
+  }
+  Engine* eng = Engine::Get();
+  for (auto& kv : groups) {
+    Prepared& P = kv.second;
+    P.opt_kind = opt_kind;
+    P.dtype = std::get<0>(kv.first);
+    P.is_push = is_push;
+    P.owners = P.ops[0].e->striped ? devset_ : std::vector<int>{P.ops[0].e->home};
+    for (auto& op : P.ops) {
+      for (int d : P.owners) StateOn(*op.e, d, opt_kind);
+    }
+    P.plan = GetPlan(P.ops, opt_kind, P.owners, P.ops[0].e->striped);
+    std::set<int> part_set(P.owners.begin(), P.owners.end());
+    for (auto& op : P.ops) {
+      for (auto& s : op.srcs) part_set.insert(s.dev());
+      for (auto& o : op.outs) part_set.insert(o.dev());
+    }
+    P.parts.assign(part_set.begin(), part_set.end());
+    if (P.parts.size() > 1) {
+      int enabled = eng->EnablePeerAccess(P.parts);
+      KV_CHECK_EQ(enabled, static_cast<int>(P.parts.size() * (P.parts.size() - 1)))
+          << "GPU peer access is not available between all participating devices";
+    }
+    out->push_back(std::move(P));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// run: what happens on every step
+// ---------------------------------------------------------------------------------------------
+void KVStore::RunPrepared(Prepared& P) {
+  Engine* eng = Engine::Get();
+  const int opt_kind = P.opt_kind;
+  const bool fused_opt = P.is_push && opt_.enabled && (opt_kind == kOptSGD || opt_kind == kOptAdam);
+  for (auto& io : P.stage_in) CopyFromTo(io.first, io.second);
+
+  // ---- optimizer bookkeeping: update counts first (Optimizer._update_count, optimizer.py:412-430)
+  if (fused_opt) {
+    for (auto& op : P.ops) {
+      auto it = opt_.count.find(op.e->key);
+      const int c = (it == opt_.count.end() ? opt_.begin_num_update : it->second) + 1;
+      if (it == opt_.count.end()) opt_.count[op.e->key] = c; else it->second = c;
+      opt_.num_update = std::max(opt_.num_update, c);
+    }
+  }
+  // per-key (lr, wd) and the scalar parameters: refreshed when a hyper-parameter changed (and on
+  // every step for Adam, whose effective lr depends on the per-key update count)
+  if (P.hyper_version != opt_version_ || opt_kind == kOptAdam) {
+    P.hyper.resize(P.ops.size() * 2);
+    for (size_t k = 0; k < P.ops.size(); ++k) {
+      KeyHyper(*P.ops[k].e, opt_kind, &P.hyper[2 * k], &P.hyper[2 * k + 1]);
+    }
+    if (P.hyper_version != opt_version_) {
+      DenseLaunch& L = P.scalars;
+      L = DenseLaunch();
+      if (opt_kind == kOptSGD) {
+        // SGD._update_impl (optimizer.py:618-624): momentum only if > 0, clip only if truthy
+        L.momentum = opt_.momentum > 0 ? ScalarParam(opt_.momentum) : 0.f;
+        L.rescale = ScalarParam(opt_.rescale);
+        L.clip = opt_.clip != 0.0 ? ScalarParam(opt_.clip) : -1.f;
+      } else if (opt_kind == kOptAdam) {
+        L.rescale = ScalarParam(opt_.rescale);
+        L.clip = opt_.clip != 0.0 ? ScalarParam(opt_.clip) : -1.f;
+        L.beta1 = ScalarParam(opt_.beta1);
+        L.beta2 = ScalarParam(opt_.beta2);
+        L.eps = ScalarParam(opt_.eps);
+      } else if (opt_kind == kOptTest) {
+        L.rescale = ScalarParam(opt_.rescale);
+      }
+      P.hyper_version = opt_version_;
+    }
+  }
+
+  // ---- dependencies
+  const bool multi = P.parts.size() > 1;
+  for (auto& op : P.ops) {
+    for (auto& s : op.srcs) eng->BeginRead(s.dev(), *s.var());
+    for (auto& o : op.outs) eng->BeginWrite(o.dev(), *o.var());
+    for (int d : P.owners) {
+      DevState& s = op.e->dev[d];
+      if (P.is_push) eng->BeginWrite(d, *s.w.var()); else eng->BeginRead(d, *s.w.var());
+    }
+  }
+  if (multi) eng->JoinStreams(P.parts);
+
+  // ---- launch, one kernel per owner
+  DenseLaunch L = P.scalars;
+  L.max_src = P.plan->max_src;
+  L.dtype = P.dtype;
+  L.opt = opt_kind;
+  L.order = order_local_ ? kOrderLocal : kOrderDevice;
+  for (auto& pd : P.plan->per_dev) {
+    DeviceGuard g(pd.dev);
+    cudaStream_t st = eng->Stream(pd.dev);
+    if (pd.hyper != P.hyper) {
+      KV_CUDA(cudaMemcpyAsync(pd.d_hyper, P.hyper.data(), P.hyper.size() * sizeof(float),
+                              cudaMemcpyHostToDevice, st));
+      pd.hyper = P.hyper;
+    }
+    if (pd.n_chunks == 0) continue;
+    L.keys = static_cast<const KeyDesc*>(pd.d_keys);
+    L.chunks = static_cast<const ChunkDesc*>(pd.d_chunks);
+    L.hyper = static_cast<const float*>(pd.d_hyper);
+    L.n_chunks = pd.n_chunks;
+    LaunchDenseFused(L, st);
+    eng->CountLaunch("dense_fused", P.plan->algorithmic_bytes / P.plan->per_dev.size());
+  }
+  if (multi) eng->JoinStreams(P.parts);
+
+  // ---- mark results
+  uint64_t seq[kMaxDevices] = {0};
+  for (int d : P.parts) seq[d] = eng->Issue(d);
+  for (auto& op : P.ops) {
+    for (auto& s : op.srcs) eng->MarkRead(s.dev(), seq[s.dev()], s.var());
+    for (auto& o : op.outs) eng->MarkWrite(o.dev(), seq[o.dev()], o.var());
+    for (int d : P.owners) {
+      DevState& s = op.e->dev[d];
+      if (P.is_push) {
+        eng->MarkWrite(d, seq[d], s.w.var());
+        if (!s.w32.is_none()) eng->MarkWrite(d, seq[d], s.w32.var());
+        if (!s.s1.is_none()) eng->MarkWrite(d, seq[d], s.s1.var());
+        if (!s.s2.is_none()) eng->MarkWrite(d, seq[d], s.s2.var());
+      } else {
+        eng->MarkRead(d, seq[d], s.w.var());
+      }
+    }
+  }
+  for (auto& io : P.stage_out) CopyFromTo(io.first, io.second);
+}
+
+}  // namespace b200kv

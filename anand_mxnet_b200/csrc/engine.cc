@@ -21,20 +21,22 @@ void Engine::Init() {
     KV_FATAL << "libb200kv needs a CUDA device and found none (" << cudaGetErrorString(e)
              << "); there is no CPU fallback for the KVStore path";
   }
-  n = std::min(n, kMaxDevices);
-  devs_.resize(n);
+  ndev_ = std::min(n, kMaxDevices);
+  lanes_.resize(kMaxStreams);
+  mem_.resize(ndev_);
   inited_ = true;
 }
 
 int Engine::NumDevices() {
   Init();
-  return static_cast<int>(devs_.size());
+  return ndev_;
 }
 
-cudaStream_t Engine::Stream(int dev) {
+cudaStream_t Engine::Stream(int sid) {
   Init();
-  KV_CHECK(dev >= 0 && dev < static_cast<int>(devs_.size())) << "invalid gpu id " << dev;
-  Dev& d = devs_[dev];
+  const int dev = DevOf(sid);
+  KV_CHECK(sid >= 0 && sid < kMaxStreams && dev < ndev_) << "invalid gpu id " << dev;
+  Lane& d = lanes_[sid];
   if (d.own == nullptr) {
     DeviceGuard g(dev);
     KV_CUDA(cudaStreamCreateWithFlags(&d.own, cudaStreamNonBlocking));
@@ -47,21 +49,22 @@ cudaStream_t Engine::Stream(int dev) {
 
 void Engine::SetStream(int dev, cudaStream_t s) {
   cudaStream_t old = Stream(dev);
-  Dev& d = devs_[dev];
+  Lane& d = lanes_[dev];
   cudaStream_t next = s ? s : d.own;
   if (next == old) return;
   // work already issued on the old stream stays ordered before work on the new one
   DeviceGuard g(dev);
+  ++d.issued;  // force a fresh event: the caller's framework may have enqueued work we never saw
   cudaEvent_t ev = RecordLatest(dev);
   KV_CUDA(cudaStreamWaitEvent(next, ev, 0));
   d.cur = next;
 }
 
-cudaEvent_t Engine::RecordLatest(int dev) {
-  Dev& d = devs_[dev];
-  Stream(dev);
+cudaEvent_t Engine::RecordLatest(int sid) {
+  Stream(sid);
+  Lane& d = lanes_[sid];
   if (d.latest == nullptr || d.recorded < d.issued) {
-    DeviceGuard g(dev);
+    DeviceGuard g(DevOf(sid));
     d.ring_pos = (d.ring_pos + 1) % d.ring.size();
     d.latest = d.ring[d.ring_pos];
     KV_CUDA(cudaEventRecord(d.latest, d.cur));
@@ -70,27 +73,27 @@ cudaEvent_t Engine::RecordLatest(int dev) {
   return d.latest;
 }
 
-uint64_t Engine::Issue(int dev) {
-  Stream(dev);
-  return ++devs_[dev].issued;
+uint64_t Engine::Issue(int sid) {
+  Stream(sid);
+  return ++lanes_[sid].issued;
 }
 
-void Engine::StreamWait(int dev, Tag t) {
-  if (t.dev < 0 || t.dev == dev) return;  // same device: stream order
-  Stream(dev);
-  Dev& d = devs_[dev];
+void Engine::StreamWait(int sid, Tag t) {
+  if (t.dev < 0 || t.dev == sid) return;  // same lane: stream order
+  Stream(sid);
+  Lane& d = lanes_[sid];
   if (d.waited[t.dev] >= t.seq) return;
-  if (devs_[t.dev].completed >= t.seq) return;
+  if (lanes_[t.dev].completed >= t.seq) return;
   cudaEvent_t ev = RecordLatest(t.dev);
-  DeviceGuard g(dev);
+  DeviceGuard g(DevOf(sid));
   KV_CUDA(cudaStreamWaitEvent(d.cur, ev, 0));
-  d.waited[t.dev] = devs_[t.dev].recorded;
+  d.waited[t.dev] = lanes_[t.dev].recorded;
 }
 
 void Engine::HostWait(Tag t) {
   if (t.dev < 0) return;
   Init();
-  Dev& d = devs_[t.dev];
+  Lane& d = lanes_[t.dev];
   if (d.completed >= t.seq) return;
   cudaEvent_t ev = RecordLatest(t.dev);
   uint64_t upto = d.recorded;
@@ -98,26 +101,26 @@ void Engine::HostWait(Tag t) {
   d.completed = std::max(d.completed, upto);
 }
 
-void Engine::BeginRead(int dev, const Var& v) { StreamWait(dev, v.writer); }
+void Engine::BeginRead(int sid, const Var& v) { StreamWait(sid, v.writer); }
 
-void Engine::BeginWrite(int dev, const Var& v) {
-  StreamWait(dev, v.writer);
+void Engine::BeginWrite(int sid, const Var& v) {
+  StreamWait(sid, v.writer);
   if (v.has_readers) {
-    for (int e = 0; e < static_cast<int>(devs_.size()); ++e) {
-      if (v.reader_seq[e]) StreamWait(dev, Tag{e, v.reader_seq[e]});
+    for (int e = 0; e < kMaxStreams; ++e) {
+      if (v.reader_seq[e]) StreamWait(sid, Tag{e, v.reader_seq[e]});
     }
   }
 }
 
-void Engine::MarkRead(int dev, uint64_t seq, Var* v) {
-  v->reader_seq[dev] = seq;
+void Engine::MarkRead(int sid, uint64_t seq, Var* v) {
+  v->reader_seq[sid] = seq;
   v->has_readers = true;
 }
 
-void Engine::MarkWrite(int dev, uint64_t seq, Var* v) {
-  v->writer = Tag{dev, seq};
+void Engine::MarkWrite(int sid, uint64_t seq, Var* v) {
+  v->writer = Tag{sid, seq};
   if (v->has_readers) {
-    for (int e = 0; e < kMaxDevices; ++e) v->reader_seq[e] = 0;
+    for (int e = 0; e < kMaxStreams; ++e) v->reader_seq[e] = 0;
     v->has_readers = false;
   }
 }
@@ -127,7 +130,7 @@ void Engine::WaitToRead(const Var& v) { HostWait(v.writer); }
 void Engine::WaitToWrite(const Var& v) {
   HostWait(v.writer);
   if (v.has_readers) {
-    for (int e = 0; e < static_cast<int>(devs_.size()); ++e) {
+    for (int e = 0; e < kMaxStreams; ++e) {
       if (v.reader_seq[e]) HostWait(Tag{e, v.reader_seq[e]});
     }
   }
@@ -135,28 +138,28 @@ void Engine::WaitToWrite(const Var& v) {
 
 void Engine::WaitAll() {
   if (!inited_) return;
-  for (int e = 0; e < static_cast<int>(devs_.size()); ++e) {
-    Dev& d = devs_[e];
+  for (int e = 0; e < kMaxStreams; ++e) {
+    Lane& d = lanes_[e];
     if (d.cur == nullptr) continue;
-    DeviceGuard g(e);
+    DeviceGuard g(DevOf(e));
     uint64_t upto = d.issued;
     KV_CUDA(cudaStreamSynchronize(d.cur));
     d.completed = std::max(d.completed, upto);
   }
 }
 
-void Engine::JoinStreams(const std::vector<int>& devs) {
-  if (devs.size() < 2) return;
-  // hub = devs[0]: it waits for every other stream, then every other stream waits for it.
+void Engine::JoinStreams(const std::vector<int>& sids) {
+  if (sids.size() < 2) return;
+  // hub = sids[0]: it waits for every other stream, then every other stream waits for it.
   // Issue() on every stream first so that a fresh event is recorded even when the only new work on
   // a (caller-provided) stream was enqueued by the caller's framework and never counted here.
-  const int hub = devs[0];
-  for (size_t i = 1; i < devs.size(); ++i) {
-    uint64_t s = Issue(devs[i]);
-    StreamWait(hub, Tag{devs[i], s});
+  const int hub = sids[0];
+  for (size_t i = 1; i < sids.size(); ++i) {
+    uint64_t s = Issue(sids[i]);
+    StreamWait(hub, Tag{sids[i], s});
   }
   uint64_t seq = Issue(hub);
-  for (size_t i = 1; i < devs.size(); ++i) StreamWait(devs[i], Tag{hub, seq});
+  for (size_t i = 1; i < sids.size(); ++i) StreamWait(sids[i], Tag{hub, seq});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -167,8 +170,9 @@ size_t Engine::RoundSize(size_t bytes) {
 }
 
 void* Engine::Alloc(int dev, size_t bytes) {
-  Stream(dev);
-  Dev& d = devs_[dev];
+  Init();
+  KV_CHECK(dev >= 0 && dev < ndev_) << "invalid gpu id " << dev;
+  DevMem& d = mem_[dev];
   size_t r = RoundSize(bytes);
   auto it = d.pool.find(r);
   if (it != d.pool.end()) {
@@ -182,6 +186,7 @@ void* Engine::Alloc(int dev, size_t bytes) {
   if (e != cudaSuccess) {
     cudaGetLastError();
     // release the cache and retry once
+    WaitAll();
     for (auto& kv : d.pool) cudaFree(kv.second);
     d.pool.clear();
     KV_CUDA(cudaMalloc(&p, r));
@@ -192,7 +197,7 @@ void* Engine::Alloc(int dev, size_t bytes) {
 
 void Engine::Free(int dev, void* p, size_t bytes) {
   if (p == nullptr || !inited_) return;
-  devs_[dev].pool.emplace(RoundSize(bytes), p);
+  mem_[dev].pool.emplace(RoundSize(bytes), p);
 }
 
 void* Engine::AllocPinned(size_t bytes) {
@@ -216,20 +221,20 @@ void Engine::FreePinned(void* p, size_t bytes) {
 
 size_t Engine::BytesAllocated(int dev) {
   Init();
-  return devs_[dev].bytes;
+  return mem_[dev].bytes;
 }
 
 int Engine::EnablePeerAccess(const std::vector<int>& devs) {
   Init();
   int enabled = 0;
   for (int a : devs) {
-    DeviceGuard g(a);
     for (int b : devs) {
       if (a == b) continue;
       if (peer_[a][b]) {
         ++enabled;
         continue;
       }
+      DeviceGuard g(a);
       int can = 0;
       KV_CUDA(cudaDeviceCanAccessPeer(&can, a, b));
       if (!can) continue;

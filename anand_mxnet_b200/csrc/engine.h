@@ -4,14 +4,19 @@
 // every operation declares the arrays it reads and the arrays it mutates; the engine guarantees
 // read-after-write / write-after-read / write-after-write order per array, runs independent work
 // concurrently, and lets the caller block with WaitForVar / WaitForAll. The reference realises that
-// with worker threads that each own one CUDA stream and `cudaStreamSynchronize` after every op.
+// with worker threads that each own one CUDA stream (normal / priority / copy pools per GPU) and a
+// `cudaStreamSynchronize` after every op.
 //
-// B200 design: no worker threads and no per-op host synchronisation. Each GPU has ONE in-order
-// stream (the library's own, or a caller-provided one -- B200KVEngineSetStream -- so KVStore work
-// is ordered with the framework that produced the gradients). An array carries the tags
-// (device, sequence-number) of its last writer and last readers; same-device order is stream
-// order, cross-device order is a cudaStreamWaitEvent on an event recorded lazily -- only when some
-// other stream (or the host) actually has to wait. Host waits are cudaEventSynchronize.
+// B200 design: no worker threads and no per-op host synchronisation. Each GPU has THREE in-order
+// lanes -- compute (library-owned, or a caller-provided stream via B200KVEngineSetStream so KVStore
+// work is ordered with the framework that produced the gradients), host-to-device copies, and
+// device-to-host copies (the reference's kCopyToGPU / kCopyFromGPU pools) -- so PCIe traffic in
+// both directions overlaps the kernels. A lane is identified by a stream id:
+//     sid = dev (compute), kMaxDevices + dev (H2D), 2*kMaxDevices + dev (D2H).
+// An array carries the tags (sid, sequence-number) of its last writer and last readers; same-lane
+// order is stream order, cross-lane order is a cudaStreamWaitEvent on an event recorded lazily --
+// only when some other lane (or the host) actually has to wait. Host waits are
+// cudaEventSynchronize.
 #pragma once
 #include <map>
 #include <mutex>
@@ -21,15 +26,17 @@
 
 namespace b200kv {
 
+constexpr int kMaxStreams = 3 * kMaxDevices;
+
 struct Tag {
-  int dev = -1;      // -1: no pending device work
-  uint64_t seq = 0;  // position in that device's issue order
+  int dev = -1;      // stream id of the lane (-1: no pending device work)
+  uint64_t seq = 0;  // position in that lane's issue order
 };
 
 // Per-array dependency record (the reference's engine::Var).
 struct Var {
   Tag writer;
-  uint64_t reader_seq[kMaxDevices] = {0};  // last read issued on each device
+  uint64_t reader_seq[kMaxStreams] = {0};  // last read issued on each lane
   bool has_readers = false;
 };
 
@@ -37,26 +44,30 @@ class Engine {
  public:
   static Engine* Get();
 
+  static int DevOf(int sid) { return sid % kMaxDevices; }
+  static int CopyInLane(int dev) { return kMaxDevices + dev; }
+  static int CopyOutLane(int dev) { return 2 * kMaxDevices + dev; }
+
   int NumDevices();
-  cudaStream_t Stream(int dev);
-  void SetStream(int dev, cudaStream_t s);  // nullptr restores the library-owned stream
+  cudaStream_t Stream(int sid);
+  void SetStream(int dev, cudaStream_t s);  // compute lane; nullptr restores the library's stream
 
-  // ---- dependency protocol: call BeginRead/BeginWrite before enqueueing an op on `dev`, then
-  // Issue(dev) once the op is enqueued and Mark* the arrays with the returned sequence number.
-  void BeginRead(int dev, const Var& v);   // stream[dev] waits for v's writer
-  void BeginWrite(int dev, const Var& v);  // ... and for every reader
-  uint64_t Issue(int dev);
-  void MarkRead(int dev, uint64_t seq, Var* v);
-  void MarkWrite(int dev, uint64_t seq, Var* v);
+  // ---- dependency protocol: call BeginRead/BeginWrite before enqueueing an op on lane `sid`, then
+  // Issue(sid) once the op is enqueued and Mark* the arrays with the returned sequence number.
+  void BeginRead(int sid, const Var& v);   // lane waits for v's writer
+  void BeginWrite(int sid, const Var& v);  // ... and for every reader
+  uint64_t Issue(int sid);
+  void MarkRead(int sid, uint64_t seq, Var* v);
+  void MarkWrite(int sid, uint64_t seq, Var* v);
 
-  void StreamWait(int dev, Tag t);  // stream[dev] waits for device work `t`
+  void StreamWait(int sid, Tag t);  // lane `sid` waits for device work `t`
   void HostWait(Tag t);             // calling thread waits for device work `t`
   void WaitToRead(const Var& v);
   void WaitToWrite(const Var& v);
   void WaitAll();
-  // Full barrier among the streams of `devs`: everything issued so far on any of them completes
-  // before anything issued afterwards on any of them starts (2N event ops, not N^2).
-  void JoinStreams(const std::vector<int>& devs);
+  // Full barrier among lanes: everything issued so far on any of them completes before anything
+  // issued afterwards on any of them starts (2N event operations, not N^2).
+  void JoinStreams(const std::vector<int>& sids);
 
   // ---- memory (pooled: blocks are cached per device and size class, never returned to the driver
   // before shutdown; the reference's GPUPooledStorageManager plays the same role)
@@ -82,20 +93,24 @@ class Engine {
  private:
   Engine();
   void Init();
-  cudaEvent_t RecordLatest(int dev);
+  cudaEvent_t RecordLatest(int sid);
   static size_t RoundSize(size_t bytes);
 
-  struct Dev {
+  struct Lane {
     cudaStream_t own = nullptr, cur = nullptr;
     std::vector<cudaEvent_t> ring;
     size_t ring_pos = 0;
     cudaEvent_t latest = nullptr;
     uint64_t issued = 0, recorded = 0, completed = 0;
-    uint64_t waited[kMaxDevices] = {0};  // waited[e]: this stream already waits for e's seq <= value
+    uint64_t waited[kMaxStreams] = {0};  // waited[e]: this lane already waits for e's seq <= value
+  };
+  struct DevMem {
     std::multimap<size_t, void*> pool;
     size_t bytes = 0;
   };
-  std::vector<Dev> devs_;
+  std::vector<Lane> lanes_;
+  std::vector<DevMem> mem_;
+  int ndev_ = 0;
   std::multimap<size_t, void*> pinned_pool_;
   bool peer_[kMaxDevices][kMaxDevices] = {{false}};
   bool inited_ = false;

@@ -89,6 +89,29 @@ struct Plan {
   ~Plan();
 };
 
+// Everything one fused launch group needs at run time, computed once per distinct call signature:
+// placement done, state allocated, plan built, the arrays whose dependencies must be tracked, the
+// host<->device staging copies to issue around the launch.
+struct Prepared {
+  int opt_kind = kOptAssign;
+  int dtype = kFloat32;
+  bool is_push = false;
+  std::vector<DenseOp> ops;                              // device-side operands
+  std::vector<std::pair<NDArray, NDArray>> stage_in;     // (host source, device staging buffer)
+  std::vector<std::pair<NDArray, NDArray>> stage_out;    // (device staging buffer, host out)
+  std::vector<int> owners, parts;
+  std::shared_ptr<Plan> plan;
+  std::vector<float> hyper;                              // per key (lr, wd)
+  uint64_t hyper_version = 0;
+  DenseLaunch scalars;                                   // momentum / rescale / clip / betas
+};
+
+struct CachedCall {
+  std::vector<uint64_t> sig;       // keys + storage identities of every operand of the C call
+  std::vector<Prepared> launches;
+  uint64_t epoch = 0;
+};
+
 class KVStore {
  public:
   explicit KVStore(const std::string& type);
@@ -118,6 +141,7 @@ class KVStore {
   void SetOptimizer(const std::string& name,
                     const std::vector<std::pair<std::string, std::string>>& kw);
   OptConfig& opt() { return opt_; }
+  void TouchOpt() { ++opt_version_; }  // call after changing opt() scalars / multipliers
   NDArray GetOptimizerState(int key, int state_id);
   void SetOptimizerState(int key, int state_id, const NDArray& v);
   void Flush() {}
@@ -132,6 +156,15 @@ class KVStore {
 
   // dense machinery
   void ExecDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stripe = true);
+  void PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stripe,
+                    std::vector<Prepared>* out);
+  void RunPrepared(Prepared& p);
+  // call-level cache: a repeated C call (same keys, same arrays) skips grouping/validation/planning
+  bool CallSignature(int tag, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
+                     const std::vector<int>* okeys, const std::vector<NDArray>* outs,
+                     std::vector<uint64_t>* sig);
+  bool RunCachedCall(const std::vector<uint64_t>& sig);
+  void StoreCachedCall(const std::vector<uint64_t>& sig, std::vector<Prepared>&& launches);
   void ExecCallbackPush(KeyEntry& e, const std::vector<NDArray>& srcs);
   void EnsureOnDevice(KeyEntry& e, int dev);            // HOST -> WHOLE(dev)
   void EnsureStriped(KeyEntry& e);                      // WHOLE -> STRIPED(devset_)
@@ -165,6 +198,9 @@ class KVStore {
   void* updater_handle_ = nullptr;
   OptConfig opt_;
   std::unordered_map<uint64_t, std::shared_ptr<Plan>> plans_;
+  std::unordered_map<uint64_t, std::shared_ptr<CachedCall>> call_cache_;
+  uint64_t opt_version_ = 1;   // bumped whenever a hyper-parameter / multiplier changes
+  uint64_t layout_epoch_ = 1;  // bumped whenever placement / optimizer kind / updater changes
   std::string gc_type_ = "none";
   friend struct PlanBuilder;
 };

@@ -155,6 +155,7 @@ void KVStore::SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle) {
   updater_ = fn;
   str_updater_ = sfn;
   updater_handle_ = handle;
+  ++layout_epoch_;
   // an explicit updater replaces a previously fused optimizer (set_optimizer -> _set_updater)
   if (fn != nullptr) opt_.enabled = false;
 }
@@ -225,6 +226,8 @@ void KVStore::SetOptimizer(const std::string& name,
     o.num_update = std::max(o.num_update, opt_.num_update);
   }
   opt_ = o;
+  ++layout_epoch_;
+  ++opt_version_;
   updater_ = nullptr;
   str_updater_ = nullptr;
 }
@@ -303,6 +306,12 @@ void KVStore::Pull(const std::vector<int>& keys, const std::vector<NDArray>& out
 
 void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>& values,
                        const std::vector<int>* okeys, const std::vector<NDArray>* outs) {
+  // a repeated call (same keys, same arrays) replays its prepared launches
+  const bool callback_mode = updater_ != nullptr && !opt_.enabled;
+  std::vector<uint64_t> sig;
+  const bool cacheable = !callback_mode &&
+      CallSignature(opt_.enabled ? 100 + opt_.kind : 1, keys, values, okeys, outs, &sig);
+  if (cacheable && RunCachedCall(sig)) return;
   std::vector<int> uniq;
   std::vector<std::vector<NDArray>> grouped;
   GroupKVPairs(keys, values, &uniq, &grouped, [](int, const NDArray& nd) {
@@ -373,12 +382,18 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
     p.outs = ogrouped[i];
     pulls.push_back(p);
   }
-  if (!fused.empty()) ExecDense(fused, opt_.enabled ? opt_.kind : kOptAssign);
-  if (!pulls.empty()) ExecDense(pulls, kOptPullOnly);
+  std::vector<Prepared> launches;
+  PrepareDense(fused, opt_.enabled ? opt_.kind : kOptAssign, true, &launches);
+  PrepareDense(pulls, kOptPullOnly, true, &launches);
+  for (auto& p : launches) RunPrepared(p);
+  if (cacheable) StoreCachedCall(sig, std::move(launches));
 }
 
 void KVStore::PullImpl(const std::vector<int>& keys, const std::vector<NDArray>& outs,
                        bool ignore_sparse) {
+  std::vector<uint64_t> sig;
+  const bool cacheable = CallSignature(2, std::vector<int>(), std::vector<NDArray>(), &keys, &outs, &sig);
+  if (cacheable && RunCachedCall(sig)) return;
   std::vector<int> uniq;
   std::vector<std::vector<NDArray>> grouped;
   GroupKVPairs(keys, outs, &uniq, &grouped, [this, ignore_sparse](int key, const NDArray& nd) {
@@ -404,7 +419,10 @@ void KVStore::PullImpl(const std::vector<int>& keys, const std::vector<NDArray>&
     p.outs = grouped[i];
     pulls.push_back(p);
   }
-  if (!pulls.empty()) ExecDense(pulls, kOptPullOnly);
+  std::vector<Prepared> launches;
+  PrepareDense(pulls, kOptPullOnly, true, &launches);
+  for (auto& p : launches) RunPrepared(p);
+  if (cacheable) StoreCachedCall(sig, std::move(launches));
 }
 
 // =================================================================================================
@@ -420,6 +438,7 @@ void KVStore::SetDeviceSet(const std::vector<int>& devs) {
   }
   devset_ = devs;
   plans_.clear();
+  ++layout_epoch_;
   if (devs.size() > 1) {
     int enabled = Engine::Get()->EnablePeerAccess(devs);
     const int want = static_cast<int>(devs.size() * (devs.size() - 1));
@@ -502,6 +521,7 @@ void KVStore::EnsureWhole(KeyEntry& e, int dev) {
   }
   e.striped = false;
   e.home = dev;
+  ++layout_epoch_;
 }
 
 static NDArray ZeroState(const KeyEntry& e, int dev) {
@@ -548,7 +568,7 @@ NDArray KVStore::StageSrc(KeyEntry& e, size_t slot, const NDArray& host_src, int
   if (e.stage_src.size() <= slot) e.stage_src.resize(slot + 1);
   NDArray& st = e.stage_src[slot];
   if (st.is_none() || st.dev() != dev) st = NDArray(e.shape, Context::GPU(dev), e.dtype);
-  CopyFromTo(host_src, st);
+  (void)host_src;  // the H2D copy is issued every time the prepared launch runs
   return st;
 }
 
@@ -672,188 +692,6 @@ std::shared_ptr<Plan> KVStore::GetPlan(const std::vector<DenseOp>& ops, int opt_
   return plan;
 }
 
-void KVStore::ExecDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stripe) {
-  // one launch per key dtype (the kernel is specialised on the storage type)
-  std::map<int, std::vector<DenseOp>> by_dtype;
-  for (auto& op : ops) by_dtype[op.e->dtype].push_back(op);
-  if (by_dtype.size() > 1) {
-    for (auto& kv : by_dtype) ExecDense(kv.second, opt_kind, allow_stripe);
-    return;
-  }
-  Engine* eng = Engine::Get();
-  const int dtype = ops[0].e->dtype;
-  const bool is_push = opt_kind != kOptPullOnly;
-
-  // ---- 1. device set: a push with values on >= 2 GPUs (re)defines the stripe owners
-  if (is_push && allow_stripe) {
-    std::vector<int> devs;
-    for (auto& s : ops[0].srcs) {
-      if (s.on_gpu() && std::find(devs.begin(), devs.end(), s.dev()) == devs.end()) devs.push_back(s.dev());
-    }
-    if (devs.size() >= 2) SetDeviceSet(devs);
-  }
-  // ---- 2. placement of every key, staging of host-resident operands
-  std::set<int> owner_set, part_set;
-  for (auto& op : ops) {
-    KeyEntry& e = *op.e;
-    std::vector<int> sdev;
-    for (auto& s : op.srcs) {
-      if (s.on_gpu() && std::find(sdev.begin(), sdev.end(), s.dev()) == sdev.end()) sdev.push_back(s.dev());
-    }
-    if (is_push && allow_stripe && sdev.size() >= 2) {
-      KV_CHECK(sdev == devset_) << "key " << e.key << ": values live on a different GPU list than "
-                                << "the other keys of this push";
-      EnsureStriped(e);
-    } else if (!e.striped && e.home < 0) {
-      int pick = -1;
-      for (auto& s : op.srcs) if (pick < 0 && s.on_gpu()) pick = s.dev();
-      for (auto& o : op.outs) if (pick < 0 && o.on_gpu()) pick = o.dev();
-      if (pick < 0) pick = devset_.empty() ? 0 : devset_[0];
-      EnsureOnDevice(e, pick);
-    }
-    const int stage_dev = e.striped ? devset_[0] : e.home;
-    for (size_t i = 0; i < op.srcs.size(); ++i) {
-      if (!op.srcs[i].on_gpu()) op.srcs[i] = StageSrc(e, i, op.srcs[i], stage_dev);
-    }
-    if (e.striped) {
-      for (int d : devset_) owner_set.insert(d);
-    } else {
-      owner_set.insert(e.home);
-    }
-  }
-  // outs: remember the host arrays, substitute device staging buffers
-  struct HostOut { NDArray host, stage; };
-  std::vector<HostOut> host_outs;
-  for (auto& op : ops) {
-    KeyEntry& e = *op.e;
-    const int stage_dev = e.striped ? devset_[0] : e.home;
-    for (size_t i = 0; i < op.outs.size(); ++i) {
-      KV_CHECK_EQ(op.outs[i].Size(), e.size) << "pull: shape mismatch for key " << e.key;
-      KV_CHECK_EQ(op.outs[i].dtype(), e.dtype) << "pull: dtype mismatch for key " << e.key;
-      if (!op.outs[i].on_gpu()) {
-        HostOut h{op.outs[i], StageOut(e, i, op.outs[i], stage_dev)};
-        op.outs[i] = h.stage;
-        host_outs.push_back(h);
-      }
-    }
-    KV_CHECK(op.outs.size() <= static_cast<size_t>(kMaxDst)) << "at most " << kMaxDst << " outs per key";
-  }
-  // all striped or all whole-on-one-owner per launch group: split if mixed
-  {
-    std::vector<DenseOp> striped_ops, whole_ops;
-    for (auto& op : ops) (op.e->striped ? striped_ops : whole_ops).push_back(op);
-    std::map<int, std::vector<DenseOp>> by_home;
-    for (auto& op : whole_ops) by_home[op.e->home].push_back(op);
-    const size_t groups = (striped_ops.empty() ? 0 : 1) + by_home.size();
-    if (groups > 1) {
-      // host outs were already substituted; finish them after the sub-launches
-      if (!striped_ops.empty()) ExecDense(striped_ops, opt_kind, allow_stripe);
-      for (auto& kv : by_home) ExecDense(kv.second, opt_kind, allow_stripe);
-      for (auto& h : host_outs) CopyFromTo(h.stage, h.host);
-      return;
-    }
-  }
-  std::vector<int> owners;
-  if (ops[0].e->striped) owners = devset_;
-  else owners = {ops[0].e->home};
-
-  // ---- 3. optimizer bookkeeping: update counts first, then per-key (lr, wd)
-  if (is_push && opt_.enabled && (opt_kind == kOptSGD || opt_kind == kOptAdam)) {
-    for (auto& op : ops) {  // Optimizer._update_count (optimizer.py:412-430)
-      auto it = opt_.count.find(op.e->key);
-      int c = (it == opt_.count.end() ? opt_.begin_num_update : it->second) + 1;
-      opt_.count[op.e->key] = c;
-      opt_.num_update = std::max(opt_.num_update, c);
-    }
-  }
-  for (auto& op : ops) {
-    for (int d : owners) StateOn(*op.e, d, opt_kind);
-  }
-  std::shared_ptr<Plan> plan = GetPlan(ops, opt_kind, owners, ops[0].e->striped);
-
-  // ---- 4. dependencies
-  for (int d : owners) part_set.insert(d);
-  for (auto& op : ops) {
-    for (auto& s : op.srcs) part_set.insert(s.dev());
-    for (auto& o : op.outs) part_set.insert(o.dev());
-  }
-  std::vector<int> parts(part_set.begin(), part_set.end());
-  if (parts.size() > 1) {
-    int enabled = eng->EnablePeerAccess(parts);
-    KV_CHECK_EQ(enabled, static_cast<int>(parts.size() * (parts.size() - 1)))
-        << "GPU peer access is not available between all participating devices";
-  }
-  for (auto& op : ops) {
-    for (auto& s : op.srcs) eng->BeginRead(s.dev(), *s.var());
-    for (auto& o : op.outs) eng->BeginWrite(o.dev(), *o.var());
-    for (int d : owners) {
-      DevState& s = op.e->dev[d];
-      if (is_push) eng->BeginWrite(d, *s.w.var()); else eng->BeginRead(d, *s.w.var());
-    }
-  }
-  if (parts.size() > 1) eng->JoinStreams(parts);
-
-  // ---- 5. launch, one kernel per owner
-  DenseLaunch L;
-  L.max_src = plan->max_src;
-  L.dtype = dtype;
-  L.opt = opt_kind;
-  L.order = order_local_ ? kOrderLocal : kOrderDevice;
-  if (opt_kind == kOptSGD) {
-    // SGD._update_impl (optimizer.py:618-624): momentum only if > 0, clip only if truthy
-    L.momentum = opt_.momentum > 0 ? ScalarParam(opt_.momentum) : 0.f;
-    L.rescale = ScalarParam(opt_.rescale);
-    L.clip = opt_.clip != 0.0 ? ScalarParam(opt_.clip) : -1.f;
-  } else if (opt_kind == kOptAdam) {
-    L.rescale = ScalarParam(opt_.rescale);
-    L.clip = opt_.clip != 0.0 ? ScalarParam(opt_.clip) : -1.f;
-    L.beta1 = ScalarParam(opt_.beta1);
-    L.beta2 = ScalarParam(opt_.beta2);
-    L.eps = ScalarParam(opt_.eps);
-  } else if (opt_kind == kOptTest) {
-    L.rescale = ScalarParam(opt_.rescale);
-  }
-  std::vector<float> hyper(ops.size() * 2);
-  for (size_t k = 0; k < ops.size(); ++k) KeyHyper(*ops[k].e, opt_kind, &hyper[2 * k], &hyper[2 * k + 1]);
-  for (auto& p : plan->per_dev) {
-    DeviceGuard g(p.dev);
-    cudaStream_t st = eng->Stream(p.dev);
-    if (p.hyper != hyper) {
-      KV_CUDA(cudaMemcpyAsync(p.d_hyper, hyper.data(), hyper.size() * sizeof(float),
-                              cudaMemcpyHostToDevice, st));
-      p.hyper = hyper;
-    }
-    if (p.n_chunks == 0) continue;
-    L.keys = static_cast<const KeyDesc*>(p.d_keys);
-    L.chunks = static_cast<const ChunkDesc*>(p.d_chunks);
-    L.hyper = static_cast<const float*>(p.d_hyper);
-    L.n_chunks = p.n_chunks;
-    LaunchDenseFused(L, st);
-    eng->CountLaunch("dense_fused", plan->algorithmic_bytes / plan->per_dev.size());
-  }
-  if (parts.size() > 1) eng->JoinStreams(parts);
-
-  // ---- 6. mark results
-  std::map<int, uint64_t> seq;
-  for (int d : parts) seq[d] = eng->Issue(d);
-  for (auto& op : ops) {
-    for (auto& s : op.srcs) eng->MarkRead(s.dev(), seq[s.dev()], s.var());
-    for (auto& o : op.outs) eng->MarkWrite(o.dev(), seq[o.dev()], o.var());
-    for (int d : owners) {
-      DevState& s = op.e->dev[d];
-      if (is_push) {
-        eng->MarkWrite(d, seq[d], s.w.var());
-        if (!s.w32.is_none()) eng->MarkWrite(d, seq[d], s.w32.var());
-        if (!s.s1.is_none()) eng->MarkWrite(d, seq[d], s.s1.var());
-        if (!s.s2.is_none()) eng->MarkWrite(d, seq[d], s.s2.var());
-      } else {
-        eng->MarkRead(d, seq[d], s.w.var());
-      }
-    }
-  }
-  for (auto& h : host_outs) CopyFromTo(h.stage, h.host);
-}
-
 // =================================================================================================
 // updater-callback path (kvstore_local.h:217-236): reduce, then call back into the host language
 // =================================================================================================
@@ -934,6 +772,7 @@ void KVStore::SetOptimizerState(int key, int state_id, const NDArray& v) {
   if (a->is_none()) *a = NDArray(e.shape, Context::GPU(dev), kFloat32);
   CopyFromTo(v.Reshaped(e.shape), *a);
   plans_.clear();
+  ++layout_epoch_;
 }
 
 std::string KVStore::DescribePlan(const std::vector<int>& keys, int num_devices) {

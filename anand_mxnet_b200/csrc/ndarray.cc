@@ -103,8 +103,9 @@ NDArray NDArray::DataView() const {
   NDArray v = *this;
   v.stype_ = kDefaultStorage;
   if (stype_ == kRowSparseStorage) {
-    v.shape_ = shape_;
-    v.shape_[0] = st_->nnr;
+    std::vector<int64_t> s = shape_.get();
+    s[0] = st_->nnr;
+    v.shape_ = s;
   }
   return v;
 }
@@ -114,7 +115,7 @@ NDArray NDArray::AuxView() const {
   NDArray v = *this;
   v.stype_ = kDefaultStorage;
   v.dtype_ = kInt64;
-  v.shape_ = {st_->nnr};
+  v.shape_ = std::vector<int64_t>{st_->nnr};
   v.aux_view_ = true;
   return v;
 }
@@ -147,7 +148,7 @@ NDArray NDArray::FromDLPack(DLManagedTensorABI* t, bool transient) {
   KV_CHECK(dt >= 0) << "unsupported DLPack dtype code " << int(d.dtype.code) << " bits "
                     << int(d.dtype.bits);
   a.dtype_ = dt;
-  a.shape_.assign(d.shape, d.shape + d.ndim);
+  a.shape_ = std::vector<int64_t>(d.shape, d.shape + d.ndim);
   if (d.strides != nullptr) {  // must be compact row-major
     int64_t expect = 1;
     for (int i = d.ndim - 1; i >= 0; --i) {
@@ -183,20 +184,25 @@ void RawCopy(void* dst, Context dctx, Var* dvar, const void* src, Context sctx, 
     std::memcpy(dst, src, bytes);
     return;
   }
-  // the copy runs on the destination GPU's stream (or the source's for device -> host)
-  const int dev = dctx.is_gpu() ? dctx.dev_id : sctx.dev_id;
-  cudaStream_t s = e->Stream(dev);
-  e->BeginRead(dev, *svar);
-  e->BeginWrite(dev, *dvar);
-  DeviceGuard g(dev);
+  // device<->device copies run on the destination GPU's compute lane; host->device and
+  // device->host copies on that GPU's dedicated copy lanes, so both PCIe directions overlap the
+  // kernels (the reference's kCopyToGPU / kCopyFromGPU worker pools)
+  int lane;
+  if (dctx.is_gpu() && sctx.is_gpu()) lane = dctx.dev_id;
+  else if (dctx.is_gpu()) lane = Engine::CopyInLane(dctx.dev_id);
+  else lane = Engine::CopyOutLane(sctx.dev_id);
+  cudaStream_t s = e->Stream(lane);
+  e->BeginRead(lane, *svar);
+  e->BeginWrite(lane, *dvar);
+  DeviceGuard g(Engine::DevOf(lane));
   if (dctx.is_gpu() && sctx.is_gpu() && dctx.dev_id != sctx.dev_id) {
     KV_CUDA(cudaMemcpyPeerAsync(dst, dctx.dev_id, src, sctx.dev_id, bytes, s));
   } else {
     KV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
   }
-  uint64_t seq = e->Issue(dev);
-  e->MarkRead(dev, seq, svar);
-  e->MarkWrite(dev, seq, dvar);
+  uint64_t seq = e->Issue(lane);
+  e->MarkRead(lane, seq, svar);
+  e->MarkWrite(lane, seq, dvar);
 }
 
 void CopyFromTo(const NDArray& from, const NDArray& to) {

@@ -37,6 +37,29 @@ struct Storage {
   ~Storage();
 };
 
+// Immutable shape shared between handle copies: copying an NDArray (the C API does it for every
+// operand of every call) must not allocate.
+class SharedShape {
+ public:
+  SharedShape() : p_(Empty()) {}
+  SharedShape(const std::vector<int64_t>& v)  // NOLINT(runtime/explicit)
+      : p_(std::make_shared<const std::vector<int64_t>>(v)) {}
+  SharedShape& operator=(const std::vector<int64_t>& v) {
+    p_ = std::make_shared<const std::vector<int64_t>>(v);
+    return *this;
+  }
+  operator const std::vector<int64_t>&() const { return *p_; }  // NOLINT(runtime/explicit)
+  const std::vector<int64_t>& get() const { return *p_; }
+
+ private:
+  static const std::shared_ptr<const std::vector<int64_t>>& Empty() {
+    static const auto* e = new std::shared_ptr<const std::vector<int64_t>>(
+        std::make_shared<const std::vector<int64_t>>());
+    return *e;
+  }
+  std::shared_ptr<const std::vector<int64_t>> p_;
+};
+
 class NDArray {
  public:
   NDArray() {}
@@ -47,7 +70,7 @@ class NDArray {
   static NDArray FromDLPack(DLManagedTensorABI* t, bool transient);
 
   bool is_none() const { return st_ == nullptr; }
-  const std::vector<int64_t>& shape() const { return shape_; }
+  const std::vector<int64_t>& shape() const { return shape_.get(); }
   int dtype() const { return dtype_; }
   int stype() const { return stype_; }
   Context ctx() const { return st_ ? st_->ctx : Context(); }
@@ -79,7 +102,7 @@ class NDArray {
 
  private:
   std::shared_ptr<Storage> st_;
-  std::vector<int64_t> shape_;
+  SharedShape shape_;
   int dtype_ = kFloat32;
   int stype_ = kDefaultStorage;
   size_t byte_offset_ = 0;

@@ -68,11 +68,12 @@ def _invoke(op_name, inputs, out=None, **kwargs):
 
 
 class NDArray(object):
-    __slots__ = ['handle', '_keepalive', '__weakref__']
+    __slots__ = ['handle', '_hv', '_keepalive', '__weakref__']
 
     def __init__(self, handle):
         assert isinstance(handle, ctypes.c_void_p)
         self.handle = handle
+        self._hv = handle.value      # plain int: list marshalling reads it without ctypes hops
         self._keepalive = None
 
     def __del__(self):
@@ -259,6 +260,7 @@ class NDArray(object):
     def __setstate__(self, state):
         a = array(state['np'], Context(*state['ctx']), state['dtype'])
         self.handle = a.handle
+        self._hv = a.handle.value
         self._keepalive = None
         a.handle = ctypes.c_void_p(None)
 

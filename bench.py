@@ -150,7 +150,34 @@ class ClockSampler(object):
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline
 # ------------------------------------------------------------------------------------------------
-def cpu_kvstore_step_fn(workload, n_src):
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def best_cpu_threads(workload, n_src):
+    """The reference sizes its CPU kernels' OpenMP team from the visible cores
+    (engine::OpenMP::GetRecommendedOMPThreadCount); on a big shared host that is far from the
+    fastest choice for 157 mostly-small tensors, so the baseline gets the BEST team size from a
+    short probe (one step each, ascending, stop once clearly past the optimum)."""
+    best, best_t = 1, float("inf")
+    cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, host_cores()) if c <= host_cores()})
+    for c in cands:
+        step, _, _ = cpu_kvstore_step_fn(workload, n_src, c)
+        step()
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+        elif dt > 2.0 * best_t:
+            break
+    return best
+
+
+def cpu_kvstore_step_fn(workload, n_src, threads=None):
     """One kvstore('local') step on host cores: CommCPU reduce of n_src gradient buffers per key
     (comm.h:357-410), then the optimizer kernel per key (one updater call per key, OMP inside, as
     the reference's callback path does), then the copy to n_src outputs (comm.h:209-224)."""
@@ -158,7 +185,7 @@ def cpu_kvstore_step_fn(workload, n_src):
     import kvoracle as K
     ref = K.ref()
     o = K.get_oracle()
-    cores = os.cpu_count() or 1
+    cores = threads or host_cores()
     shapes = WORKLOADS[workload]["shapes"]()
     rng = np.random.default_rng(0xB200)
     sizes = [int(np.prod(s)) for s in shapes]
@@ -206,7 +233,7 @@ def cpu_kvstore_step_fn(workload, n_src):
 def run_reference(args):
     """The reference arm: the reference's own CPU implementation of the path on this box's cores."""
     n_src = max(1, args.gpus)
-    step, kind, cores = cpu_kvstore_step_fn(args.workload, n_src)
+    step, kind, cores = cpu_kvstore_step_fn(args.workload, n_src, best_cpu_threads(args.workload, n_src))
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -224,7 +251,7 @@ def run_reference(args):
             "config": {"workload": WORKLOADS[args.workload]["desc"], "store": "kvstore('local') on CPU",
                        "values_per_key": n_src},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": sample},
+                             "sample": sample, "host_cores_visible": host_cores()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -259,22 +286,40 @@ def run_single_gpu(args):
     n_elem = sum(int(np.prod(s)) for s in shapes)
     gen = torch.Generator(device=dev)
     gen.manual_seed(0xB200)
+    sizes = [int(np.prod(s)) for s in shapes]
+    offs = np.concatenate([[0], np.cumsum([(n + 127) // 128 * 128 for n in sizes])]).astype(np.int64)
 
-    def urand(s):
-        return torch.rand(s, device=dev, generator=gen) * 2 - 1
+    def flat_views(fill):
+        """one flat buffer per role (three torch kernels in total), one 512-byte aligned view per
+        tensor -- the arrays stay separate NDArrays, exactly what a framework hands the store"""
+        flat = torch.empty(int(offs[-1]), device=dev)
+        if fill:
+            flat.uniform_(-1, 1, generator=gen)
+        return flat, [flat[int(offs[i]):int(offs[i]) + sizes[i]].view(shapes[i]) for i in range(len(shapes))]
 
     # ---- device-resident arm
     kv = mx.kv.create("device")
-    kv.init(keys, [mx.nd.from_torch(urand(s)) for s in shapes])
+    _w_flat, w_views = flat_views(True)
+    kv.init(keys, [mx.nd.from_torch(t) for t in w_views])
     kv.set_optimizer(make_optimizer(mx, args.workload, 1))
-    grads_t = [urand(s) for s in shapes]
-    outs_t = [torch.empty(s, device=dev) for s in shapes]
+    _g_flat, grads_t = flat_views(True)
+    _o_flat, outs_t = flat_views(False)
     grads = [mx.nd.from_torch(t) for t in grads_t]
     outs = [mx.nd.from_torch(t) for t in outs_t]
     torch.cuda.synchronize()
+    kv.pushpull(keys, grads, out=outs)      # python front-end once: hands lr / multipliers over
+    # the timed call is the C-ABI entry point itself with prebuilt argument arrays, as a compiled
+    # host would issue it; the python front-end's per-call marshalling is reported separately
+    from anand_mxnet_b200.kvstore.base import _ctype_key_value
+    ckeys, cvals, _ = _ctype_key_value(keys, grads)
+    _, couts, _ = _ctype_key_value(keys, outs)
+    lib, handle, nkeys = mx.base._LIB, kv.handle, ctypes.c_uint(len(keys))
+    zero = ctypes.c_int(0)
 
     def step():
-        kv.pushpull(keys, grads, out=outs)
+        rc = lib.MXKVStorePushPull(handle, nkeys, ckeys, nkeys, ckeys, cvals, couts, zero)
+        if rc != 0:
+            raise RuntimeError(lib.MXGetLastError().decode())
 
     for _ in range(args.warmup):
         step()
@@ -308,6 +353,25 @@ def run_single_gpu(args):
                 else "dense_fused_kernel<float,1,Adam>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_kernel}
 
+    # ---- the same loop through the python front-end (kv.pushpull): includes ctypes marshalling
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    th = time.perf_counter()
+    p0.record(stream)
+    for _ in range(args.steps):
+        kv.pushpull(keys, grads, out=outs)
+    p1.record(stream)
+    host_py_us = (time.perf_counter() - th) / args.steps * 1e6
+    torch.cuda.synchronize()
+    py_ms = p0.elapsed_time(p1) / args.steps
+    th = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    host_c_us = (time.perf_counter() - th) / args.steps * 1e6
+    torch.cuda.synchronize()
+    frontends = {"python_api_GBps": alg / (py_ms * 1e-3) / 1e9, "python_api_ms_per_step": py_ms,
+                 "python_api_host_us_per_call": host_py_us, "c_abi_host_us_per_call": host_c_us}
+
     # ---- end-to-end arm: same C-ABI call, HOST (pinned) gradient and weight buffers
     kv2 = mx.kv.create("device")
     kv2.init(keys, [mx.nd.array(np.zeros(s, np.float32), mx.cpu()) for s in shapes])
@@ -334,7 +398,7 @@ def run_single_gpu(args):
     # ---- cpu baseline (bounded sample, rank 0, N=1)
     cpu = None
     if not args.no_cpu_baseline:
-        cstep, kind, cores = cpu_kvstore_step_fn(args.workload, 1)
+        cstep, kind, cores = cpu_kvstore_step_fn(args.workload, 1, best_cpu_threads(args.workload, 1))
         cstep()
         t0 = time.perf_counter()
         n = 0
@@ -349,11 +413,12 @@ def run_single_gpu(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload]["desc"], "store": "kvstore('device')",
-                       "call": "one grouped MXKVStorePushPull over all keys per step",
+                       "call": "one grouped MXKVStorePushPull (C ABI, prebuilt argument arrays) over "
+                               "all keys per step; python front-end timing under 'frontends'",
                        "l2": "working set %.0f MB per step > 126 MB L2, no flush needed" % (alg / 1e6),
                        "optimizer": SGD_KW if WORKLOADS[args.workload]["opt"] == "sgd" else ADAM_KW},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks}
+            "clocks": clocks, "frontends": frontends}
     print(json.dumps(line))
 
 
