@@ -18,6 +18,7 @@ from . import ndarray as nd
 from . import optimizer
 from . import kvstore
 from . import kvstore as kv
+from . import dist
 from .kvstore import KVStore, KVStoreBase, create as _create_kvstore
 
 __version__ = "0.1.0"

@@ -89,8 +89,17 @@ def last_kernel_info():
 
 
 def set_stream(dev_id, cuda_stream):
-    """Issue all library work for GPU `dev_id` on a caller-owned cudaStream_t (int handle or 0)."""
-    check_call(_LIB.B200KVEngineSetStream(ctypes.c_int(dev_id), ctypes.c_void_p(cuda_stream or None)))
+    """Issue all library work for GPU `dev_id` on a caller-owned cudaStream_t (integer handle, e.g.
+    torch.cuda.current_stream().cuda_stream). 0 means the CUDA legacy default stream -- what torch
+    reports for its default stream -- and is passed as cudaStreamLegacy; None restores the
+    library's own stream."""
+    if cuda_stream is None:
+        h = None
+    elif cuda_stream == 0:
+        h = 1  # cudaStreamLegacy
+    else:
+        h = cuda_stream
+    check_call(_LIB.B200KVEngineSetStream(ctypes.c_int(dev_id), ctypes.c_void_p(h)))
 
 
 def get_stream(dev_id):

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "group.h"
 #include "kvstore.h"
 #include "ndarray.h"
 #include "ops.h"
@@ -646,12 +647,30 @@ int B200KVEngineGetStream(int dev_id, void** cuda_stream) {
   API_END();
 }
 
-int B200KVGroupInit(int, int, int, B200KVAllGatherFn, void*) {
-  g_last_error = "B200KVGroupInit: multi-process peer groups are not built into this library build";
-  return -1;
+int B200KVGroupInit(int rank, int world_size, int dev_id, B200KVAllGatherFn allgather, void* ctx) {
+  API_BEGIN();
+  PeerGroup::Init(rank, world_size, dev_id, allgather, ctx);
+  API_END();
 }
 
-int B200KVGroupDestroy(void) { return 0; }
+int B200KVGroupDestroy(void) {
+  API_BEGIN();
+  PeerGroup::Destroy();
+  API_END();
+}
+
+// host-only hook: the rank-major int64 exchange plan building uses (runs under gloo on CPU)
+B200KV_DLL int B200KVTestGatherI64(int world, B200KVAllGatherFn allgather, void* ctx,
+                                   const int64_t* mine, int n, int64_t* out) {
+  try {
+    std::vector<int64_t> m(mine, mine + n);
+    std::vector<int64_t> all = GatherI64(allgather, ctx, world, m);
+    std::memcpy(out, all.data(), all.size() * sizeof(int64_t));
+  } catch (const std::exception& e) {
+    return HandleException(e);
+  }
+  return 0;
+}
 
 int B200KVGetKernelLaunchCount(uint64_t* out) {
   *out = Engine::Get()->launch_count;

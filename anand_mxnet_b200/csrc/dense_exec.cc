@@ -12,6 +12,7 @@
 #include <map>
 #include <set>
 
+#include "group.h"
 #include "kvstore.h"
 #include "scalar_parse.h"
 
@@ -89,6 +90,11 @@ void KVStore::ExecDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stri
 void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stripe,
                            std::vector<Prepared>* out) {
   if (ops.empty()) return;
+  if (dist_) {
+    (void)allow_stripe;
+    PrepareDenseGroup(ops, opt_kind, out);
+    return;
+  }
   const bool is_push = opt_kind != kOptPullOnly;
   // ---- 1. device set: a push with values on >= 2 GPUs (re)defines the stripe owners
   if (is_push && allow_stripe) {
@@ -255,7 +261,17 @@ void KVStore::RunPrepared(Prepared& P) {
                               cudaMemcpyHostToDevice, st));
       pd.hyper = P.hyper;
     }
-    if (pd.n_chunks == 0) continue;
+    if (pd.n_chunks == 0 && !P.group) continue;
+    if (P.group) {
+      // one rank per GPU: in-kernel start/end barriers on the IPC signal pads order the ranks
+      PeerGroup* g = PeerGroup::Get();
+      KV_CHECK(g != nullptr) << "the peer group was destroyed while a store still uses it";
+      L.signal_pads = g->d_pads();
+      L.counter = g->d_counter();
+      L.rank = g->rank();
+      L.world = g->world();
+      L.epoch = g->NextEpoch();
+    }
     L.keys = static_cast<const KeyDesc*>(pd.d_keys);
     L.chunks = static_cast<const ChunkDesc*>(pd.d_chunks);
     L.hyper = static_cast<const float*>(pd.d_hyper);

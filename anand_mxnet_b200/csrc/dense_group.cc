@@ -1,0 +1,185 @@
+// dense_group.cc -- the dense path when the store runs as one rank per GPU (group.h).
+//
+// Same fused kernel, different placement: the stripes of the store-global element space rotate over
+// RANKS; rank r reduces the stripes it owns reading every rank's gradient through IPC-mapped
+// pointers (its own included), updates them with its slice of the optimizer state, and writes the
+// new weights into every rank's pull targets. Plan building is collective (one all-gather of
+// arena offsets per distinct call signature); running a prepared launch involves no host
+// communication at all -- the kernel's start / end barriers order the ranks.
+#include <algorithm>
+#include <cstring>
+#include <map>
+
+#include "group.h"
+#include "kvstore.h"
+
+namespace b200kv {
+
+void PlanChunks(uint64_t goff, size_t size, uint32_t key_slot, int ndev, int owner_fixed,
+                std::vector<std::vector<ChunkDesc>>* per_slot);  // kvstore_core.cc
+
+namespace {
+constexpr int kMaxLocalOut = 2;   // pull targets per key per rank
+constexpr int kFields = 5 + kMaxLocalOut;
+uint64_t Mix(uint64_t h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+  return h;
+}
+}  // namespace
+
+void KVStore::PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::vector<Prepared>* out) {
+  PeerGroup* g = PeerGroup::Get();
+  KV_CHECK(g != nullptr);
+  const int dev = g->dev();
+  const bool is_push = opt_kind != kOptPullOnly;
+  std::map<int, Prepared> groups;  // by dtype
+  auto arena_copy = [&](const NDArray& a) { return a.on_gpu() && a.dev() == dev && g->InArena(a.data()); };
+  for (auto& op : ops) {
+    KeyEntry& e = *op.e;
+    KV_CHECK(op.srcs.size() <= 1)
+        << "one-rank-per-GPU store: push exactly one value per key on each rank (key " << e.key << ")";
+    KV_CHECK(op.outs.size() <= static_cast<size_t>(kMaxLocalOut))
+        << "one-rank-per-GPU store: at most " << kMaxLocalOut << " pull targets per key per rank";
+    if (e.home < 0) EnsureOnDevice(e, dev);
+    KV_CHECK_EQ(e.home, dev) << "key " << e.key << " lives on another GPU than this rank's";
+    Prepared& P = groups[e.dtype];
+    DenseOp dop = op;
+    for (size_t i = 0; i < dop.srcs.size(); ++i) {
+      KV_CHECK_EQ(dop.srcs[i].Size(), e.size) << "push: shape mismatch for key " << e.key;
+      if (!arena_copy(dop.srcs[i])) {  // not peer-addressable: stage through the IPC arena
+        NDArray st = StageSrc(e, i, dop.srcs[i], dev);
+        KV_CHECK(g->InArena(st.data())) << "IPC arena exhausted; raise B200KV_IPC_ARENA_MB";
+        P.stage_in.emplace_back(dop.srcs[i], st);
+        dop.srcs[i] = st;
+      }
+    }
+    for (size_t i = 0; i < dop.outs.size(); ++i) {
+      KV_CHECK_EQ(dop.outs[i].Size(), e.size) << "pull: shape mismatch for key " << e.key;
+      KV_CHECK_EQ(dop.outs[i].dtype(), e.dtype) << "pull: dtype mismatch for key " << e.key;
+      if (!arena_copy(dop.outs[i])) {
+        NDArray st = StageOut(e, i, dop.outs[i], dev);
+        KV_CHECK(g->InArena(st.data())) << "IPC arena exhausted; raise B200KV_IPC_ARENA_MB";
+        P.stage_out.emplace_back(st, dop.outs[i]);
+        dop.outs[i] = st;
+      }
+    }
+    P.ops.push_back(std::move(dop));
+  }
+  for (auto& kv : groups) {
+    Prepared& P = kv.second;
+    P.opt_kind = opt_kind;
+    P.dtype = kv.first;
+    P.is_push = is_push;
+    P.group = true;
+    P.owners = {dev};
+    P.parts = {dev};
+    for (auto& op : P.ops) StateOn(*op.e, dev, opt_kind);
+    P.plan = GetPlanGroup(P.ops, opt_kind);
+    out->push_back(std::move(P));
+  }
+}
+
+std::shared_ptr<Plan> KVStore::GetPlanGroup(const std::vector<DenseOp>& ops, int opt_kind) {
+  PeerGroup* g = PeerGroup::Get();
+  const int dev = g->dev(), W = g->world(), R = g->rank();
+  const bool is_push = opt_kind != kOptPullOnly;
+  uint64_t sig = Mix(0x6702, static_cast<uint64_t>(opt_kind) * 131 + W);
+  for (auto& op : ops) {
+    sig = Mix(sig, static_cast<uint64_t>(op.e->key));
+    for (auto& s : op.srcs) sig = Mix(sig, reinterpret_cast<uint64_t>(s.data()));
+    sig = Mix(sig, 0xabcdef);
+    for (auto& o : op.outs) sig = Mix(sig, reinterpret_cast<uint64_t>(o.data()));
+    DevState& s = op.e->dev[dev];
+    for (const NDArray* a : {&s.w, &s.s1, &s.s2, &s.w32}) {
+      sig = Mix(sig, reinterpret_cast<uint64_t>(a->is_none() ? nullptr : a->data()));
+    }
+  }
+  auto it = plans_.find(sig);
+  if (it != plans_.end()) return it->second;
+  if (plans_.size() > 256) plans_.clear();
+
+  // ---- collective: everybody's operand offsets inside its IPC arena
+  std::vector<int64_t> mine(ops.size() * kFields, -1);
+  for (size_t k = 0; k < ops.size(); ++k) {
+    const DenseOp& op = ops[k];
+    int64_t* f = &mine[k * kFields];
+    f[0] = op.e->key;
+    f[1] = static_cast<int64_t>(op.e->size);
+    f[2] = static_cast<int64_t>(op.e->goff);
+    f[3] = op.srcs.empty() ? -1 : g->OffsetOf(op.srcs[0].data());
+    f[4] = static_cast<int64_t>(op.outs.size());
+    for (size_t i = 0; i < op.outs.size(); ++i) f[5 + i] = g->OffsetOf(op.outs[i].data());
+  }
+  const std::vector<int64_t> all = g->AllGatherI64(mine);
+  auto field = [&](int r, size_t k, int i) { return all[(static_cast<size_t>(r) * ops.size() + k) * kFields + i]; };
+
+  auto plan = std::make_shared<Plan>();
+  plan->n_keys = static_cast<int>(ops.size());
+  plan->max_src = is_push ? W : 0;
+  std::vector<KeyDesc> kd(ops.size());
+  std::vector<std::vector<ChunkDesc>> chunks(W);
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  for (size_t k = 0; k < ops.size(); ++k) {
+    const DenseOp& op = ops[k];
+    KeyEntry& e = *op.e;
+    KeyDesc& K = kd[k];
+    std::memset(&K, 0, sizeof(K));
+    bool ok = true;
+    int n_out = 0;
+    for (int r = 0; r < W; ++r) {
+      KV_CHECK(field(r, k, 0) == e.key && field(r, k, 1) == static_cast<int64_t>(e.size) &&
+               field(r, k, 2) == static_cast<int64_t>(e.goff))
+          << "rank " << r << " issued a different call (key/size/order mismatch at position " << k
+          << "): every rank must init and push the same keys in the same order";
+      if (is_push) {
+        KV_CHECK(field(r, k, 3) >= 0) << "rank " << r << " pushed no value for key " << e.key;
+        K.src[r] = g->PeerPtr(r, field(r, k, 3));
+        ok = ok && aligned(K.src[r]);
+      }
+      for (int i = 0; i < field(r, k, 4); ++i) {
+        KV_CHECK(n_out < kMaxDst) << "too many pull targets across ranks for key " << e.key;
+        K.out[n_out] = g->PeerPtr(r, field(r, k, 5 + i));
+        ok = ok && aligned(K.out[n_out]);
+        ++n_out;
+      }
+    }
+    DevState& s = e.dev[dev];
+    const bool use_state = opt_kind == kOptSGD || opt_kind == kOptAdam;
+    K.w = s.w.data();
+    K.w32 = (use_state && !s.w32.is_none()) ? static_cast<float*>(s.w32.data()) : nullptr;
+    K.s1 = (use_state && !s.s1.is_none()) ? static_cast<float*>(s.s1.data()) : nullptr;
+    K.s2 = (opt_kind == kOptAdam && !s.s2.is_none()) ? static_cast<float*>(s.s2.data()) : nullptr;
+    ok = ok && aligned(K.w) && aligned(K.w32) && aligned(K.s1) && aligned(K.s2);
+    K.n_src = is_push ? W : 0;
+    K.n_out = n_out;
+    K.vec_ok = ok ? 1u : 0u;
+    PlanChunks(e.goff, e.size, static_cast<uint32_t>(k), W, W > 1 ? -1 : 0, &chunks);
+    // bus bytes per GPU, as tools/bandwidth/measure.py:137-138 counts them
+    plan->algorithmic_bytes += static_cast<uint64_t>(e.size) * DTypeSize(e.dtype) * 2 * (W - 1) / W;
+  }
+  Engine* eng = Engine::Get();
+  Plan::PerDev p;
+  p.dev = dev;
+  std::vector<ChunkDesc>& own = chunks[R];
+  p.n_chunks = static_cast<int>(own.size());
+  p.bytes_keys = ops.size() * sizeof(KeyDesc);
+  p.bytes_chunks = std::max<size_t>(own.size(), 1) * sizeof(ChunkDesc);
+  p.bytes_hyper = ops.size() * 2 * sizeof(float);
+  p.d_keys = eng->Alloc(dev, p.bytes_keys);
+  p.d_chunks = eng->Alloc(dev, p.bytes_chunks);
+  p.d_hyper = eng->Alloc(dev, p.bytes_hyper);
+  {
+    DeviceGuard guard(dev);
+    cudaStream_t st = eng->Stream(dev);
+    KV_CUDA(cudaMemcpyAsync(p.d_keys, kd.data(), p.bytes_keys, cudaMemcpyHostToDevice, st));
+    if (!own.empty()) {
+      KV_CUDA(cudaMemcpyAsync(p.d_chunks, own.data(), own.size() * sizeof(ChunkDesc),
+                              cudaMemcpyHostToDevice, st));
+    }
+  }
+  plan->per_dev.push_back(std::move(p));
+  plans_[sig] = plan;
+  return plan;
+}
+
+}  // namespace b200kv

@@ -182,12 +182,61 @@ struct KernelArgs {
   const float2* hyper;  // per key (lr, wd); re-uploaded only when a value changes
   int order;
   float momentum, rescale, clip, beta1, beta2, eps;
+  // one-rank-per-GPU launches (group.h): IPC-mapped signal pads of every rank, or null
+  uint32_t* const* pads;
+  uint32_t* counter;  // CTAs of this rank that have finished
+  int rank, world;
+  uint32_t epoch;
+  int n_chunks;
 };
+
+// ---- cross-process barrier on IPC-mapped signal pads ------------------------------------------
+// pad layout per rank: start flags [kMaxDevices], end flags [kMaxDevices], one 128-byte line each.
+// Rank r writes its epoch into slot r of EVERY peer's pad; it waits on its OWN pad (local memory
+// written remotely), so spinning never crosses NVLink.
+constexpr int kPadStrideK = 32;
+constexpr int kMaxDevK = 16;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// threads 0..world-1 of the calling CTA each handle one peer; `phase` 0 = start, 1 = end.
+__device__ __forceinline__ void peer_signal_and_wait(const KernelArgs& a, int phase, bool signal) {
+  const int t = threadIdx.x;
+  if (t < a.world && t != a.rank) {
+    const int base = phase * kMaxDevK * kPadStrideK;
+    if (signal) st_release_sys(a.pads[t] + base + a.rank * kPadStrideK, a.epoch);
+    const uint32_t* mine = a.pads[a.rank] + base + t * kPadStrideK;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - a.epoch) < 0) {
+      __nanosleep(64);
+      if (clock64() - t0 > 40000000000LL) {  // ~20 s at 2 GHz: a peer never launched
+        printf("b200kv: rank %d timed out waiting for rank %d (phase %d, epoch %u)\n", a.rank, t,
+               phase, a.epoch);
+        __trap();
+      }
+    }
+  }
+}
 
 template <typename T, int MAXSRC, int OPT>
 __global__ void __launch_bounds__(kThreads) dense_fused_kernel(const KernelArgs a) {
   constexpr int V = 16 / sizeof(T);
   __shared__ KeyDesc sk;
+  __shared__ uint32_t s_last;
+  if (a.pads != nullptr) {
+    // start barrier: a rank's kernel only starts after its stream produced its gradients, so
+    // "every peer has started" == "every peer's gradients (and pull targets) are ready"
+    peer_signal_and_wait(a, 0, blockIdx.x == 0);
+    __syncthreads();
+  }
+  if (static_cast<int>(blockIdx.x) < a.n_chunks) {
   const ChunkDesc c = a.chunks[blockIdx.x];
   {
     constexpr int NW = sizeof(KeyDesc) / 16;
@@ -208,12 +257,34 @@ __global__ void __launch_bounds__(kThreads) dense_fused_kernel(const KernelArgs 
   for (uint32_t e = nvec * V + threadIdx.x; e < c.len; e += kThreads) {
     process<T, MAXSRC, OPT, 1>(sk, c.off + e, n_src, n_out, a.order, h);
   }
+  }  // blockIdx.x < n_chunks
+  if (a.pads != nullptr) {
+    // end barrier: the LAST CTA of this rank to finish tells every peer "I have read your
+    // gradients and written your weights" and waits for the same from them; the kernel -- hence
+    // everything the stream runs after it -- completes only when all peers are done with us.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();  // this CTA's peer stores are visible system-wide ...
+      const uint32_t done = atomicAdd(a.counter, 1u);  // ... before it is counted as finished
+      s_last = (done == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence_system();
+      peer_signal_and_wait(a, 1, true);
+      __syncthreads();
+      if (threadIdx.x == 0) *a.counter = 0;  // ready for the next launch (stream-ordered)
+    }
+  }
 }
 
 template <typename T, int MAXSRC, int OPT>
 void launch_one(const DenseLaunch& p, cudaStream_t s) {
-  KernelArgs a{p.keys, p.chunks, reinterpret_cast<const float2*>(p.hyper), p.order, p.momentum, p.rescale, p.clip, p.beta1, p.beta2, p.eps};
-  dense_fused_kernel<T, MAXSRC, OPT><<<p.n_chunks, kThreads, 0, s>>>(a);
+  KernelArgs a{p.keys, p.chunks, reinterpret_cast<const float2*>(p.hyper), p.order, p.momentum,
+               p.rescale, p.clip, p.beta1, p.beta2, p.eps, p.signal_pads, p.counter, p.rank, p.world,
+               p.epoch, p.n_chunks};
+  const int grid = p.n_chunks > 0 ? p.n_chunks : 1;  // a rank with no chunk still joins the barriers
+  dense_fused_kernel<T, MAXSRC, OPT><<<grid, kThreads, 0, s>>>(a);
 }
 
 template <typename T, int OPT>
@@ -241,7 +312,7 @@ void launch_opt(const DenseLaunch& p, cudaStream_t s) {
 }  // namespace
 
 void LaunchDenseFused(const DenseLaunch& p, cudaStream_t stream) {
-  if (p.n_chunks <= 0) return;
+  if (p.n_chunks <= 0 && p.signal_pads == nullptr) return;
   KV_CHECK(p.max_src <= kMaxSrc) << "at most " << kMaxSrc << " values per key";
   switch (p.dtype) {
     case kFloat32: launch_opt<float>(p, stream); break;

@@ -3,6 +3,8 @@
 
 #include <algorithm>
 
+#include "group.h"
+
 namespace b200kv {
 
 Engine* Engine::Get() {
@@ -179,6 +181,13 @@ void* Engine::Alloc(int dev, size_t bytes) {
     void* p = it->second;
     d.pool.erase(it);
     return p;
+  }
+  if (PeerGroup* grp = PeerGroup::Get()) {
+    // one-rank-per-GPU mode: allocations come out of the IPC arena so peers can address them
+    if (grp->dev() == dev) {
+      void* ap = grp->ArenaAlloc(r);
+      if (ap != nullptr) return ap;
+    }
   }
   DeviceGuard g(dev);
   void* p = nullptr;

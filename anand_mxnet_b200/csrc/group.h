@@ -1,0 +1,79 @@
+// group.h -- one-process-per-GPU peer group: NVLink peer memory across processes through CUDA IPC.
+//
+// The reference is single-process (one process drives all GPUs, peer access by
+// cudaDeviceEnablePeerAccess, src/kvstore/comm.h:715-757). The B200 deployment model is one rank
+// per GPU (torchrun); the same fused kernel then reads the peers' gradients and writes the peers'
+// weights through IPC-mapped pointers:
+//   * every rank owns one IPC ARENA (a single cudaMalloc, exported once with cudaIpcGetMemHandle and
+//     mapped by every peer at group creation); the library's GPU allocations of that rank come out
+//     of the arena, so any NDArray created through the C ABI is addressable by every peer as
+//     peer_base[rank] + offset;
+//   * plan building is collective: ranks all-gather the arena offsets of their operands once per
+//     distinct call signature (host callback supplied by the launcher -- torch.distributed -- the
+//     library itself never opens a socket);
+//   * steady state has NO host-side communication: cross-rank ordering is an in-kernel barrier on
+//     IPC-mapped signal pads (st.release.sys / ld.acquire.sys), one at kernel start ("my gradients
+//     are ready") and one at the end ("I have finished reading yours and writing your weights").
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "common.h"
+
+extern "C" typedef int (*B200KVAllGatherFnC)(const void* send, void* recv, size_t nbytes, void* ctx);
+
+namespace b200kv {
+
+constexpr int kPadStride = 32;                         // uint32 slots per flag: one 128-byte line
+constexpr int kPadWords = 2 * kMaxDevices * kPadStride;  // start flags, then end flags
+
+class PeerGroup {
+ public:
+  static PeerGroup* Get();  // nullptr until Init()
+  static void Init(int rank, int world, int dev, B200KVAllGatherFnC fn, void* ctx);
+  static void Destroy();
+
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  int dev() const { return dev_; }
+
+  // gathers nbytes from every rank into recv[rank*nbytes ...]
+  void AllGather(const void* send, void* recv, size_t nbytes);
+  // gathers one int64 vector per rank (all the same length) -> [world][n] row-major
+  std::vector<int64_t> AllGatherI64(const std::vector<int64_t>& mine);
+
+  // ---- arena
+  void* ArenaAlloc(size_t bytes);  // bump allocation, 512-byte aligned; nullptr when exhausted
+  bool InArena(const void* p) const {
+    return p >= arena_ && p < static_cast<const char*>(arena_) + arena_bytes_;
+  }
+  int64_t OffsetOf(const void* p) const {
+    return static_cast<const char*>(p) - static_cast<const char*>(arena_);
+  }
+  void* PeerPtr(int peer, int64_t offset) const { return static_cast<char*>(peer_base_[peer]) + offset; }
+
+  // ---- in-kernel barrier state
+  uint32_t* const* d_pads() const { return d_pads_; }  // device array [world] of pad pointers
+  uint32_t* d_counter() const { return d_counter_; }   // "CTAs finished" counter of this rank
+  uint32_t NextEpoch() { return ++epoch_; }
+
+ private:
+  PeerGroup() {}
+  int rank_ = 0, world_ = 1, dev_ = 0;
+  B200KVAllGatherFnC fn_ = nullptr;
+  void* ctx_ = nullptr;
+  void* arena_ = nullptr;
+  size_t arena_bytes_ = 0, arena_used_ = 0;
+  void* peer_base_[kMaxDevices] = {nullptr};
+  uint32_t* pads_[kMaxDevices] = {nullptr};
+  uint32_t** d_pads_ = nullptr;
+  uint32_t* d_counter_ = nullptr;
+  uint32_t epoch_ = 0;
+};
+
+// Pure host logic, testable without a GPU: rank-major gather of equal-length int64 vectors through
+// the launcher's all-gather callback.
+std::vector<int64_t> GatherI64(B200KVAllGatherFnC fn, void* ctx, int world,
+                               const std::vector<int64_t>& mine);
+
+}  // namespace b200kv

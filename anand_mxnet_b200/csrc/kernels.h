@@ -64,6 +64,7 @@ struct DenseLaunch {
   float momentum = 0.f, rescale = 1.f, clip = -1.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
   // cross-process launches (one rank per GPU): signal pads for the in-kernel start/end barriers
   uint32_t* const* signal_pads = nullptr;  // device array [world] of peer-mapped pads, or null
+  uint32_t* counter = nullptr;             // this rank's finished-CTA counter
   int rank = 0, world = 1;
   uint32_t epoch = 0;
 };

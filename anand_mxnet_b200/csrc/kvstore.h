@@ -96,6 +96,7 @@ struct Prepared {
   int opt_kind = kOptAssign;
   int dtype = kFloat32;
   bool is_push = false;
+  bool group = false;                                    // one-rank-per-GPU launch (group.h)
   std::vector<DenseOp> ops;                              // device-side operands
   std::vector<std::pair<NDArray, NDArray>> stage_in;     // (host source, device staging buffer)
   std::vector<std::pair<NDArray, NDArray>> stage_out;    // (device staging buffer, host out)
@@ -118,8 +119,8 @@ class KVStore {
   ~KVStore();
 
   const std::string& type() const { return type_; }
-  int rank() const { return 0; }
-  int group_size() const { return 1; }
+  int rank() const { return rank_; }              // 0 / 1 unless created inside a peer group
+  int group_size() const { return group_size_; }
 
   void Init(const std::vector<int>& keys, const std::vector<NDArray>& values);
   void InitStr(const std::vector<std::string>& keys, const std::vector<NDArray>& values);
@@ -159,6 +160,8 @@ class KVStore {
   void PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stripe,
                     std::vector<Prepared>* out);
   void RunPrepared(Prepared& p);
+  void PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::vector<Prepared>* out);
+  std::shared_ptr<Plan> GetPlanGroup(const std::vector<DenseOp>& ops, int opt_kind);
   // call-level cache: a repeated C call (same keys, same arrays) skips grouping/validation/planning
   bool CallSignature(int tag, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
                      const std::vector<int>* okeys, const std::vector<NDArray>* outs,
@@ -184,6 +187,8 @@ class KVStore {
   NDArray UniqueRowIds(const NDArray& row_ids, int dev, int64_t* count);
 
   std::string type_;
+  bool dist_ = false;         // created inside a one-rank-per-GPU peer group
+  int rank_ = 0, group_size_ = 1;
   bool order_local_ = true;   // 'local' => CommCPU association, 'device' => left fold
   int key_type_ = -1;         // -1 undefined, 0 string, 1 int (kvstore_local.h:60-64)
   std::unordered_map<int, std::unique_ptr<KeyEntry>> local_;

@@ -8,6 +8,7 @@
 #include <iostream>
 #include <set>
 
+#include "group.h"
 #include "scalar_parse.h"
 
 namespace b200kv {
@@ -65,6 +66,13 @@ KVStore::KVStore(const std::string& type) : type_(type) {
       << "library (single-node 'local' / 'device' / 'nccl' only)";
   order_local_ = !(t.find("device") != std::string::npos || t.find("nccl") != std::string::npos);
   Engine::Get()->NumDevices();  // fails loudly when there is no GPU
+  if (PeerGroup* g = PeerGroup::Get()) {
+    // one rank per GPU: this store is one worker of a group (the role dist_device_sync plays in
+    // the reference, without servers: the ranks reduce among themselves over NVLink)
+    dist_ = g->world() > 1;
+    rank_ = g->rank();
+    group_size_ = g->world();
+  }
 }
 
 KVStore::~KVStore() {
@@ -345,6 +353,7 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
     pushed.insert(e.key);
     if (srcs[0].stype() == kRowSparseStorage) {
       for (auto& s : srcs) KV_CHECK_EQ(s.stype(), kRowSparseStorage) << "mixed storage types in push";
+      KV_CHECK(!dist_) << "row_sparse keys are not supported by the one-rank-per-GPU store yet";
       PushRowSparse(e, srcs);
       continue;
     }
@@ -357,6 +366,8 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
       KV_CHECK_EQ(s.dtype(), e.dtype) << "push: dtype mismatch for key " << e.key;
     }
     auto oit = out_of.find(e.key);
+    KV_CHECK(!(callback && dist_))
+        << "the one-rank-per-GPU store runs fused optimizers only (sgd / adam / test) or no updater";
     if (callback) {
       ExecCallbackPush(e, srcs);
       if (oit != out_of.end()) {

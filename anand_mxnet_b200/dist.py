@@ -1,0 +1,73 @@
+"""One-rank-per-GPU launch support: join the ranks of a torch.distributed job into a libb200kv peer
+group (CUDA-IPC mapped NVLink peer memory, see csrc/group.h).
+
+    torchrun --nproc-per-node 8 train.py
+        import torch.distributed as dist, anand_mxnet_b200 as mx
+        dist.init_process_group('nccl')            # or gloo
+        mx.dist.init_peer_group()                  # once, before creating arrays / stores
+        kv = mx.kv.create('device')                # kv.rank / kv.num_workers follow the job
+
+torch.distributed is plumbing only: the library asks the host for ONE primitive, an all-gather of a
+few bytes, used at group creation (IPC handles) and whenever a new call signature is planned
+(operand offsets). Steady-state steps involve no host communication.
+"""
+import ctypes
+import os
+
+from .base import _LIB, check_call
+
+_ALLGATHER_PROTO = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                    ctypes.c_void_p)
+_state = {}
+
+
+def make_allgather_callback(group=None):
+    """A C callback that all-gathers `nbytes` over a (CPU / gloo) torch.distributed group."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+
+    def _cb(send, recv, nbytes, _ctx):
+        try:
+            src = (ctypes.c_ubyte * nbytes).from_address(send)
+            mine = torch.frombuffer(src, dtype=torch.uint8).clone()
+            outs = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(outs, mine, group=group)
+            for r, o in enumerate(outs):
+                ctypes.memmove(recv + r * nbytes, o.data_ptr(), nbytes)
+            return 0
+        except Exception as e:  # pragma: no cover - surfaced through the C error path
+            print("b200kv all-gather callback failed:", e)
+            return 1
+    return _ALLGATHER_PROTO(_cb)
+
+
+def init_peer_group(device_id=None):
+    """Create the peer group for the calling torch.distributed job (idempotent)."""
+    import torch.distributed as dist
+    if _state.get('inited'):
+        return
+    assert dist.is_initialized(), "call torch.distributed.init_process_group first"
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if device_id is None:
+        device_id = int(os.environ.get('LOCAL_RANK', rank))
+    # bootstrap traffic is a few hundred bytes on the host: always a gloo group
+    cpu_group = dist.new_group(backend='gloo') if dist.get_backend() != 'gloo' else None
+    cb = make_allgather_callback(cpu_group)
+    _state.update(cb=cb, group=cpu_group, inited=True, rank=rank, world=world, device=device_id)
+    check_call(_LIB.B200KVGroupInit(ctypes.c_int(rank), ctypes.c_int(world), ctypes.c_int(device_id),
+                                    cb, None))
+
+
+def destroy_peer_group():
+    if _state.get('inited'):
+        check_call(_LIB.B200KVGroupDestroy())
+        _state.clear()
+
+
+def rank():
+    return _state.get('rank', 0)
+
+
+def world_size():
+    return _state.get('world', 1)

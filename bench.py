@@ -279,8 +279,12 @@ def run_single_gpu(args):
     import anand_mxnet_b200 as mx
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
-    stream = torch.cuda.current_stream()
-    mx.base.set_stream(0, stream.cuda_stream)   # library work is issued on torch's stream
+    # a dedicated non-default stream shared by torch (events, data generation) and the library
+    # (B200KVEngineSetStream): the CUDA events below are recorded on the stream the kernels run on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    mx.base.set_stream(0, stream.cuda_stream)
+    assert mx.base.get_stream(0) == stream.cuda_stream
     shapes = WORKLOADS[args.workload]["shapes"]()
     keys = list(range(len(shapes)))
     n_elem = sum(int(np.prod(s)) for s in shapes)
@@ -388,8 +392,8 @@ def run_single_gpu(args):
     e0.record(stream)
     for _ in range(e2e_steps):
         kv2.pushpull(keys, hgrads, out=houts)
+    mx.nd.waitall()        # the last D2H copies run on the copy-out lane: wait before stamping
     e1.record(stream)
-    mx.nd.waitall()
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
     e2e = {"value": alg / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_elem * 4,

@@ -1,0 +1,126 @@
+"""One-rank-per-GPU store (CUDA-IPC peer group, in-kernel barriers): parity against the oracle.
+Spawns one process per GPU (2, and 4 when available) with a gloo bootstrap group on 127.0.0.1."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+SHAPES = [(4, 4), (100, 100), (3,), (1027,), (70001, 3), (1500, 1500)]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _grad(rank, step, k, shape):
+    return np.random.default_rng(1000 * rank + 17 * step + k).uniform(-1, 1, shape).astype(np.float32)
+
+
+def _worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "oracle")]
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["LOCAL_RANK"] = str(rank)
+    os.environ["B200KV_IPC_ARENA_MB"] = "512"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    errors = []
+    try:
+        import kvoracle as K
+        import anand_mxnet_b200 as mx
+        mx.dist.init_peer_group(rank)
+        ctx = mx.gpu(rank)
+        keys = list(range(len(SHAPES)))
+
+        def eq(a, b):
+            return np.array_equal(np.ascontiguousarray(a).view(np.uint8),
+                                  np.ascontiguousarray(b).view(np.uint8))
+        for kvtype, order in (("device", "device"), ("local", "local")):
+            # ---- plain reduce + broadcast (no optimizer)
+            kv = mx.kv.create(kvtype)
+            if not (kv.rank == rank and kv.num_workers == world):
+                errors.append("rank/num_workers wrong")
+            kv.init(keys, [mx.nd.zeros(s, ctx) for s in SHAPES])
+            outs = [mx.nd.empty(s, ctx) for s in SHAPES]
+            for step in range(2):
+                vals = [mx.nd.array(_grad(rank, step, k, s), ctx) for k, s in enumerate(SHAPES)]
+                kv.pushpull(keys, vals, out=outs)
+                for k, s in enumerate(SHAPES):
+                    want = K.get_oracle().reduce([_grad(r, step, k, s) for r in range(world)], order)
+                    if not eq(outs[k].asnumpy().ravel(), want):
+                        errors.append("reduce %s step %d key %d" % (kvtype, step, k))
+            # ---- fused SGD-momentum, state striped over the ranks
+            kv = mx.kv.create(kvtype)
+            model = K.LocalKVStoreModel(order)
+            for k, s in enumerate(SHAPES):
+                w = np.random.default_rng(99 + k).uniform(-1, 1, s).astype(np.float32)
+                kv.init(k, mx.nd.array(w, ctx))
+                model.init(k, w)
+            kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4,
+                                              rescale_grad=1.0 / (64 * world), clip_gradient=0.01))
+            model.set_optimizer('sgd', lr=0.1, momentum=0.9, wd=1e-4,
+                                rescale_grad=1.0 / (64 * world), clip_gradient=0.01)
+            # one gradient comes from torch memory (outside the IPC arena): staged automatically
+            for step in range(3):
+                vals = []
+                for k, s in enumerate(SHAPES):
+                    g = _grad(rank, 10 + step, k, s)
+                    if k == 1:
+                        vals.append(mx.nd.from_torch(torch.from_numpy(g).cuda()))
+                    else:
+                        vals.append(mx.nd.array(g, ctx))
+                torch.cuda.synchronize()
+                kv.pushpull(keys, vals, out=outs)
+                for k, s in enumerate(SHAPES):
+                    model.push(k, [_grad(r, 10 + step, k, s) for r in range(world)])
+                    if not eq(outs[k].asnumpy(), model.pull(k)):
+                        errors.append("sgd %s step %d key %d" % (kvtype, step, k))
+            fresh = [mx.nd.empty(s, ctx) for s in SHAPES]
+            kv.pull(keys, out=fresh)
+            for k in keys:
+                if not eq(fresh[k].asnumpy(), model.pull(k)):
+                    errors.append("pull %s key %d" % (kvtype, k))
+        mx.nd.waitall()
+        dist.barrier()
+        mx.dist.destroy_peer_group()
+    except Exception as e:  # noqa
+        import traceback
+        errors.append(traceback.format_exc())
+    finally:
+        q.put((rank, errors))
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_group_parity(world):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = []
+    try:
+        results = [q.get(timeout=300) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for rank, errors in results:
+        assert not errors, (rank, errors[:3])

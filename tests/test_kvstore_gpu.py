@@ -169,7 +169,7 @@ def test_unaligned_external_memory(mx):
         assert eq(out_view.cpu().numpy(), a[1:1 + n] + a[1:1 + n])
         assert out_t[:3].abs().sum().item() == 0 and out_t[3 + n:].abs().sum().item() == 0
     finally:
-        mx.base.set_stream(0, 0)
+        mx.base.set_stream(0, None)
 
 
 def test_host_buffers_end_to_end(mx, oracle):
