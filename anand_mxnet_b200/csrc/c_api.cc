@@ -659,6 +659,23 @@ int B200KVGroupDestroy(void) {
   API_END();
 }
 
+// test hook: copy n (src -> dst) array pairs with ONE TMA bulk-copy launch (pack_kernels.cu);
+// pairs the pack path cannot take (different GPUs, foreign host memory) use CopyFromTo
+B200KV_DLL int B200KVTestPackCopy(int n, NDArrayHandle* srcs, NDArrayHandle* dsts, int* n_packed) {
+  API_BEGIN();
+  std::vector<std::pair<NDArray, NDArray>> pairs;
+  for (int i = 0; i < n; ++i) {
+    KV_CHECK_EQ(ND(srcs[i]).ByteSize(), ND(dsts[i]).ByteSize());
+    pairs.emplace_back(ND(srcs[i]), ND(dsts[i]));
+  }
+  std::shared_ptr<PackList> pl = BuildPackList(&pairs);
+  *n_packed = pl ? static_cast<int>(pl->pairs.size()) : 0;
+  if (pl) RunPackList(*pl);
+  for (auto& pr : pairs) CopyFromTo(pr.first, pr.second);
+  Engine::Get()->WaitAll();
+  API_END();
+}
+
 // host-only hook: the rank-major int64 exchange plan building uses (runs under gloo on CPU)
 B200KV_DLL int B200KVTestGatherI64(int world, B200KVAllGatherFn allgather, void* ctx,
                                    const int64_t* mine, int n, int64_t* out) {

@@ -24,6 +24,68 @@ static uint64_t Mix(uint64_t h, uint64_t v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// same-GPU staging copies as one TMA bulk-copy launch
+// ---------------------------------------------------------------------------------------------
+PackList::~PackList() { Engine::Get()->Free(dev, d_items, bytes_items); }
+
+// Moves the same-GPU pairs of `pairs` into a PackList (tiles of <= 16 KB uploaded once).
+std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>* pairs) {
+  std::vector<std::pair<NDArray, NDArray>> rest;
+  auto pl = std::make_shared<PackList>();
+  std::vector<PackItem> items;
+  for (auto& pr : *pairs) {
+    const NDArray& from = pr.first;
+    const NDArray& to = pr.second;
+    // same-GPU pairs, or one side in kernel-visible pinned host memory (the SMs then drive the
+    // PCIe transfer with TMA bulk copies: one launch instead of one cudaMemcpyAsync per array)
+    int pdev = -1;
+    if (from.on_gpu() && to.on_gpu() && from.dev() == to.dev()) pdev = from.dev();
+    else if (from.on_gpu() && to.kernel_visible_host()) pdev = from.dev();
+    else if (to.on_gpu() && from.kernel_visible_host()) pdev = to.dev();
+    if (pdev < 0 || (pl->dev >= 0 && pdev != pl->dev)) {
+      rest.push_back(pr);
+      continue;
+    }
+    pl->dev = pdev;
+    const char* s = static_cast<const char*>(from.data());
+    char* d = static_cast<char*>(to.data());
+    const uint64_t n = from.ByteSize();
+    for (uint64_t off = 0; off < n; off += kPackTileBytes) {
+      items.push_back(PackItem{s + off, d + off, std::min<uint64_t>(kPackTileBytes, n - off)});
+    }
+    pl->total_bytes += n;
+    pl->pairs.push_back(pr);
+  }
+  *pairs = rest;
+  if (items.empty()) return nullptr;
+  Engine* eng = Engine::Get();
+  pl->n_items = static_cast<int>(items.size());
+  pl->bytes_items = items.size() * sizeof(PackItem);
+  pl->d_items = eng->Alloc(pl->dev, pl->bytes_items);
+  DeviceGuard g(pl->dev);
+  KV_CUDA(cudaMemcpyAsync(pl->d_items, items.data(), pl->bytes_items, cudaMemcpyHostToDevice,
+                          eng->Stream(pl->dev)));
+  return pl;
+}
+
+void RunPackList(PackList& pl) {
+  Engine* eng = Engine::Get();
+  const int dev = pl.dev;
+  for (auto& pr : pl.pairs) {
+    eng->BeginRead(dev, *pr.first.var());
+    eng->BeginWrite(dev, *pr.second.var());
+  }
+  DeviceGuard g(dev);
+  LaunchPackBulk(static_cast<const PackItem*>(pl.d_items), pl.n_items, pl.total_bytes, eng->Stream(dev));
+  eng->CountLaunch("pack_bulk(tma)", 2 * pl.total_bytes);
+  const uint64_t seq = eng->Issue(dev);
+  for (auto& pr : pl.pairs) {
+    eng->MarkRead(dev, seq, pr.first.var());
+    eng->MarkWrite(dev, seq, pr.second.var());
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // call-level cache
 // ---------------------------------------------------------------------------------------------
 bool KVStore::CallSignature(int tag, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
@@ -133,9 +195,17 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
     }
     KV_CHECK(op.outs.size() <= static_cast<size_t>(kMaxDst)) << "at most " << kMaxDst << " outs per key";
     const auto gkey = std::make_tuple(e.dtype, e.striped ? 1 : 0, e.striped ? -1 : e.home);
+    // Host-resident operands: arrays in the library's own pinned+mapped memory are handed to the
+    // kernel as they are (it reads gradients / writes weights over PCIe itself: one launch, no
+    // copies, both PCIe directions busy at once); foreign host memory is staged through the GPU.
+    static const bool kZeroCopy = []() {
+      const char* z = std::getenv("B200KV_HOST_ZEROCOPY");
+      return z == nullptr || std::atoi(z) != 0;
+    }();
+    auto direct = [&](const NDArray& a) { return a.on_gpu() || (kZeroCopy && a.kernel_visible_host()); };
     size_t staged = 0;
-    for (auto& s : op.srcs) if (!s.on_gpu()) staged += s.ByteSize();
-    for (auto& o : op.outs) if (!o.on_gpu()) staged += o.ByteSize();
+    for (auto& s : op.srcs) if (!direct(s)) staged += s.ByteSize();
+    for (auto& o : op.outs) if (!direct(o)) staged += o.ByteSize();
     auto& bk = bucket_of[gkey];
     if (staged > 0 && bk.second > 0 && bk.second + staged > kStageBucketBytes) {
       ++bk.first;
@@ -146,7 +216,7 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
     const int stage_dev = e.striped ? devset_[0] : e.home;
     DenseOp dop = op;
     for (size_t i = 0; i < dop.srcs.size(); ++i) {
-      if (!dop.srcs[i].on_gpu()) {
+      if (!direct(dop.srcs[i])) {
         NDArray st = StageSrc(e, i, dop.srcs[i], stage_dev);
         P.stage_in.emplace_back(dop.srcs[i], st);
         dop.srcs[i] = st;
@@ -155,7 +225,7 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
     for (size_t i = 0; i < dop.outs.size(); ++i) {
       KV_CHECK_EQ(dop.outs[i].Size(), e.size) << "pull: shape mismatch for key " << e.key;
       KV_CHECK_EQ(dop.outs[i].dtype(), e.dtype) << "pull: dtype mismatch for key " << e.key;
-      if (!dop.outs[i].on_gpu()) {
+      if (!direct(dop.outs[i])) {
         NDArray st = StageOut(e, i, dop.outs[i], stage_dev);
         P.stage_out.emplace_back(st, dop.outs[i]);
         dop.outs[i] = st;
@@ -176,8 +246,8 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
     P.plan = GetPlan(P.ops, opt_kind, P.owners, P.ops[0].e->striped);
     std::set<int> part_set(P.owners.begin(), P.owners.end());
     for (auto& op : P.ops) {
-      for (auto& s : op.srcs) part_set.insert(s.dev());
-      for (auto& o : op.outs) part_set.insert(o.dev());
+      for (auto& s : op.srcs) if (s.on_gpu()) part_set.insert(s.dev());
+      for (auto& o : op.outs) if (o.on_gpu()) part_set.insert(o.dev());
     }
     P.parts.assign(part_set.begin(), part_set.end());
     if (P.parts.size() > 1) {
@@ -196,6 +266,7 @@ void KVStore::RunPrepared(Prepared& P) {
   Engine* eng = Engine::Get();
   const int opt_kind = P.opt_kind;
   const bool fused_opt = P.is_push && opt_.enabled && (opt_kind == kOptSGD || opt_kind == kOptAdam);
+  if (P.pack_in) RunPackList(*P.pack_in);
   for (auto& io : P.stage_in) CopyFromTo(io.first, io.second);
 
   // ---- optimizer bookkeeping: update counts first (Optimizer._update_count, optimizer.py:412-430)
@@ -237,9 +308,11 @@ void KVStore::RunPrepared(Prepared& P) {
 
   // ---- dependencies
   const bool multi = P.parts.size() > 1;
+  const int host_lane = P.owners[0];  // kernel-visible host operands are touched by the owners' kernels
+  auto lane_of = [&](const NDArray& a) { return a.on_gpu() ? a.dev() : host_lane; };
   for (auto& op : P.ops) {
-    for (auto& s : op.srcs) eng->BeginRead(s.dev(), *s.var());
-    for (auto& o : op.outs) eng->BeginWrite(o.dev(), *o.var());
+    for (auto& s : op.srcs) eng->BeginRead(lane_of(s), *s.var());
+    for (auto& o : op.outs) eng->BeginWrite(lane_of(o), *o.var());
     for (int d : P.owners) {
       DevState& s = op.e->dev[d];
       if (P.is_push) eng->BeginWrite(d, *s.w.var()); else eng->BeginRead(d, *s.w.var());
@@ -285,8 +358,8 @@ void KVStore::RunPrepared(Prepared& P) {
   uint64_t seq[kMaxDevices] = {0};
   for (int d : P.parts) seq[d] = eng->Issue(d);
   for (auto& op : P.ops) {
-    for (auto& s : op.srcs) eng->MarkRead(s.dev(), seq[s.dev()], s.var());
-    for (auto& o : op.outs) eng->MarkWrite(o.dev(), seq[o.dev()], o.var());
+    for (auto& s : op.srcs) eng->MarkRead(lane_of(s), seq[lane_of(s)], s.var());
+    for (auto& o : op.outs) eng->MarkWrite(lane_of(o), seq[lane_of(o)], o.var());
     for (int d : P.owners) {
       DevState& s = op.e->dev[d];
       if (P.is_push) {
@@ -299,6 +372,7 @@ void KVStore::RunPrepared(Prepared& P) {
       }
     }
   }
+  if (P.pack_out) RunPackList(*P.pack_out);
   for (auto& io : P.stage_out) CopyFromTo(io.first, io.second);
 }
 

@@ -219,7 +219,8 @@ void* Engine::AllocPinned(size_t bytes) {
     return p;
   }
   void* p = nullptr;
-  KV_CUDA(cudaHostAlloc(&p, r, cudaHostAllocPortable));
+  // portable + mapped: every GPU's kernels can read/write it through the same (UVA) pointer
+  KV_CUDA(cudaHostAlloc(&p, r, cudaHostAllocPortable | cudaHostAllocMapped));
   return p;
 }
 

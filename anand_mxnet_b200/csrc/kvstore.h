@@ -89,6 +89,21 @@ struct Plan {
   ~Plan();
 };
 
+// Same-GPU staging copies of one prepared launch, executed as ONE TMA bulk-copy kernel
+// (pack_kernels.cu) instead of one cudaMemcpyAsync per array.
+struct PackList {
+  int dev = -1;
+  std::vector<std::pair<NDArray, NDArray>> pairs;  // (from, to), both on `dev`
+  void* d_items = nullptr;                          // PackItem[n] on the device (tiles <= 16 KB)
+  size_t bytes_items = 0;
+  int n_items = 0;
+  uint64_t total_bytes = 0;
+  ~PackList();
+};
+
+std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>* pairs);
+void RunPackList(PackList& pl);
+
 // Everything one fused launch group needs at run time, computed once per distinct call signature:
 // placement done, state allocated, plan built, the arrays whose dependencies must be tracked, the
 // host<->device staging copies to issue around the launch.
@@ -100,6 +115,7 @@ struct Prepared {
   std::vector<DenseOp> ops;                              // device-side operands
   std::vector<std::pair<NDArray, NDArray>> stage_in;     // (host source, device staging buffer)
   std::vector<std::pair<NDArray, NDArray>> stage_out;    // (device staging buffer, host out)
+  std::shared_ptr<PackList> pack_in, pack_out;           // same-GPU staging: one TMA pack launch
   std::vector<int> owners, parts;
   std::shared_ptr<Plan> plan;
   std::vector<float> hyper;                              // per key (lr, wd)

@@ -76,6 +76,10 @@ class NDArray {
   Context ctx() const { return st_ ? st_->ctx : Context(); }
   int dev() const { return st_->ctx.dev_id; }
   bool on_gpu() const { return st_ && st_->ctx.is_gpu(); }
+  // host array in the library's own pinned+mapped memory: kernels can address it directly (UVA),
+  // so the fused kernel reads gradients from / writes weights to it over PCIe without staging
+  bool kernel_visible_host() const { return st_ && !st_->ctx.is_gpu() && !st_->external; }
+  bool kernel_visible() const { return on_gpu() || kernel_visible_host(); }
   size_t Size() const;        // product of shape
   size_t RowLength() const;   // product of shape[1:]
   size_t ByteSize() const { return Size() * DTypeSize(dtype_); }

@@ -392,3 +392,30 @@ def test_resnet50_sized_properties(mx):
     mx.nd.waitall()
     for a, b in zip(outs_t, outs2_t):
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------ TMA pack kernel
+def test_pack_bulk_copy(mx):
+    """Many arrays (3 elements .. 4 MB, fp32 and 16-bit, aligned and ragged byte sizes) copied by
+    ONE TMA bulk-copy launch: device->device, pinned host->device and device->pinned host."""
+    import ctypes
+    rng = np.random.default_rng(12)
+    shapes = [(3,), (1,), (4099,), (16384,), (1000, 1000), (7, 11, 13), (4096 * 4 + 4,)]
+    lib = mx.base._LIB
+    for src_ctx, dst_ctx in ((mx.gpu(0), mx.gpu(0)), (mx.cpu(), mx.gpu(0)), (mx.gpu(0), mx.cpu())):
+        srcs, dsts, want = [], [], []
+        for i, s in enumerate(shapes):
+            dt = np.float16 if i % 3 == 2 else np.float32
+            a = rng.uniform(-1, 1, s).astype(dt)
+            want.append(a)
+            srcs.append(mx.nd.array(a, src_ctx, dt))
+            dsts.append(mx.nd.array(np.zeros(s, dt), dst_ctx, dt))
+        n = len(shapes)
+        sa = (ctypes.c_void_p * n)(*[x._hv for x in srcs])
+        da = (ctypes.c_void_p * n)(*[x._hv for x in dsts])
+        packed = ctypes.c_int()
+        mx.base.check_call(lib.B200KVTestPackCopy(n, sa, da, ctypes.byref(packed)))
+        assert packed.value == n
+        assert mx.base.last_kernel_info()[0].startswith("pack_bulk")
+        for d, w in zip(dsts, want):
+            assert eq(d.asnumpy(), w)
