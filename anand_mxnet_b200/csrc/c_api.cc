@@ -149,6 +149,7 @@ int MXNDArrayFree(NDArrayHandle handle) {
 
 int MXNDArraySyncCopyFromCPU(NDArrayHandle handle, const void* data, size_t size) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   NDArray& a = ND(handle);
   KV_CHECK_EQ(a.stype(), kDefaultStorage) << "SyncCopyFromCPU on a sparse array: copy the data and "
                                           << "aux arrays (MXNDArrayGetDataNDArray / GetAuxNDArray)";
@@ -167,6 +168,7 @@ int MXNDArraySyncCopyFromCPU(NDArrayHandle handle, const void* data, size_t size
 
 int MXNDArraySyncCopyToCPU(NDArrayHandle handle, void* data, size_t size) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   NDArray& a = ND(handle);
   KV_CHECK_EQ(a.stype(), kDefaultStorage) << "SyncCopyToCPU on a sparse array";
   KV_CHECK_EQ(a.Size(), size) << "Memory size do not match";
@@ -179,6 +181,7 @@ int MXNDArraySyncCopyToCPU(NDArrayHandle handle, void* data, size_t size) {
 
 int MXNDArraySyncCopyFromNDArray(NDArrayHandle handle_dst, const NDArrayHandle handle_src, const int i) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   NDArray& dst = ND(handle_dst);
   NDArray& src = ND(handle_src);
   KV_CHECK_EQ(src.stype(), kDefaultStorage) << "source must be a dense array";
@@ -204,6 +207,7 @@ int MXNDArraySyncCopyFromNDArray(NDArrayHandle handle_dst, const NDArrayHandle h
 
 int MXNDArrayWaitToRead(NDArrayHandle handle) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   NDArray& a = ND(handle);
   if (!a.is_none()) Engine::Get()->WaitToRead(*a.var());
   API_END();
@@ -211,6 +215,7 @@ int MXNDArrayWaitToRead(NDArrayHandle handle) {
 
 int MXNDArrayWaitToWrite(NDArrayHandle handle) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   NDArray& a = ND(handle);
   if (!a.is_none()) Engine::Get()->WaitToWrite(*a.var());
   API_END();
@@ -218,6 +223,7 @@ int MXNDArrayWaitToWrite(NDArrayHandle handle) {
 
 int MXNDArrayWaitAll(void) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   Engine::Get()->WaitAll();
   API_END();
 }
@@ -292,6 +298,7 @@ int MXNDArrayGetContext(NDArrayHandle handle, int* out_dev_type, int* out_dev_id
 
 int MXNDArrayToDLPack(NDArrayHandle handle, DLManagedTensorHandle* out_dlpack) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   NDArray& a = ND(handle);
   KV_CHECK_EQ(a.stype(), kDefaultStorage) << "only dense arrays export to DLPack";
   struct Holder {
@@ -355,6 +362,7 @@ int MXImperativeInvokeEx(AtomicSymbolCreator creator, int num_inputs, NDArrayHan
                          int* num_outputs, NDArrayHandle** outputs, int num_params,
                          const char** param_keys, const char** param_vals, const int** out_stypes) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   const OpInfo* op = static_cast<const OpInfo*>(creator);
   KV_CHECK(op != nullptr) << "null operator handle";
   std::vector<NDArray> in = NDVec(inputs, num_inputs);
@@ -596,6 +604,7 @@ int B200KVStoreLookupKey(KVStoreHandle handle, const char* str_key, int* out_key
 
 int B200KVStoreGetOptimizerState(KVStoreHandle handle, int key, int state_id, NDArrayHandle* out) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   *out = new NDArray(KV(handle).GetOptimizerState(key, state_id));
   API_END();
 }
@@ -623,9 +632,9 @@ int B200KVStoreSetUpdateCount(KVStoreHandle handle, int key, int count) {
   API_END();
 }
 
-int B200KVStoreSetBucketBytes(KVStoreHandle handle, size_t) {
+int B200KVStoreSetBucketBytes(KVStoreHandle handle, size_t max_bytes) {
   API_BEGIN();
-  KV(handle);
+  KV(handle).SetBucketBytes(max_bytes);
   API_END();
 }
 
@@ -637,6 +646,7 @@ int B200KVStoreFlush(KVStoreHandle handle) {
 
 int B200KVEngineSetStream(int dev_id, void* cuda_stream) {
   API_BEGIN();
+  KVStore::FlushAll();  // queued (bucketed) KVStore calls run before anything observes arrays
   Engine::Get()->SetStream(dev_id, static_cast<cudaStream_t>(cuda_stream));
   API_END();
 }

@@ -198,14 +198,19 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
     // Host-resident operands: arrays in the library's own pinned+mapped memory are handed to the
     // kernel as they are (it reads gradients / writes weights over PCIe itself: one launch, no
     // copies, both PCIe directions busy at once); foreign host memory is staged through the GPU.
-    static const bool kZeroCopy = []() {
-      const char* z = std::getenv("B200KV_HOST_ZEROCOPY");
-      return z == nullptr || std::atoi(z) != 0;
+    // B200KV_HOST_MODE: zc (default) kernel reads and writes host memory; staged: DMA both ways;
+    // in_dma: gradients by the copy engine, weights written by the kernel; in_tma: gradients by
+    // the TMA pack kernel, weights written by the kernel
+    static const int kHostMode = []() {
+      const char* z = std::getenv("B200KV_HOST_MODE");
+      const std::string m = z ? z : "zc";
+      return m == "staged" ? 0 : m == "in_dma" ? 2 : m == "in_tma" ? 3 : 1;
     }();
-    auto direct = [&](const NDArray& a) { return a.on_gpu() || (kZeroCopy && a.kernel_visible_host()); };
+    auto direct_in = [&](const NDArray& a) { return a.on_gpu() || (kHostMode == 1 && a.kernel_visible_host()); };
+    auto direct_out = [&](const NDArray& a) { return a.on_gpu() || (kHostMode >= 1 && a.kernel_visible_host()); };
     size_t staged = 0;
-    for (auto& s : op.srcs) if (!direct(s)) staged += s.ByteSize();
-    for (auto& o : op.outs) if (!direct(o)) staged += o.ByteSize();
+    for (auto& s : op.srcs) if (!direct_in(s)) staged += s.ByteSize();
+    for (auto& o : op.outs) if (!direct_out(o)) staged += o.ByteSize();
     auto& bk = bucket_of[gkey];
     if (staged > 0 && bk.second > 0 && bk.second + staged > kStageBucketBytes) {
       ++bk.first;
@@ -216,7 +221,7 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
     const int stage_dev = e.striped ? devset_[0] : e.home;
     DenseOp dop = op;
     for (size_t i = 0; i < dop.srcs.size(); ++i) {
-      if (!direct(dop.srcs[i])) {
+      if (!direct_in(dop.srcs[i])) {
         NDArray st = StageSrc(e, i, dop.srcs[i], stage_dev);
         P.stage_in.emplace_back(dop.srcs[i], st);
         dop.srcs[i] = st;
@@ -225,7 +230,7 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
     for (size_t i = 0; i < dop.outs.size(); ++i) {
       KV_CHECK_EQ(dop.outs[i].Size(), e.size) << "pull: shape mismatch for key " << e.key;
       KV_CHECK_EQ(dop.outs[i].dtype(), e.dtype) << "pull: dtype mismatch for key " << e.key;
-      if (!direct(dop.outs[i])) {
+      if (!direct_out(dop.outs[i])) {
         NDArray st = StageOut(e, i, dop.outs[i], stage_dev);
         P.stage_out.emplace_back(st, dop.outs[i]);
         dop.outs[i] = st;
@@ -254,6 +259,9 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
       int enabled = eng->EnablePeerAccess(P.parts);
       KV_CHECK_EQ(enabled, static_cast<int>(P.parts.size() * (P.parts.size() - 1)))
           << "GPU peer access is not available between all participating devices";
+    }
+    if (std::getenv("B200KV_HOST_MODE") && std::string(std::getenv("B200KV_HOST_MODE")) == "in_tma") {
+      P.pack_in = BuildPackList(&P.stage_in);
     }
     out->push_back(std::move(P));
   }

@@ -161,7 +161,10 @@ class KVStore {
   void TouchOpt() { ++opt_version_; }  // call after changing opt() scalars / multipliers
   NDArray GetOptimizerState(int key, int state_id);
   void SetOptimizerState(int key, int state_id, const NDArray& v);
-  void Flush() {}
+  // deferred bucket execution (see kvstore_core.cc)
+  void SetBucketBytes(size_t n);
+  void Flush();
+  static void FlushAll();
   std::string DescribePlan(const std::vector<int>& keys, int num_devices);
 
  private:
@@ -220,6 +223,16 @@ class KVStore {
   OptConfig opt_;
   std::unordered_map<uint64_t, std::shared_ptr<Plan>> plans_;
   std::unordered_map<uint64_t, std::shared_ptr<CachedCall>> call_cache_;
+  struct PendingOp {
+    std::vector<int> vkeys, okeys;
+    std::vector<NDArray> vals, outs;
+    int priority = 0;
+  };
+  bool TryDefer(int kind, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
+                const std::vector<int>& okeys, const std::vector<NDArray>& outs, int priority);
+  std::vector<PendingOp> pending_;
+  std::unordered_set<int> pending_pushed_, pending_pulled_;
+  size_t pending_bytes_ = 0, bucket_bytes_ = 0;
   uint64_t opt_version_ = 1;   // bumped whenever a hyper-parameter / multiplier changes
   uint64_t layout_epoch_ = 1;  // bumped whenever placement / optimizer kind / updater changes
   std::string gc_type_ = "none";

@@ -25,6 +25,8 @@ static uint64_t RoundUp(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 static bool Is16Bit(int dtype) { return dtype == kFloat16 || dtype == kBfloat16; }
 
+static std::set<KVStore*>& LiveStores();  // stores with possibly queued work (FlushAll)
+
 // Chunk a key's elements for the device that owns them. A chunk never crosses a chunk boundary of
 // the store-global element space, hence never an ownership stripe. owner_fixed >= 0: the whole key
 // belongs to that slot (WHOLE placement); otherwise stripes rotate over ndev slots.
@@ -73,10 +75,14 @@ KVStore::KVStore(const std::string& type) : type_(type) {
     rank_ = g->rank();
     group_size_ = g->world();
   }
+  if (const char* b = std::getenv("B200KV_BUCKET_MB")) bucket_bytes_ = static_cast<size_t>(std::atoi(b)) << 20;
+  LiveStores().insert(this);
 }
 
 KVStore::~KVStore() {
+  LiveStores().erase(this);
   try {
+    Flush();
     Engine::Get()->WaitAll();
   } catch (...) {
   }
@@ -298,17 +304,114 @@ static void GroupKVPairs(const std::vector<int>& keys, const std::vector<NDArray
 // =================================================================================================
 // push / pull / pushpull
 // =================================================================================================
-void KVStore::Push(const std::vector<int>& keys, const std::vector<NDArray>& values, int) {
+// ---- deferred bucket execution ------------------------------------------------------------------
+// The reference's callers issue one push / pull per parameter (gluon/trainer.py:371-396 with
+// priority=-i; tools/bandwidth/measure.py:112-122). Executed one by one that is a kernel launch per
+// key. With B200KVStoreSetBucketBytes(n > 0) the calls are queued -- they "return after enqueueing"
+// exactly as the reference's asynchronous contract allows (kvstore.h:129-141,168-180) -- and fused
+// into ONE launch per device when the queued bytes reach n, when any array is waited on / read,
+// or on Flush(). Per-key order is preserved; higher priority values are issued first.
+static std::set<KVStore*>& LiveStores() {
+  static auto* s = new std::set<KVStore*>();
+  return *s;
+}
+
+void KVStore::FlushAll() {
+  for (KVStore* kv : LiveStores()) kv->Flush();
+}
+
+bool KVStore::TryDefer(int kind, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
+                       const std::vector<int>& okeys, const std::vector<NDArray>& outs, int priority) {
+  if (bucket_bytes_ == 0 || (updater_ != nullptr && !opt_.enabled)) return false;
+  size_t bytes = 0;
+  for (size_t i = 0; i < vkeys.size(); ++i) {
+    KeyEntry& e = Entry(vkeys[i]);  // un-initialised keys still fail synchronously
+    const NDArray& v = values[i];
+    if (v.stype() != kDefaultStorage || e.stype != kDefaultStorage) return false;
+    KV_CHECK_EQ(v.Size(), e.size) << "push: shape mismatch for key " << e.key;
+    KV_CHECK_EQ(v.dtype(), e.dtype) << "push: dtype mismatch for key " << e.key;
+    bytes += v.ByteSize();
+  }
+  for (size_t i = 0; i < okeys.size(); ++i) {
+    KeyEntry& e = Entry(okeys[i]);
+    const NDArray& o = outs[i];
+    if (o.stype() != kDefaultStorage || e.stype != kDefaultStorage) return false;
+    KV_CHECK_EQ(o.Size(), e.size) << "pull: shape mismatch for key " << e.key;
+    KV_CHECK_EQ(o.dtype(), e.dtype) << "pull: dtype mismatch for key " << e.key;
+    bytes += o.ByteSize();
+  }
+  // a second push of a key, or a push after a queued pull of it, must not be merged with the
+  // queued one: run what is queued first
+  bool conflict = false;
+  for (int k : vkeys) {
+    if (pending_pushed_.count(k) || pending_pulled_.count(k)) conflict = true;
+  }
+  if (kind == 2) {
+    // pushpull whose pull side targets keys already pushed in this queue is fine; nothing to do
+  }
+  if (conflict) Flush();
+  PendingOp op;
+  op.vkeys = vkeys;
+  op.vals = values;
+  op.okeys = okeys;
+  op.outs = outs;
+  op.priority = priority;
+  pending_.push_back(std::move(op));
+  for (int k : vkeys) pending_pushed_.insert(k);
+  for (int k : okeys) pending_pulled_.insert(k);
+  pending_bytes_ += bytes;
+  if (pending_bytes_ >= bucket_bytes_) Flush();
+  return true;
+}
+
+void KVStore::Flush() {
+  if (pending_.empty()) return;
+  std::vector<PendingOp> ops;
+  ops.swap(pending_);
+  pending_pushed_.clear();
+  pending_pulled_.clear();
+  pending_bytes_ = 0;
+  // higher priority first; equal priorities (push i and pull i both carry -i) keep call order
+  std::stable_sort(ops.begin(), ops.end(),
+                   [](const PendingOp& a, const PendingOp& b) { return a.priority > b.priority; });
+  std::vector<int> vkeys, okeys;
+  std::vector<NDArray> vals, outs;
+  for (auto& op : ops) {
+    vkeys.insert(vkeys.end(), op.vkeys.begin(), op.vkeys.end());
+    vals.insert(vals.end(), op.vals.begin(), op.vals.end());
+    okeys.insert(okeys.end(), op.okeys.begin(), op.okeys.end());
+    outs.insert(outs.end(), op.outs.begin(), op.outs.end());
+  }
+  if (!vkeys.empty()) {
+    PushImpl(vkeys, vals, okeys.empty() ? nullptr : &okeys, okeys.empty() ? nullptr : &outs);
+  } else {
+    PullImpl(okeys, outs, true);
+  }
+}
+
+void KVStore::SetBucketBytes(size_t n) {
+  Flush();
+  bucket_bytes_ = n;
+}
+
+void KVStore::Push(const std::vector<int>& keys, const std::vector<NDArray>& values, int priority) {
+  if (TryDefer(0, keys, values, {}, {}, priority)) return;
+  Flush();
   PushImpl(keys, values, nullptr, nullptr);
 }
 
 void KVStore::PushPull(const std::vector<int>& vkeys, const std::vector<int>& okeys,
-                       const std::vector<NDArray>& values, const std::vector<NDArray>& outs, int) {
+                       const std::vector<NDArray>& values, const std::vector<NDArray>& outs,
+                       int priority) {
+  if (TryDefer(2, vkeys, values, okeys, outs, priority)) return;
+  Flush();
   PushImpl(vkeys, values, &okeys, &outs);
 }
 
-void KVStore::Pull(const std::vector<int>& keys, const std::vector<NDArray>& outs, int,
+void KVStore::Pull(const std::vector<int>& keys, const std::vector<NDArray>& outs, int priority,
                    bool ignore_sparse) {
+  if (ignore_sparse && TryDefer(1, {}, {}, keys, outs, priority)) return;
+  Flush();
   PullImpl(keys, outs, ignore_sparse);
 }
 
