@@ -309,6 +309,15 @@ class KVStore(KVStoreBase):
     def _barrier(self):
         check_call(_LIB.MXKVStoreBarrier(self.handle))
 
+    def set_bucket_bytes(self, nbytes):
+        """B200 extension: queue per-key push / pull / pushpull calls and fuse them into one launch
+        per device every `nbytes` of operands (0 = run each call immediately, the default). Queued
+        calls are flushed whenever an array is waited on or read, so results are unchanged."""
+        check_call(_LIB.B200KVStoreSetBucketBytes(self.handle, ctypes.c_size_t(int(nbytes))))
+
+    def flush(self):
+        check_call(_LIB.B200KVStoreFlush(self.handle))
+
     def _send_command_to_servers(self, head, body):
         check_call(_LIB.MXKVStoreSendCommmandToServers(self.handle, mx_uint(head), c_str(body)))
 
