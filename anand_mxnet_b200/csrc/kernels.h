@@ -120,6 +120,16 @@ struct RetainLaunch {
 };
 void LaunchRetain(const RetainLaunch& p, cudaStream_t stream);
 
+// ---- 2-bit gradient compression with residual (compress_kernels.cu;
+// src/kvstore/gradient_compression-inl.h:40-132, comm.h:552-596 ReduceCompressed) ----
+// residual += grad; >= +t -> code 11, residual -= t; <= -t -> code 10, residual += t; else 00.
+// 16 values per 32-bit word, value i in byte (i%16)/4, bit pair 6-2*(i%4).
+void LaunchQuantize2Bit(const float* grad, float* residual, uint32_t* compressed, size_t n,
+                        float threshold, cudaStream_t stream);
+// merged[i] = deq(comp[0])[i] + deq(comp[1])[i] + ...   (left fold, ElementwiseSum order)
+void LaunchDequantizeSum2Bit(const uint32_t* const* d_compressed /* device array [nsrc] */, int nsrc,
+                             float* merged, size_t n, float threshold, cudaStream_t stream);
+
 // ---- TMA bulk-copy packing of many small arrays into one fusion buffer (pack_kernels.cu) ----
 constexpr int kPackTileBytes = 16384;  // one TMA bulk copy; items passed to the kernel are <= this
 struct PackItem { const void* src; void* dst; uint64_t bytes; };

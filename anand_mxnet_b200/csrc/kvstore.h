@@ -63,6 +63,10 @@ struct KeyEntry {
   NDArray merged;       // reduce target of the updater-callback path (on `home`)
   NDArray rsp;          // row_sparse stored value (on `home` or host)
   std::vector<NDArray> stage_src, stage_out;  // device staging of host-resident values / outs
+  // 2-bit gradient compression: per source slot residual (fp32) and compressed words, both on the
+  // source's GPU; decoded sum on `home`
+  std::vector<NDArray> gc_residual, gc_compressed;
+  NDArray gc_merged;
 };
 
 struct DenseOp {
@@ -199,6 +203,9 @@ class KVStore {
   void KeyHyper(const KeyEntry& e, int opt_kind, float* lr, float* wd);
   std::shared_ptr<Plan> GetPlan(const std::vector<DenseOp>& ops, int opt_kind,
                                 const std::vector<int>& devs, bool striped);
+
+  NDArray CompressedReduce(KeyEntry& e, const std::vector<NDArray>& srcs);  // compress.cc
+  float gc_threshold_ = 0.5f;
 
   // row_sparse machinery (rowsparse.cc)
   void PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs);

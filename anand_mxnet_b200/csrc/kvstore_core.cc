@@ -175,12 +175,20 @@ void KVStore::SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle) {
 }
 
 void KVStore::SetGradientCompression(const std::vector<std::pair<std::string, std::string>>& kw) {
+  // GradientCompression::SetParams (src/kvstore/gradient_compression.cc:44-60): type in
+  // {none, 2bit}, threshold > 0 (default 0.5)
+  std::string type = gc_type_;
+  float threshold = gc_threshold_;
   for (auto& kv : kw) {
-    if (kv.first == "type") gc_type_ = kv.second;
+    if (kv.first == "type") type = Lower(kv.second);
+    else if (kv.first == "threshold") threshold = DmlcStof(kv.second);
+    else KV_FATAL << "Cannot find argument '" << kv.first << "', Possible Arguments: type, threshold";
   }
-  KV_CHECK(gc_type_ == "none")
-      << "gradient compression type '" << gc_type_ << "' is not implemented on the B200 KVStore "
-      << "path yet (2-bit compression is a next-row item)";
+  KV_CHECK(type == "none" || type == "2bit") << "Unknown type for gradient compression " << type;
+  KV_CHECK(threshold > 0) << "threshold must be greater than 0";
+  gc_type_ = type;
+  gc_threshold_ = threshold;
+  ++layout_epoch_;
 }
 
 // =================================================================================================
@@ -322,7 +330,7 @@ void KVStore::FlushAll() {
 
 bool KVStore::TryDefer(int kind, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
                        const std::vector<int>& okeys, const std::vector<NDArray>& outs, int priority) {
-  if (bucket_bytes_ == 0 || (updater_ != nullptr && !opt_.enabled)) return false;
+  if (bucket_bytes_ == 0 || (updater_ != nullptr && !opt_.enabled) || gc_type_ != "none") return false;
   size_t bytes = 0;
   for (size_t i = 0; i < vkeys.size(); ++i) {
     KeyEntry& e = Entry(vkeys[i]);  // un-initialised keys still fail synchronously
@@ -420,7 +428,7 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
   // a repeated call (same keys, same arrays) replays its prepared launches
   const bool callback_mode = updater_ != nullptr && !opt_.enabled;
   std::vector<uint64_t> sig;
-  const bool cacheable = !callback_mode &&
+  const bool cacheable = !callback_mode && gc_type_ == "none" &&
       CallSignature(opt_.enabled ? 100 + opt_.kind : 1, keys, values, okeys, outs, &sig);
   if (cacheable && RunCachedCall(sig)) return;
   std::vector<int> uniq;
@@ -452,8 +460,15 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
   const bool callback = updater_ != nullptr && !opt_.enabled;
   for (size_t i = 0; i < uniq.size(); ++i) {
     KeyEntry& e = Entry(uniq[i]);
-    const std::vector<NDArray>& srcs = grouped[i];
+    std::vector<NDArray>& srcs = grouped[i];
     pushed.insert(e.key);
+    if (gc_type_ == "2bit" && srcs[0].stype() == kDefaultStorage) {
+      // CommDevice::Reduce -> ReduceCompressed (comm.h:507-509): quantise every value with its
+      // residual, decode + sum on the owner; the optimizer then sees that merged gradient
+      for (auto& s : srcs) KV_CHECK_EQ(s.Size(), e.size) << "push: shape mismatch for key " << e.key;
+      NDArray merged = CompressedReduce(e, srcs);
+      srcs.assign(1, merged);
+    }
     if (srcs[0].stype() == kRowSparseStorage) {
       for (auto& s : srcs) KV_CHECK_EQ(s.stype(), kRowSparseStorage) << "mixed storage types in push";
       KV_CHECK(!dist_) << "row_sparse keys are not supported by the one-rank-per-GPU store yet";
