@@ -663,6 +663,16 @@ int B200KVGroupInit(int rank, int world_size, int dev_id, B200KVAllGatherFn allg
   API_END();
 }
 
+int B200KVGroupInitExternal(int rank, int world_size, int dev_id, B200KVAllGatherFn allgather,
+                            void* ctx, void* arena, size_t arena_bytes, void* const* peer_arenas,
+                            void* multicast_arena) {
+  API_BEGIN();
+  KV_CHECK(arena != nullptr && peer_arenas != nullptr && arena_bytes > 0);
+  PeerGroup::Init(rank, world_size, dev_id, allgather, ctx, arena, arena_bytes, peer_arenas,
+                  multicast_arena);
+  API_END();
+}
+
 int B200KVGroupDestroy(void) {
   API_BEGIN();
   PeerGroup::Destroy();

@@ -84,11 +84,44 @@ void KVStore::PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::ve
   }
 }
 
-std::shared_ptr<Plan> KVStore::GetPlanGroup(const std::vector<DenseOp>& ops, int opt_kind) {
+// kv.init in a group: "only the value supplied by worker with rank 0 is used" (kvstore.py:136-141,
+// the dist stores' contract). One pull-only launch whose chunks all belong to rank 0 copies rank
+// 0's stored value into every rank's stored value.
+void KVStore::BroadcastInitGroup(const std::vector<int>& keys) {
+  PeerGroup* g = PeerGroup::Get();
+  const int dev = g->dev();
+  std::map<int, Prepared> groups;
+  for (int key : keys) {
+    KeyEntry& e = Entry(key);
+    if (e.stype != kDefaultStorage) continue;
+    if (e.home < 0) EnsureOnDevice(e, dev);
+    KV_CHECK_EQ(e.home, dev) << "one-rank-per-GPU store: initialise keys on this rank's GPU";
+    KV_CHECK(g->InArena(e.dev[dev].w.data())) << "IPC arena exhausted; raise B200KV_IPC_ARENA_MB";
+    Prepared& P = groups[e.dtype];
+    DenseOp op;
+    op.e = &e;
+    op.outs = {e.dev[dev].w};
+    P.ops.push_back(op);
+  }
+  for (auto& kv : groups) {
+    Prepared& P = kv.second;
+    P.opt_kind = kOptPullOnly;
+    P.dtype = kv.first;
+    P.is_push = false;
+    P.group = true;
+    P.owners = {dev};
+    P.parts = {dev};
+    P.plan = GetPlanGroup(P.ops, kOptPullOnly, /*fixed_owner=*/0);
+    RunPrepared(P);
+  }
+}
+
+std::shared_ptr<Plan> KVStore::GetPlanGroup(const std::vector<DenseOp>& ops, int opt_kind,
+                                            int fixed_owner) {
   PeerGroup* g = PeerGroup::Get();
   const int dev = g->dev(), W = g->world(), R = g->rank();
   const bool is_push = opt_kind != kOptPullOnly;
-  uint64_t sig = Mix(0x6702, static_cast<uint64_t>(opt_kind) * 131 + W);
+  uint64_t sig = Mix(0x6702, static_cast<uint64_t>(opt_kind) * 131 + W + 7919 * (fixed_owner + 1));
   for (auto& op : ops) {
     sig = Mix(sig, static_cast<uint64_t>(op.e->key));
     for (auto& s : op.srcs) sig = Mix(sig, reinterpret_cast<uint64_t>(s.data()));
@@ -158,9 +191,40 @@ std::shared_ptr<Plan> KVStore::GetPlanGroup(const std::vector<DenseOp>& ops, int
     K.n_src = is_push ? W : 0;
     K.n_out = n_out;
     K.vec_ok = ok ? 1u : 0u;
-    PlanChunks(e.goff, e.size, static_cast<uint32_t>(k), W, W > 1 ? -1 : 0, &chunks);
+    PlanChunks(e.goff, e.size, static_cast<uint32_t>(k), W, fixed_owner >= 0 ? fixed_owner : (W > 1 ? -1 : 0),
+               &chunks);
     // bus bytes per GPU, as tools/bandwidth/measure.py:137-138 counts them
     plan->algorithmic_bytes += static_cast<uint64_t>(e.size) * DTypeSize(e.dtype) * 2 * (W - 1) / W;
+  }
+  // ---- NVLS (opt-in, B200KV_NVLS=1): usable when the launcher gave us a multicast mapping, the
+  // keys are fp32 and every rank's operands sit at the SAME arena offsets (symmetric allocation,
+  // the normal SPMD case); then the switch sums the gradients and multicasts the weights.
+  static const bool want_nvls = []() {
+    const char* z = std::getenv("B200KV_NVLS");
+    return z != nullptr && std::atoi(z) != 0;
+  }();
+  bool nvls = want_nvls && g->has_multicast() && fixed_owner < 0 && W >= 2 && W < kMaxSrc;
+  for (size_t k = 0; nvls && k < ops.size(); ++k) {
+    if (ops[k].e->dtype != kFloat32) nvls = false;
+    const int64_t nout = field(0, k, 4);
+    if (nout > 2 || W * nout > kMaxDst - 2) nvls = false;
+    for (int r = 1; nvls && r < W; ++r) {
+      if (field(r, k, 3) != field(0, k, 3) || field(r, k, 4) != nout) nvls = false;
+      for (int i = 0; nvls && i < nout; ++i) {
+        if (field(r, k, 5 + i) != field(0, k, 5 + i)) nvls = false;
+      }
+    }
+  }
+  if (nvls) {
+    for (size_t k = 0; k < ops.size(); ++k) {
+      KeyDesc& K = kd[k];
+      const int nout = static_cast<int>(field(0, k, 4));
+      if (is_push) K.src[kMaxSrc - 1] = g->McPtr(field(0, k, 3));
+      for (int i = 0; i < nout; ++i) K.out[kMaxDst - 2 + i] = g->McPtr(field(0, k, 5 + i));
+      K.nvls = 1u + static_cast<uint32_t>(nout);
+    }
+    plan->max_src = 1;  // the light instantiation: the switch does the N-way sum
+    plan->nvls = true;
   }
   Engine* eng = Engine::Get();
   Plan::PerDev p;

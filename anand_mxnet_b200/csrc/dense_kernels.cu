@@ -176,6 +176,66 @@ __device__ __forceinline__ void process(const KeyDesc& k, uint32_t base, int n_s
   for (int o = 0; o < n_out; ++o) IO<T, V>::st(static_cast<T*>(k.out[o]) + base, acc);
 }
 
+// ---- NVLS variant of one fp32 vector: the cross-rank sum happens INSIDE the NVSwitch
+// (multimem.ld_reduce on the multicast mapping of the ranks' arenas) and one multimem.st delivers
+// the new weights to every rank, so each GPU receives S/N + (N-1)/N*S bytes per step instead of
+// 2*(N-1)/N*S. The switch's summation order is unspecified: results match the reference within
+// fp32 rounding (1e-6 relative), not bit for bit -- this path is opt-in (B200KV_NVLS=1).
+__device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_f32x4(float* mc, const float (&x)[4]) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(x[0]),
+               "f"(x[1]), "f"(x[2]), "f"(x[3])
+               : "memory");
+}
+
+template <int V> struct MM;
+template <> struct MM<4> {
+  static __device__ __forceinline__ void ld_reduce(const float* mc, float (&x)[4]) {
+    const float4 g = multimem_ld_reduce_f32x4(mc);
+    x[0] = g.x; x[1] = g.y; x[2] = g.z; x[3] = g.w;
+  }
+  static __device__ __forceinline__ void st(float* mc, const float (&x)[4]) { multimem_st_f32x4(mc, x); }
+};
+template <> struct MM<1> {
+  static __device__ __forceinline__ void ld_reduce(const float* mc, float (&x)[1]) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(x[0]) : "l"(mc) : "memory");
+  }
+  static __device__ __forceinline__ void st(float* mc, const float (&x)[1]) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(x[0]) : "memory");
+  }
+};
+
+template <int OPT, int V>
+__device__ __forceinline__ void process_nvls(const KeyDesc& k, uint32_t base, const Hyper& h) {
+  float acc[V], wv[V], s1[V], s2[V];
+  const bool has_mom = k.s1 != nullptr;
+  float* w = static_cast<float*>(k.w);
+  if (OPT != kOptPullOnly) {
+    MM<V>::ld_reduce(static_cast<const float*>(k.src[kMaxSrc - 1]) + base, acc);
+    if (OPT != kOptAssign) {
+      IO<float, V>::ld(w + base, wv);
+      if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::ld(k.s1 + base, s1);
+      if (OPT == kOptAdam) IO<float, V>::ld(k.s2 + base, s2);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = step<OPT>(wv[j], acc[j], s1[j], s2[j], has_mom, h);
+      if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::st(k.s1 + base, s1);
+      if (OPT == kOptAdam) IO<float, V>::st(k.s2 + base, s2);
+    }
+    IO<float, V>::st(w + base, acc);
+  } else {
+    IO<float, V>::ld(w + base, acc);
+  }
+  const int n_mc = static_cast<int>(k.nvls) - 1;
+  for (int o = 0; o < n_mc; ++o) MM<V>::st(static_cast<float*>(k.out[kMaxDst - 2 + o]) + base, acc);
+}
+
 struct KernelArgs {
   const KeyDesc* keys;
   const ChunkDesc* chunks;
@@ -251,11 +311,16 @@ __global__ void __launch_bounds__(kThreads) dense_fused_kernel(const KernelArgs 
   h.beta1 = a.beta1; h.beta2 = a.beta2; h.eps = a.eps;
   const int n_src = sk.n_src, n_out = sk.n_out;
   const uint32_t nvec = sk.vec_ok ? c.len / V : 0;
-  for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) {
-    process<T, MAXSRC, OPT, V>(sk, c.off + v * V, n_src, n_out, a.order, h);
-  }
-  for (uint32_t e = nvec * V + threadIdx.x; e < c.len; e += kThreads) {
-    process<T, MAXSRC, OPT, 1>(sk, c.off + e, n_src, n_out, a.order, h);
+  if (sizeof(T) == 4 && sk.nvls != 0) {
+    for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) process_nvls<OPT, 4>(sk, c.off + v * 4, h);
+    for (uint32_t e = nvec * 4 + threadIdx.x; e < c.len; e += kThreads) process_nvls<OPT, 1>(sk, c.off + e, h);
+  } else {
+    for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) {
+      process<T, MAXSRC, OPT, V>(sk, c.off + v * V, n_src, n_out, a.order, h);
+    }
+    for (uint32_t e = nvec * V + threadIdx.x; e < c.len; e += kThreads) {
+      process<T, MAXSRC, OPT, 1>(sk, c.off + e, n_src, n_out, a.order, h);
+    }
   }
   }  // blockIdx.x < n_chunks
   if (a.pads != nullptr) {

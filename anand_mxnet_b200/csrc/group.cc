@@ -39,7 +39,8 @@ std::vector<int64_t> PeerGroup::AllGatherI64(const std::vector<int64_t>& mine) {
   return GatherI64(fn_, ctx_, world_, mine);
 }
 
-void PeerGroup::Init(int rank, int world, int dev, B200KVAllGatherFnC fn, void* ctx) {
+void PeerGroup::Init(int rank, int world, int dev, B200KVAllGatherFnC fn, void* ctx, void* ext_arena,
+                     size_t ext_bytes, void* const* ext_peers, void* multicast_base) {
   KV_CHECK(g_group == nullptr) << "peer group already initialised";
   KV_CHECK(world >= 1 && world <= kMaxDevices) << "world size must be 1.." << kMaxDevices;
   KV_CHECK(rank >= 0 && rank < world);
@@ -53,9 +54,19 @@ void PeerGroup::Init(int rank, int world, int dev, B200KVAllGatherFnC fn, void* 
   g->fn_ = fn;
   g->ctx_ = ctx;
   DeviceGuard guard(dev);
-  const char* mb = std::getenv("B200KV_IPC_ARENA_MB");
-  g->arena_bytes_ = static_cast<size_t>(mb ? std::max(64, std::atoi(mb)) : 6144) << 20;
-  KV_CUDA(cudaMalloc(&g->arena_, g->arena_bytes_));
+  const bool external = ext_arena != nullptr;
+  if (external) {
+    // arena allocated and peer-mapped by the launcher (torch symmetric memory: same mechanism,
+    // plus an NVSwitch multicast mapping of all ranks' arenas when the fabric supports it)
+    g->arena_ = ext_arena;
+    g->arena_bytes_ = ext_bytes;
+    g->mc_base_ = multicast_base;
+    g->external_arena_ = true;
+  } else {
+    const char* mb = std::getenv("B200KV_IPC_ARENA_MB");
+    g->arena_bytes_ = static_cast<size_t>(mb ? std::max(64, std::atoi(mb)) : 6144) << 20;
+    KV_CUDA(cudaMalloc(&g->arena_, g->arena_bytes_));
+  }
   uint32_t* pad = nullptr;
   KV_CUDA(cudaMalloc(reinterpret_cast<void**>(&pad), kPadWords * sizeof(uint32_t)));
   KV_CUDA(cudaMemset(pad, 0, kPadWords * sizeof(uint32_t)));
@@ -70,7 +81,7 @@ void PeerGroup::Init(int rank, int world, int dev, B200KVAllGatherFnC fn, void* 
   };
   Handles mine;
   std::memset(&mine, 0, sizeof(mine));
-  KV_CUDA(cudaIpcGetMemHandle(&mine.arena, g->arena_));
+  if (!external) KV_CUDA(cudaIpcGetMemHandle(&mine.arena, g->arena_));
   KV_CUDA(cudaIpcGetMemHandle(&mine.pad, pad));
   mine.dev = dev;
   std::vector<Handles> all(world);
@@ -83,8 +94,12 @@ void PeerGroup::Init(int rank, int world, int dev, B200KVAllGatherFnC fn, void* 
     }
     KV_CHECK(all[r].dev != dev) << "ranks " << rank << " and " << r << " share gpu " << dev;
     void* p = nullptr;
-    KV_CUDA(cudaIpcOpenMemHandle(&p, all[r].arena, cudaIpcMemLazyEnablePeerAccess));
-    g->peer_base_[r] = p;
+    if (external) {
+      g->peer_base_[r] = ext_peers[r];
+    } else {
+      KV_CUDA(cudaIpcOpenMemHandle(&p, all[r].arena, cudaIpcMemLazyEnablePeerAccess));
+      g->peer_base_[r] = p;
+    }
     KV_CUDA(cudaIpcOpenMemHandle(&p, all[r].pad, cudaIpcMemLazyEnablePeerAccess));
     g->pads_[r] = static_cast<uint32_t*>(p);
   }
@@ -110,7 +125,7 @@ void PeerGroup::Destroy() {
   DeviceGuard guard(g->dev_);
   for (int r = 0; r < g->world_; ++r) {
     if (r == g->rank_) continue;
-    if (g->peer_base_[r]) cudaIpcCloseMemHandle(g->peer_base_[r]);
+    if (!g->external_arena_ && g->peer_base_[r]) cudaIpcCloseMemHandle(g->peer_base_[r]);
     if (g->pads_[r]) cudaIpcCloseMemHandle(g->pads_[r]);
   }
   // the arena itself is left to process teardown: pooled blocks carved from it may still be cached

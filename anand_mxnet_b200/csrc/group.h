@@ -30,7 +30,14 @@ constexpr int kPadWords = 2 * kMaxDevices * kPadStride;  // start flags, then en
 class PeerGroup {
  public:
   static PeerGroup* Get();  // nullptr until Init()
-  static void Init(int rank, int world, int dev, B200KVAllGatherFnC fn, void* ctx);
+  // ext_arena == nullptr: the library allocates and IPC-exports its own arena. Otherwise the
+  // launcher supplies an arena it has already peer-mapped (ext_peers[r] = rank r's arena as seen
+  // from this rank) and, optionally, an NVSwitch MULTICAST mapping of all ranks' arenas
+  // (multicast_base: a store to it lands in every rank's arena at the same offset, a
+  // multimem.ld_reduce from it returns the sum over all ranks -- NVLS).
+  static void Init(int rank, int world, int dev, B200KVAllGatherFnC fn, void* ctx,
+                   void* ext_arena = nullptr, size_t ext_bytes = 0, void* const* ext_peers = nullptr,
+                   void* multicast_base = nullptr);
   static void Destroy();
 
   int rank() const { return rank_; }
@@ -51,6 +58,8 @@ class PeerGroup {
     return static_cast<const char*>(p) - static_cast<const char*>(arena_);
   }
   void* PeerPtr(int peer, int64_t offset) const { return static_cast<char*>(peer_base_[peer]) + offset; }
+  bool has_multicast() const { return mc_base_ != nullptr; }
+  void* McPtr(int64_t offset) const { return static_cast<char*>(mc_base_) + offset; }
 
   // ---- in-kernel barrier state
   uint32_t* const* d_pads() const { return d_pads_; }  // device array [world] of pad pointers
@@ -65,6 +74,8 @@ class PeerGroup {
   void* arena_ = nullptr;
   size_t arena_bytes_ = 0, arena_used_ = 0;
   void* peer_base_[kMaxDevices] = {nullptr};
+  void* mc_base_ = nullptr;
+  bool external_arena_ = false;
   uint32_t* pads_[kMaxDevices] = {nullptr};
   uint32_t** d_pads_ = nullptr;
   uint32_t* d_counter_ = nullptr;

@@ -42,7 +42,13 @@ struct alignas(16) KeyDesc {
   int32_t n_src;
   int32_t n_out;
   uint32_t vec_ok;           // all pointers 16-byte aligned -> vector path
-  uint32_t pad_[3];
+  // NVLS (one rank per GPU, NVSwitch multicast mapping of the arenas): 0 = off, else 1 + number of
+  // multicast pull targets. src[kMaxSrc-1] is then the MULTICAST address of the gradient (a
+  // multimem.ld_reduce returns the sum over all ranks, added inside the switch) and
+  // out[kMaxDst-2], out[kMaxDst-1] the multicast addresses of the pull targets (one multimem.st
+  // reaches every rank). The unicast src[]/out[] entries stay valid for the scalar tail path.
+  uint32_t nvls;
+  uint32_t pad_[2];
 };
 
 struct alignas(16) ChunkDesc {

@@ -89,6 +89,7 @@ struct Plan {
   std::vector<PerDev> per_dev;
   int n_keys = 0;
   int max_src = 0;
+  bool nvls = false;  // the launch uses NVSwitch multicast reduce / broadcast
   uint64_t algorithmic_bytes = 0;
   ~Plan();
 };
@@ -184,7 +185,8 @@ class KVStore {
                     std::vector<Prepared>* out);
   void RunPrepared(Prepared& p);
   void PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::vector<Prepared>* out);
-  std::shared_ptr<Plan> GetPlanGroup(const std::vector<DenseOp>& ops, int opt_kind);
+  std::shared_ptr<Plan> GetPlanGroup(const std::vector<DenseOp>& ops, int opt_kind, int fixed_owner = -1);
+  void BroadcastInitGroup(const std::vector<int>& keys);
   // call-level cache: a repeated C call (same keys, same arrays) skips grouping/validation/planning
   bool CallSignature(int tag, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
                      const std::vector<int>* okeys, const std::vector<NDArray>* outs,

@@ -163,6 +163,7 @@ void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>&
     }
     local_[keys[i]] = std::move(e);
   }
+  if (dist_) BroadcastInitGroup(keys);
 }
 
 void KVStore::SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle) {

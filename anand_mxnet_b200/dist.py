@@ -42,8 +42,10 @@ def make_allgather_callback(group=None):
     return _ALLGATHER_PROTO(_cb)
 
 
-def init_peer_group(device_id=None):
-    """Create the peer group for the calling torch.distributed job (idempotent)."""
+def init_peer_group(device_id=None, symmetric_memory=None):
+    """Create the peer group for the calling torch.distributed job (idempotent).
+    symmetric_memory=True (default when B200KV_NVLS=1): take the arena from torch symmetric memory
+    so that an NVSwitch multicast mapping is available to the kernels."""
     import torch.distributed as dist
     if _state.get('inited'):
         return
@@ -54,9 +56,46 @@ def init_peer_group(device_id=None):
     # bootstrap traffic is a few hundred bytes on the host: always a gloo group
     cpu_group = dist.new_group(backend='gloo') if dist.get_backend() != 'gloo' else None
     cb = make_allgather_callback(cpu_group)
-    _state.update(cb=cb, group=cpu_group, inited=True, rank=rank, world=world, device=device_id)
+    _state.update(cb=cb, group=cpu_group, inited=True, rank=rank, world=world, device=device_id,
+                  multicast=False)
+    if symmetric_memory is None:
+        symmetric_memory = os.environ.get('B200KV_NVLS', '0') not in ('', '0')
+    if symmetric_memory and _init_with_symmetric_memory(rank, world, device_id, cb):
+        return
     check_call(_LIB.B200KVGroupInit(ctypes.c_int(rank), ctypes.c_int(world), ctypes.c_int(device_id),
                                     cb, None))
+
+
+def _init_with_symmetric_memory(rank, world, device_id, cb):
+    """Arena from torch symmetric memory: torch allocates, peer-maps and (on NVSwitch fabrics)
+    creates the MULTICAST mapping of all ranks' arenas; the library only receives the pointers.
+    Needed for the NVLS mode of the fused kernel (B200KV_NVLS=1). Returns False when unavailable."""
+    try:
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        mb = int(os.environ.get('B200KV_IPC_ARENA_MB', '6144'))
+        dev = torch.device('cuda', device_id)
+        arena = symm_mem.empty(mb << 20, dtype=torch.uint8, device=dev)
+        hdl = symm_mem.rendezvous(arena, dist.group.WORLD)
+        peers = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(hdl.multicast_ptr) if hdl.multicast_ptr else 0
+        assert peers[rank] == arena.data_ptr()
+    except Exception as e:  # pragma: no cover - depends on fabric / driver support
+        print("b200kv: symmetric-memory arena unavailable (%s); using the CUDA-IPC arena" % (e,))
+        return False
+    peer_arr = (ctypes.c_void_p * world)(*peers)
+    check_call(_LIB.B200KVGroupInitExternal(ctypes.c_int(rank), ctypes.c_int(world),
+                                            ctypes.c_int(device_id), cb, None,
+                                            ctypes.c_void_p(arena.data_ptr()),
+                                            ctypes.c_size_t(arena.numel()), peer_arr,
+                                            ctypes.c_void_p(mc or None)))
+    _state.update(arena=arena, symm_handle=hdl, multicast=bool(mc))
+    return True
+
+
+def has_multicast():
+    return bool(_state.get('multicast'))
 
 
 def destroy_peer_group():

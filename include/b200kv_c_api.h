@@ -213,6 +213,15 @@ B200KV_DLL int B200KVEngineGetStream(int dev_id, void** cuda_stream);
 typedef int (*B200KVAllGatherFn)(const void* send, void* recv, size_t nbytes, void* ctx);
 B200KV_DLL int B200KVGroupInit(int rank, int world_size, int dev_id, B200KVAllGatherFn allgather,
                                void* ctx);
+/* Same, with an arena the launcher has already allocated and peer-mapped (e.g. torch symmetric
+ * memory): peer_arenas[r] = rank r's arena as addressable from this rank (entry `rank` = arena);
+ * multicast_arena = NVSwitch multicast mapping of all ranks' arenas or NULL. With a multicast
+ * mapping and B200KV_NVLS=1 the fused kernel sums gradients in the switch (multimem.ld_reduce) and
+ * multicasts the weights (multimem.st). */
+B200KV_DLL int B200KVGroupInitExternal(int rank, int world_size, int dev_id,
+                                       B200KVAllGatherFn allgather, void* ctx, void* arena,
+                                       size_t arena_bytes, void* const* peer_arenas,
+                                       void* multicast_arena);
 B200KV_DLL int B200KVGroupDestroy(void);
 
 /* Introspection for tests / bench / profiling. */

@@ -23,7 +23,7 @@ def _grad(rank, step, k, shape):
     return np.random.default_rng(1000 * rank + 17 * step + k).uniform(-1, 1, shape).astype(np.float32)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, nvls=False):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, "oracle")]
@@ -33,6 +33,8 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     os.environ["LOCAL_RANK"] = str(rank)
     os.environ["B200KV_IPC_ARENA_MB"] = "512"
+    if nvls:
+        os.environ["B200KV_NVLS"] = "1"
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     errors = []
@@ -43,9 +45,16 @@ def _worker(rank, world, port, q):
         ctx = mx.gpu(rank)
         keys = list(range(len(SHAPES)))
 
+        in_switch = nvls and mx.dist.has_multicast()
+
         def eq(a, b):
-            return np.array_equal(np.ascontiguousarray(a).view(np.uint8),
-                                  np.ascontiguousarray(b).view(np.uint8))
+            a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+            if in_switch:
+                # the NVSwitch chooses the summation order: the reference's own bound applies
+                # (tests/nightly/test_kvstore.py:95-98: sum|delta| / sum|ref| < 1e-6)
+                return a.shape == b.shape and \
+                    np.abs(a.astype(np.float64) - b).sum() <= 1e-6 * max(np.abs(b).sum(), 1e-30)
+            return np.array_equal(a.view(np.uint8), b.view(np.uint8))
         for kvtype, order in (("device", "device"), ("local", "local")):
             # ---- plain reduce + broadcast (no optimizer)
             kv = mx.kv.create(kvtype)
@@ -91,6 +100,16 @@ def _worker(rank, world, port, q):
             for k in keys:
                 if not eq(fresh[k].asnumpy(), model.pull(k)):
                     errors.append("pull %s key %d" % (kvtype, k))
+        # kv.init: "only the value supplied by worker with rank 0 is used" (kvstore.py:136-141)
+        kv = mx.kv.create('device')
+        vals0 = [np.random.default_rng(5 + k).uniform(-1, 1, s).astype(np.float32)
+                 for k, s in enumerate(SHAPES)]
+        kv.init(keys, [mx.nd.array(v + np.float32(rank), ctx) for v in vals0])
+        got = [mx.nd.empty(s, ctx) for s in SHAPES]
+        kv.pull(keys, out=got)
+        for k in keys:
+            if not eq(got[k].asnumpy(), vals0[k]):
+                errors.append("init broadcast key %d" % k)
         mx.nd.waitall()
         dist.barrier()
         mx.dist.destroy_peer_group()
@@ -99,11 +118,13 @@ def _worker(rank, world, port, q):
         errors.append(traceback.format_exc())
     finally:
         q.put((rank, errors))
+        if nvls and rank == 0:
+            print('NVLS multicast in use:', 'in_switch' in dir() and in_switch)
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_peer_group_parity(world):
+@pytest.mark.parametrize("world,nvls", [(2, False), (4, False), (2, True), (4, True)])
+def test_peer_group_parity(world, nvls):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
@@ -111,7 +132,7 @@ def test_peer_group_parity(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, nvls)) for r in range(world)]
     for p in procs:
         p.start()
     results = []
