@@ -91,40 +91,51 @@ struct RspUpdateLaunch {
   float* w = nullptr; float* s1 = nullptr; float* s2 = nullptr;
   const int64_t* gidx = nullptr; const float* gval = nullptr;
   int64_t nrows = 0, row_len = 0;
+  const int64_t* d_nrows = nullptr;  // when set: the row count lives on the device, nrows bounds it
   int opt = kOptSGDSingle;
   float lr = 0.f, wd = 0.f, momentum = 0.f, rescale = 1.f, clip = -1.f, beta1 = 0.9f,
         beta2 = 0.999f, eps = 1e-8f;
 };
 void LaunchRspUpdate(const RspUpdateLaunch& p, cudaStream_t stream);
 
-// union of row ids + in-order accumulation (ndarray_function.cc:59-175 semantics).
-// Phase 1 (device): sorted unique union of all source ids -> out_idx, count -> *d_nnr.
-size_t RspUnionWorkspaceBytes(int64_t total_ids);
-void LaunchRspUnion(const int64_t* const* d_src_idx, const int64_t* h_src_nrows, int nsrc,
-                    int64_t total_ids, int64_t* out_idx, int64_t* d_nnr, void* workspace,
-                    size_t workspace_bytes, cudaStream_t stream);
-// Phase 2: out_val[r] = 0.0f + sum over sources in list order of the rows whose id == out_idx[r]
-struct RspSumLaunch {
-  const int64_t* const* src_idx = nullptr;  // device array [nsrc] of device pointers
-  const float* const* src_val = nullptr;    // device array [nsrc]
-  const int64_t* src_nrows = nullptr;       // device array [nsrc]
+// union of row ids + in-order accumulation (ndarray_function.cc:59-175 semantics), one call:
+//   tag      keys[i] = id, vals[i] = i over the concatenation of the sources' id lists
+//   sort     stable radix sort of (key, val) on the low `id_bits` bits only
+//   heads    positions where the sorted id changes -> segment starts, count -> *d_nnr
+//   sum      one warp per segment: out_idx[r] = id, out_val[r] = 0.0f + rows in SOURCE ORDER
+//            (the stable sort keeps equal ids in concatenation = source order)
+// No binary searches, no host read of the count: the sum grid covers `total` rows and warps
+// beyond *d_nnr exit.
+struct RspSources {
+  const int64_t* idx[kMaxSrc];
+  const float* val[kMaxSrc];
+  int64_t start[kMaxSrc + 1];  // prefix of the row counts; start[nsrc] = total
   int nsrc = 0;
-  const int64_t* out_idx = nullptr; float* out_val = nullptr;
-  int64_t nnr = 0, row_len = 0;
 };
-void LaunchRspSum(const RspSumLaunch& p, cudaStream_t stream);
-// sort + unique of int64 ids (kvstore_utils.cu:43-97 semantics); count -> *d_count
-size_t UniqueWorkspaceBytes(int64_t n);
-void LaunchUnique(const int64_t* ids, int64_t n, int64_t* out, int64_t* d_count, void* workspace,
-                  size_t workspace_bytes, cudaStream_t stream);
-// sparse_retain (sparse_retain-inl.h:121-150,262-323): out_idx = ids verbatim, rows gathered
-struct RetainLaunch {
-  const int64_t* src_idx = nullptr; const float* src_val = nullptr; int64_t src_nnr = 0;
-  int src_dense_rows = 0;  // the source holds every row: id is the row position
-  const int64_t* ids = nullptr; int64_t nids = 0; int64_t row_len = 0;
-  int64_t* out_idx = nullptr; float* out_val = nullptr;
+size_t RspMergeWorkspaceBytes(int64_t total_ids);
+void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_t* out_idx,
+                    float* out_val, int64_t* d_nnr, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
+
+// row_sparse_pull for a batch of (row_ids, out) pairs that share an owner GPU
+// (kvstore_local.h:263-283 + kvstore_utils.cu:43-97 Unique + sparse_retain-inl.h:121-150,262-323):
+//   gather   comp[i] = item << id_bits | id over the concatenation of all items' row_ids
+//   sort + unique of comp (one radix sort for the whole batch, id_bits + item_bits bits)
+//   bounds   off[k] = first unique entry of item k (off[nitems] = total unique) -> device + host
+//   retain   one warp per (item, unique id): out_idx = id, row copied where present else zeros
+struct RetainItem {
+  const void* ids; int ids_dtype; int64_t n; int64_t start;  // start: prefix of n over the batch
+  const int64_t* src_idx; const float* src_val; int64_t src_nnr; int src_dense_rows;
+  int64_t row_len;
+  int64_t* out_idx; float* out_val;
 };
-void LaunchRetain(const RetainLaunch& p, cudaStream_t stream);
+size_t RetainBatchWorkspaceBytes(int nitems, int64_t total_ids);
+// d_items: device copy of `nitems` RetainItem (inside the workspace, filled by the callee from
+// h_items); d_off: device int64[nitems + 1]
+void LaunchUniqueBatch(const RetainItem* h_items, int nitems, int64_t total_ids, int id_bits,
+                       int64_t* d_off, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+void LaunchRetainBatch(int nitems, int64_t total_ids, int id_bits, const int64_t* d_off,
+                       void* workspace, cudaStream_t stream);
 
 // ---- 2-bit gradient compression with residual (compress_kernels.cu;
 // src/kvstore/gradient_compression-inl.h:40-132, comm.h:552-596 ReduceCompressed) ----

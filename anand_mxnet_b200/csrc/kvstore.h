@@ -211,8 +211,8 @@ class KVStore {
 
   // row_sparse machinery (rowsparse.cc)
   void PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs);
-  void PullRowSparseOne(KeyEntry& e, const NDArray& out, const NDArray& row_ids);
-  NDArray UniqueRowIds(const NDArray& row_ids, int dev, int64_t* count);
+  void PullRowSparseGroup(int home, const std::vector<size_t>& which, const std::vector<int>& keys,
+                          const std::vector<NDArray>& outs, const std::vector<NDArray>& row_ids);
 
   std::string type_;
   bool dist_ = false;         // created inside a one-rank-per-GPU peer group

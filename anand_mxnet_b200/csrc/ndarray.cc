@@ -78,6 +78,11 @@ void* NDArray::data() const {
   return static_cast<char*>(st_->dptr) + byte_offset_;
 }
 
+bool NDArray::RowsFit(int64_t nnr) const {
+  return static_cast<size_t>(nnr) * RowLength() * DTypeSize(dtype_) <= st_->bytes &&
+         static_cast<size_t>(nnr) * sizeof(int64_t) <= st_->aux_bytes;
+}
+
 void NDArray::CheckAndAllocRows(int64_t nnr) const {
   KV_CHECK_EQ(stype_, kRowSparseStorage);
   KV_CHECK(!st_->external) << "cannot re-allocate an external row_sparse array";

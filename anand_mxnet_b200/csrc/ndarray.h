@@ -94,6 +94,7 @@ class NDArray {
   bool storage_initialized() const { return stype_ == kDefaultStorage ? true : st_->nnr > 0; }
   // row_sparse: make room for `nnr` rows (contents undefined) and set aux_shape = nnr
   void CheckAndAllocRows(int64_t nnr) const;
+  bool RowsFit(int64_t nnr) const;  // CheckAndAllocRows(nnr) would not re-allocate
   void SetNnr(int64_t nnr) const { st_->nnr = nnr; }
 
   // views used by MXNDArrayGetDataNDArray / GetAuxNDArray: dense arrays aliasing the blobs

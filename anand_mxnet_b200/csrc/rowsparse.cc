@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <iostream>
+#include <map>
 
 #include "kvstore.h"
 #include "scalar_parse.h"
@@ -17,15 +18,38 @@ namespace b200kv {
 
 namespace {
 
-// blocking read of one int64 the device just produced (the reference blocks at the same point:
-// ndarray_function.cu:158-166, kvstore_utils.cu:77-85)
-int64_t ReadCount(int dev, const int64_t* d_count) {
-  Engine* eng = Engine::Get();
-  int64_t h = 0;
-  DeviceGuard g(dev);
-  KV_CUDA(cudaMemcpyAsync(&h, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, eng->Stream(dev)));
-  KV_CUDA(cudaStreamSynchronize(eng->Stream(dev)));
-  return h;
+// The device produces row counts; the host needs them only to set an array's aux shape (the
+// reference blocks on the same values: ndarray_function.cu:158-166, kvstore_utils.cu:77-85).
+// Counts are copied into pinned memory behind an event, so kernels queued after the copy are
+// already running while the host waits for the numbers.
+struct CountFence {
+  int dev;
+  int64_t* host;
+  size_t n;
+  cudaEvent_t ev = nullptr;
+  CountFence(int d, size_t count) : dev(d), n(count) {
+    host = static_cast<int64_t*>(Engine::Get()->AllocPinned(n * sizeof(int64_t)));
+  }
+  ~CountFence() {
+    if (ev) cudaEventDestroy(ev);
+    Engine::Get()->FreePinned(host, n * sizeof(int64_t));
+  }
+  void Post(const int64_t* d_counts, cudaStream_t st) {
+    DeviceGuard g(dev);
+    KV_CUDA(cudaMemcpyAsync(host, d_counts, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    KV_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    KV_CUDA(cudaEventRecord(ev, st));
+  }
+  const int64_t* Wait() {
+    KV_CUDA(cudaEventSynchronize(ev));
+    return host;
+  }
+};
+
+int BitsFor(int64_t n) {  // bits that hold every id in [0, n)
+  int b = 1;
+  while (b < 62 && (int64_t{1} << b) < n) ++b;
+  return b;
 }
 
 struct Scratch {
@@ -70,62 +94,49 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     KV_CHECK_EQ(en, static_cast<int>(parts.size() * (parts.size() - 1)))
         << "GPU peer access is not available between all participating devices";
   }
-  // ---- union of ids
+  // ---- union of ids + ordered sum, all on the owner's stream, row count left on the device
+  RspSources S;
   int64_t total = 0;
-  std::vector<const int64_t*> h_idx;
-  std::vector<const float*> h_val;
-  std::vector<int64_t> h_n;
   for (auto& s : srcs) {
     if (!s.storage_initialized()) continue;  // all-zero source
-    h_idx.push_back(s.row_ids());
-    h_val.push_back(static_cast<const float*>(s.data()));
-    h_n.push_back(s.nnr());
+    S.idx[S.nsrc] = s.row_ids();
+    S.val[S.nsrc] = static_cast<const float*>(s.data());
+    S.start[S.nsrc] = total;
     total += s.nnr();
+    ++S.nsrc;
   }
+  S.start[S.nsrc] = total;
   NDArray merged = NDArray::RowSparse(e.shape, Context::GPU(home), e.dtype);
   const int64_t row_len = static_cast<int64_t>(e.rsp.RowLength());
+  const bool fused = opt_.enabled && (opt_.kind == kOptSGD || opt_.kind == kOptAdam);
+  NDArray d_nnr({1}, Context::GPU(home), kInt64);  // lives until the kernels that read it retire
   if (total > 0) {
-    merged.CheckAndAllocRows(total);
+    merged.CheckAndAllocRows(total);   // upper bound; nnr is set below when the host needs it
     for (auto& s : srcs) eng->BeginRead(s.dev(), *s.var());
     if (parts.size() > 1) eng->JoinStreams(parts);
     DeviceGuard g(home);
     cudaStream_t st = eng->Stream(home);
-    const int nsrc = static_cast<int>(h_idx.size());
-    Scratch ws(home, RspUnionWorkspaceBytes(total));
-    Scratch tbl(home, 1024 + nsrc * 3 * sizeof(void*));
-    int64_t* d_count = static_cast<int64_t*>(tbl.p);
-    LaunchRspUnion(h_idx.data(), h_n.data(), nsrc, total, merged.row_ids(), d_count, ws.p, ws.bytes, st);
-    eng->CountLaunch("rsp_union(cub sort+unique)", total * 16);
-    const int64_t nnr = ReadCount(home, d_count);
-    merged.SetNnr(nnr);
-    // ---- in-order accumulation
-    char* t = static_cast<char*>(tbl.p) + 256;
-    KV_CUDA(cudaMemcpyAsync(t, h_idx.data(), nsrc * sizeof(void*), cudaMemcpyHostToDevice, st));
-    KV_CUDA(cudaMemcpyAsync(t + nsrc * sizeof(void*), h_val.data(), nsrc * sizeof(void*),
-                            cudaMemcpyHostToDevice, st));
-    KV_CUDA(cudaMemcpyAsync(t + 2 * nsrc * sizeof(void*), h_n.data(), nsrc * sizeof(int64_t),
-                            cudaMemcpyHostToDevice, st));
-    RspSumLaunch L;
-    L.src_idx = reinterpret_cast<const int64_t* const*>(t);
-    L.src_val = reinterpret_cast<const float* const*>(t + nsrc * sizeof(void*));
-    L.src_nrows = reinterpret_cast<const int64_t*>(t + 2 * nsrc * sizeof(void*));
-    L.nsrc = nsrc;
-    L.out_idx = merged.row_ids();
-    L.out_val = static_cast<float*>(merged.data());
-    L.nnr = nnr;
-    L.row_len = row_len;
-    LaunchRspSum(L, st);
-    eng->CountLaunch("rsp_sum", static_cast<uint64_t>(total + nnr) * row_len * 4);
+    Scratch ws(home, RspMergeWorkspaceBytes(total));
+    LaunchRspMerge(S, BitsFor(e.shape[0]), row_len, merged.row_ids(), static_cast<float*>(merged.data()),
+                   static_cast<int64_t*>(d_nnr.data()), ws.p, ws.bytes, st);
+    eng->CountLaunch("rsp_merge(tag, sort, heads)", total * 24);
+    eng->CountLaunch("rsp_sum", static_cast<uint64_t>(total) * row_len * 4 * 2);
     if (parts.size() > 1) eng->JoinStreams(parts);
     uint64_t seq = eng->Issue(home);
     eng->MarkWrite(home, seq, merged.var());
+    eng->MarkWrite(home, seq, d_nnr.var());
     for (auto& s : srcs) {
       uint64_t sq = s.dev() == home ? seq : eng->Issue(s.dev());
       eng->MarkRead(s.dev(), sq, s.var());
     }
+    if (!fused) {
+      CountFence f(home, 1);
+      f.Post(static_cast<const int64_t*>(d_nnr.data()), st);
+      merged.SetNnr(f.Wait()[0]);
+    }
   }
   // ---- consume the merged gradient
-  if (opt_.enabled && (opt_.kind == kOptSGD || opt_.kind == kOptAdam)) {
+  if (fused) {
     KV_CHECK(opt_.lazy_update) << "lazy_update=False for row_sparse gradients is a next-row item";
     KV_CHECK_EQ(e.rsp.nnr(), e.shape[0])
         << "key " << e.key << ": the stored row_sparse weight must hold every row for sparse "
@@ -135,7 +146,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     int c = (it == opt_.count.end() ? opt_.begin_num_update : it->second) + 1;
     opt_.count[e.key] = c;
     opt_.num_update = std::max(opt_.num_update, c);
-    if (merged.nnr() == 0) return;
+    if (total == 0) return;
     auto lm = opt_.lr_mult.find(e.key);
     auto wm = opt_.wd_mult.find(e.key);
     double lrd = opt_.lr * (lm == opt_.lr_mult.end() ? 1.0 : lm->second);
@@ -173,15 +184,17 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     U.s2 = s.s2.is_none() ? nullptr : static_cast<float*>(s.s2.data());
     U.gidx = merged.row_ids();
     U.gval = static_cast<const float*>(merged.data());
-    U.nrows = merged.nnr();
+    U.nrows = total;  // upper bound of the grid; the kernel reads the union's size on the device
+    U.d_nrows = static_cast<const int64_t*>(d_nnr.data());
     U.row_len = row_len;
     DeviceGuard g(home);
     eng->BeginWrite(home, *e.rsp.var());
     LaunchRspUpdate(U, eng->Stream(home));
-    eng->CountLaunch("rsp_update", static_cast<uint64_t>(merged.nnr()) * row_len * 4 * 3);
+    eng->CountLaunch("rsp_update", static_cast<uint64_t>(total) * row_len * 4 * 3);
     uint64_t seq = eng->Issue(home);
     eng->MarkWrite(home, seq, e.rsp.var());
     eng->MarkRead(home, seq, merged.var());
+    eng->MarkRead(home, seq, d_nnr.var());
     return;
   }
   if (updater_ != nullptr && !opt_.enabled) {
@@ -197,36 +210,11 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
   e.rsp = merged;  // no updater: local = merged (kvstore_local.h:237-243)
 }
 
-// KVStoreLocal::Unique (kvstore_local.h:428-472): ids of any integer/float dtype and any shape ->
-// ascending unique int64 in a row_sparse container whose aux_shape is the unique count.
-NDArray KVStore::UniqueRowIds(const NDArray& row_ids, int dev, int64_t* count) {
-  Engine* eng = Engine::Get();
-  const int64_t n = static_cast<int64_t>(row_ids.Size());
-  NDArray ids_dev = row_ids.on_gpu() && row_ids.dev() == dev ? row_ids : row_ids.Copy(Context::GPU(dev));
-  NDArray out({std::max<int64_t>(n, 1)}, Context::GPU(dev), kInt64);
-  *count = 0;
-  if (n == 0) return out;
-  DeviceGuard g(dev);
-  cudaStream_t st = eng->Stream(dev);
-  eng->BeginRead(dev, *ids_dev.var());
-  NDArray ids64 = ids_dev;
-  if (ids_dev.dtype() != kInt64) {
-    ids64 = NDArray({n}, Context::GPU(dev), kInt64);
-    LaunchCast(ids64.data(), kInt64, ids_dev.data(), ids_dev.dtype(), n, st);
-    eng->CountLaunch("cast", 0);
-  }
-  Scratch ws(dev, UniqueWorkspaceBytes(n));
-  Scratch cnt(dev, 256);
-  LaunchUnique(static_cast<const int64_t*>(ids64.data()), n, static_cast<int64_t*>(out.data()),
-               static_cast<int64_t*>(cnt.p), ws.p, ws.bytes, st);
-  eng->CountLaunch("unique(cub sort+unique)", n * 16);
-  uint64_t seq = eng->Issue(dev);
-  eng->MarkRead(dev, seq, ids_dev.var());
-  eng->MarkWrite(dev, seq, out.var());
-  *count = ReadCount(dev, static_cast<int64_t*>(cnt.p));
-  return out;  // the first *count entries are the ascending unique ids
-}
-
+// row_sparse_pull (KVStoreLocal::PullRowSparseImpl kvstore_local.h:263-283, Unique :428-472,
+// CommDevice::BroadcastRowSparse comm.h:618-674): every (key, out, row_ids) triple gets the
+// ascending unique ids requested and the stored rows for them. All triples that share an owner
+// GPU go through ONE sort/unique and ONE retain kernel; the per-output counts come back through
+// a CountFence while the retain kernel is already running.
 void KVStore::PullRowSparse(const std::vector<int>& keys, const std::vector<NDArray>& outs,
                             const std::vector<NDArray>& row_ids, int) {
   KV_CHECK_EQ(keys.size(), outs.size());
@@ -243,69 +231,113 @@ void KVStore::PullRowSparse(const std::vector<int>& keys, const std::vector<NDAr
         << "Expected default storage type for row_sparse_pull rowids, but detected storage type "
         << row_ids[i].stype();
   }
+  Engine* eng = Engine::Get();
+  std::map<int, std::vector<size_t>> by_home;  // owner GPU -> triples, in key order
   for (size_t i : order) {
     KeyEntry& e = Entry(keys[i]);
     KV_CHECK_EQ(e.stype, kRowSparseStorage) << "PullRowSparse expects row_sparse src NDArray";
-    PullRowSparseOne(e, outs[i], row_ids[i]);
+    const NDArray& out = outs[i];
+    if (e.home < 0) e.home = out.on_gpu() ? out.dev() : (row_ids[i].on_gpu() ? row_ids[i].dev() : 0);
+    if (!e.rsp.on_gpu()) e.rsp = e.rsp.Copy(Context::GPU(e.home));
+    KV_CHECK(out.shape() == e.shape) << "row_sparse_pull: out shape mismatch for key " << e.key;
+    KV_CHECK_EQ(out.dtype(), e.dtype) << "row_sparse_pull: out dtype mismatch for key " << e.key;
+    if (out.SameStorage(e.rsp)) {
+      std::cerr << "The output of row_sparse_pull() on key " << e.key << " refers to the same NDArray "
+                << "as the one stored in KVStore. Consider a new NDArray buffer for the output.\n";
+    }
+    if (row_ids[i].Size() == 0 || !e.rsp.storage_initialized()) {
+      // FillZerosRspImpl (sparse_retain-inl.h:271-275)
+      eng->WaitToWrite(*out.var());
+      out.SetNnr(0);
+      continue;
+    }
+    by_home[e.home].push_back(i);
   }
+  for (auto& kv : by_home) PullRowSparseGroup(kv.first, kv.second, keys, outs, row_ids);
 }
 
-void KVStore::PullRowSparseOne(KeyEntry& e, const NDArray& out, const NDArray& row_ids) {
+void KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
+                                 const std::vector<int>& keys, const std::vector<NDArray>& outs,
+                                 const std::vector<NDArray>& row_ids) {
   Engine* eng = Engine::Get();
-  if (e.home < 0) e.home = out.on_gpu() ? out.dev() : (row_ids.on_gpu() ? row_ids.dev() : 0);
-  const int home = e.home;
-  if (!e.rsp.on_gpu()) e.rsp = e.rsp.Copy(Context::GPU(home));
-  KV_CHECK(out.shape() == e.shape) << "row_sparse_pull: out shape mismatch for key " << e.key;
-  KV_CHECK_EQ(out.dtype(), e.dtype) << "row_sparse_pull: out dtype mismatch for key " << e.key;
-  if (out.SameStorage(e.rsp)) {
-    std::cerr << "The output of row_sparse_pull() on key " << e.key << " refers to the same NDArray "
-              << "as the one stored in KVStore. Consider a new NDArray buffer for the output.\n";
+  const int nitems = static_cast<int>(which.size());
+  std::vector<RetainItem> items(nitems);
+  std::vector<NDArray> ids(nitems), targets(nitems);
+  std::vector<int> parts{home};
+  auto add_part = [&](int d) {
+    if (std::find(parts.begin(), parts.end(), d) == parts.end()) parts.push_back(d);
+  };
+  int64_t total = 0;
+  int id_bits = 1;
+  for (int k = 0; k < nitems; ++k) {
+    const size_t i = which[k];
+    KeyEntry& e = Entry(keys[i]);
+    const NDArray& out = outs[i];
+    // ids are read in place when they live on a GPU (peer load), else copied to the owner
+    ids[k] = row_ids[i].on_gpu() ? row_ids[i] : row_ids[i].Copy(Context::GPU(home));
+    add_part(ids[k].dev());
+    // rows go straight into `out` when it lives on a GPU (peer store over NVLink)
+    targets[k] = out.on_gpu() ? out : NDArray::RowSparse(e.shape, Context::GPU(home), e.dtype);
+    add_part(targets[k].dev());
+    const int64_t n = static_cast<int64_t>(ids[k].Size());
+    if (!targets[k].RowsFit(n)) eng->WaitToWrite(*targets[k].var());  // buffers get re-allocated
+    targets[k].CheckAndAllocRows(n);       // upper bound; nnr is set once the count is known
+    RetainItem& it = items[k];
+    it.ids = ids[k].data();
+    it.ids_dtype = ids[k].dtype();
+    it.n = n;
+    it.start = total;
+    it.src_idx = e.rsp.row_ids();
+    it.src_val = static_cast<const float*>(e.rsp.data());
+    it.src_nnr = e.rsp.nnr();
+    it.src_dense_rows = e.rsp.nnr() == e.shape[0] ? 1 : 0;  // sparse_retain-inl.h:290
+    it.row_len = static_cast<int64_t>(e.rsp.RowLength());
+    it.out_idx = targets[k].row_ids();
+    it.out_val = static_cast<float*>(targets[k].data());
+    total += n;
+    id_bits = std::max(id_bits, BitsFor(e.shape[0]));
   }
-  int64_t m = 0;
-  NDArray uniq = UniqueRowIds(row_ids, home, &m);
-  // retain on the owner, straight into `out` when it lives on a GPU (peer store over NVLink)
-  const bool direct = out.on_gpu();
-  NDArray target = direct ? out : NDArray::RowSparse(e.shape, Context::GPU(home), e.dtype);
-  if (m == 0 || !e.rsp.storage_initialized()) {
-    // FillZerosRspImpl (sparse_retain-inl.h:271-275)
-    eng->WaitToWrite(*out.var());
-    out.SetNnr(0);
-    return;
+  if (parts.size() > 1) {
+    int en = eng->EnablePeerAccess(parts);
+    KV_CHECK_EQ(en, static_cast<int>(parts.size() * (parts.size() - 1)))
+        << "GPU peer access is not available between all participating devices";
   }
-  if (direct && out.dev() != home) {
-    int en = eng->EnablePeerAccess({home, out.dev()});
-    KV_CHECK_EQ(en, 2) << "GPU peer access is not available between gpu " << home << " and gpu "
-                       << out.dev();
+  for (int k = 0; k < nitems; ++k) {
+    eng->BeginRead(ids[k].dev(), *ids[k].var());
+    eng->BeginRead(home, *Entry(keys[which[k]]).rsp.var());
+    eng->BeginWrite(targets[k].dev(), *targets[k].var());
   }
-  target.CheckAndAllocRows(m);
-  eng->BeginRead(home, *e.rsp.var());
-  eng->BeginWrite(home, *target.var());
-  if (direct && out.dev() != home) eng->JoinStreams({home, out.dev()});
-  RetainLaunch L;
-  L.src_idx = e.rsp.row_ids();
-  L.src_val = static_cast<const float*>(e.rsp.data());
-  L.src_nnr = e.rsp.nnr();
-  L.src_dense_rows = e.rsp.nnr() == e.shape[0] ? 1 : 0;  // sparse_retain-inl.h:290
-  L.ids = static_cast<const int64_t*>(uniq.data());
-  L.nids = m;
-  L.row_len = static_cast<int64_t>(e.rsp.RowLength());
-  L.out_idx = target.row_ids();
-  L.out_val = static_cast<float*>(target.data());
+  if (parts.size() > 1) eng->JoinStreams(parts);
+  CountFence fence(home, nitems + 1);
+  NDArray d_off({nitems + 1}, Context::GPU(home), kInt64);
+  NDArray ws({static_cast<int64_t>(RetainBatchWorkspaceBytes(nitems, total))}, Context::GPU(home), kUint8);
   {
     DeviceGuard g(home);
-    LaunchRetain(L, eng->Stream(home));
+    cudaStream_t st = eng->Stream(home);
+    LaunchUniqueBatch(items.data(), nitems, total, id_bits, static_cast<int64_t*>(d_off.data()),
+                      ws.data(), ws.ByteSize(), st);
+    eng->CountLaunch("unique_batch(gather, sort, unique, bounds)", total * 32);
+    fence.Post(static_cast<const int64_t*>(d_off.data()), st);
+    LaunchRetainBatch(nitems, total, id_bits, static_cast<const int64_t*>(d_off.data()), ws.data(), st);
+    uint64_t bytes = 0;
+    for (auto& it : items) bytes += static_cast<uint64_t>(it.n) * (it.row_len * 8 + 16);
+    eng->CountLaunch("sparse_retain", bytes);
   }
-  eng->CountLaunch("sparse_retain", static_cast<uint64_t>(m) * (L.row_len * 8 + 16));
-  if (direct && out.dev() != home) eng->JoinStreams({home, out.dev()});
+  if (parts.size() > 1) eng->JoinStreams(parts);
   uint64_t seq = eng->Issue(home);
-  eng->MarkRead(home, seq, e.rsp.var());
-  eng->MarkRead(home, seq, uniq.var());
-  if (direct) {
-    uint64_t sq = out.dev() == home ? seq : eng->Issue(out.dev());
-    eng->MarkWrite(out.dev(), sq, out.var());
-  } else {
-    eng->MarkWrite(home, seq, target.var());
-    CopyFromTo(target, out);
+  eng->MarkWrite(home, seq, d_off.var());
+  eng->MarkWrite(home, seq, ws.var());
+  for (int k = 0; k < nitems; ++k) {
+    eng->MarkRead(home, seq, Entry(keys[which[k]]).rsp.var());
+    eng->MarkRead(ids[k].dev(), ids[k].dev() == home ? seq : eng->Issue(ids[k].dev()), ids[k].var());
+    eng->MarkWrite(targets[k].dev(), targets[k].dev() == home ? seq : eng->Issue(targets[k].dev()),
+                   targets[k].var());
+  }
+  const int64_t* off = fence.Wait();
+  for (int k = 0; k < nitems; ++k) {
+    targets[k].SetNnr(off[k + 1] - off[k]);
+    const NDArray& out = outs[which[k]];
+    if (!out.on_gpu()) CopyFromTo(targets[k], out);
   }
 }
 

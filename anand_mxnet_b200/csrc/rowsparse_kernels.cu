@@ -4,16 +4,20 @@
 //   * reduce: out ids = ascending unique union of the sources' ids; out rows start at 0.0f and the
 //     sources are accumulated in list order (src/ndarray/ndarray_function.cc:59-175 on CPU,
 //     ndarray_function.cu:104-190 on GPU -- the GPU version marks a flag array as long as the whole
-//     table (1M rows -> 8 MB scan); here the union is a radix sort + unique over the <= N*nnr ids
-//     actually present, independent of table height);
+//     table (1M rows -> 8 MB scan); here the union is a radix sort over the <= N*nnr ids actually
+//     present, independent of table height);
 //   * unique: sort + unique of the requested row ids (src/kvstore/kvstore_utils.cu:43-97);
 //   * retain: every requested id is emitted, rows copied where present else zero
 //     (src/operator/tensor/sparse_retain-inl.h:121-150,262-323);
 //   * lazy optimizer updates over the gradient's rows (optimizer_op-inl.h:426-475,749-801,1350-1408).
 //
-// Row gathers/scatters are HBM-bound: one warp per row, 16-byte accesses along the row, ids looked
-// up once per warp by binary search (sources are sorted), no atomics (the union makes every output
-// row single-writer and the in-order source loop keeps the float association deterministic).
+// Row gathers/scatters are HBM- (or NVLink-) bound: one warp per row, 16-byte accesses along the
+// row, all of a row's source loads issued before the ordered adds. The id bookkeeping is arranged
+// so that no warp ever chases pointers through PEER memory: the union sorts (id, position) pairs,
+// which hands every output row its source rows directly (the first version binary-searched every
+// source's id list per row -- 17 dependent peer loads at ~2 us each made that kernel 20x slower
+// than its traffic). Row counts stay on the device: grids cover the upper bound and surplus warps
+// exit, so a push with a fused optimizer never blocks the host.
 #include <cub/cub.cuh>
 
 #include "common.h"
@@ -25,11 +29,29 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
-__device__ __forceinline__ int64_t lower_bound_i64(const int64_t* a, int64_t n, int64_t key) {
-  int64_t lo = 0, hi = n;
+// lower bound by the whole warp: 32 probes per round (log33 n rounds instead of log2 n)
+__device__ __forceinline__ int64_t warp_lower_bound(const int64_t* a, int64_t n, int64_t key, int lane) {
+  int64_t lo = 0, hi = n;  // the answer lies in [lo, hi]
   while (lo < hi) {
-    const int64_t mid = lo + ((hi - lo) >> 1);
-    if (a[mid] < key) lo = mid + 1; else hi = mid;
+    const int64_t len = hi - lo;
+    const int64_t step = (len + 32) / 33;
+    const int64_t p = lo + (lane + 1) * step - 1;
+    const bool lt = p < hi ? (a[p] < key) : false;
+    const int c = __popc(__ballot_sync(0xffffffffu, lt));  // probes are sorted: a prefix is true
+    const int64_t nlo = lo + c * step;
+    const int64_t nhi = c == 32 ? hi : min(hi, lo + (c + 1) * step - 1);
+    lo = nlo;
+    hi = nhi;
+  }
+  return lo;
+}
+
+// index of the segment that contains i: largest s with start[s] <= i (start ascending, small)
+__device__ __forceinline__ int find_segment(const int64_t* start, int nseg, int64_t i) {
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (start[mid] <= i) lo = mid; else hi = mid - 1;
   }
   return lo;
 }
@@ -38,7 +60,8 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t* a, int64_t n, 
 template <int OPT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_update_kernel(RspUpdateLaunch p) {
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (row >= p.nrows) return;
+  const int64_t nrows = p.d_nrows ? *p.d_nrows : p.nrows;
+  if (row >= nrows) return;
   const int lane = threadIdx.x & 31;
   Hyper h{p.lr, p.wd, p.momentum, p.rescale, p.clip, p.beta1, p.beta2, p.eps};
   const int64_t wrow = p.gidx[row];
@@ -82,99 +105,228 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_update_kernel(RspUpda
   }
 }
 
-// out_val[r] = 0.0f; for s in list order: if s holds out_idx[r]: out_val[r] += src_val[s][row]
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(RspSumLaunch p) {
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (r >= p.nnr) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t id = p.out_idx[r];
-  float* out = p.out_val + r * p.row_len;
-  const bool vec = (p.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out_val) & 15) == 0);
-  // positions of this row in every source (-1: absent); nsrc <= kMaxSrc
-  int64_t pos[kMaxSrc];
-  for (int s = 0; s < p.nsrc; ++s) {
-    const int64_t n = p.src_nrows[s];
-    const int64_t* idx = p.src_idx[s];
-    const int64_t lb = lower_bound_i64(idx, n, id);
-    pos[s] = (lb < n && idx[lb] == id) ? lb : -1;
+// ---------------------------------------------------------------------------------------------
+// push: union + ordered sum
+
+__global__ void rsp_tag_kernel(RspSources s, int64_t* keys, uint32_t* vals) {
+  const int64_t total = s.start[s.nsrc];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = find_segment(s.start, s.nsrc, i);
+    keys[i] = s.idx[k][i - s.start[k]];
+    vals[i] = static_cast<uint32_t>(i);
   }
+}
+
+struct HeadPred {
+  const int64_t* keys;
+  __device__ __forceinline__ bool operator()(const uint32_t& i) const {
+    return i == 0 || keys[i] != keys[i - 1];
+  }
+};
+
+struct MergeSum {
+  RspSources s;
+  const int64_t* keys;   // sorted ids
+  const uint32_t* vals;  // concatenation positions, source order inside equal ids
+  const uint32_t* seg;   // segment starts
+  const int64_t* d_nnr;
+  int64_t* out_idx; float* out_val;
+  int64_t row_len;
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t nnr = *p.d_nnr;
+  if (r >= nnr) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = p.s.start[p.s.nsrc];
+  const uint32_t b = p.seg[r];
+  const uint32_t e = r + 1 < nnr ? p.seg[r + 1] : static_cast<uint32_t>(total);
+  if (lane == 0) p.out_idx[r] = p.keys[b];
+  // this row's sources, in source order; a row_sparse array holds an id at most once, so there
+  // are at most nsrc <= kMaxSrc of them (anything beyond is a malformed input and is ignored)
+  const int cnt = min(static_cast<int>(e - b), kMaxSrc);
+  const float* rows[kMaxSrc];
+#pragma unroll
+  for (int j = 0; j < kMaxSrc; ++j) {
+    if (j < cnt) {
+      const int64_t pos = p.vals[b + j];
+      const int k = find_segment(p.s.start, p.s.nsrc, pos);
+      rows[j] = p.s.val[k] + (pos - p.s.start[k]) * p.row_len;
+    } else {
+      rows[j] = nullptr;
+    }
+  }
+  float* out = p.out_val + r * p.row_len;
+  bool vec = (p.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out_val) & 15) == 0);
+  for (int k = 0; k < p.s.nsrc; ++k) vec = vec && ((reinterpret_cast<uintptr_t>(p.s.val[k]) & 15) == 0);
   if (vec) {
     const int64_t nv = p.row_len / 4;
     for (int64_t v = lane; v < nv; v += 32) {
+      float4 x[kMaxSrc];
+#pragma unroll
+      for (int j = 0; j < kMaxSrc; ++j) {
+        if (j < cnt) x[j] = __ldcs(reinterpret_cast<const float4*>(rows[j]) + v);
+      }
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < p.nsrc; ++s) {
-        if (pos[s] < 0) continue;
-        const float* sv = p.src_val[s] + pos[s] * p.row_len;
-        if ((reinterpret_cast<uintptr_t>(sv) & 15) == 0) {
-          const float4 x = __ldcs(reinterpret_cast<const float4*>(sv) + v);
-          acc.x = __fadd_rn(acc.x, x.x); acc.y = __fadd_rn(acc.y, x.y);
-          acc.z = __fadd_rn(acc.z, x.z); acc.w = __fadd_rn(acc.w, x.w);
-        } else {
-          acc.x = __fadd_rn(acc.x, sv[4 * v]); acc.y = __fadd_rn(acc.y, sv[4 * v + 1]);
-          acc.z = __fadd_rn(acc.z, sv[4 * v + 2]); acc.w = __fadd_rn(acc.w, sv[4 * v + 3]);
+#pragma unroll
+      for (int j = 0; j < kMaxSrc; ++j) {
+        if (j < cnt) {
+          acc.x = __fadd_rn(acc.x, x[j].x); acc.y = __fadd_rn(acc.y, x[j].y);
+          acc.z = __fadd_rn(acc.z, x[j].z); acc.w = __fadd_rn(acc.w, x[j].w);
         }
       }
       reinterpret_cast<float4*>(out)[v] = acc;
     }
   } else {
-    for (int64_t j = lane; j < p.row_len; j += 32) {
+    for (int64_t c = lane; c < p.row_len; c += 32) {
       float acc = 0.f;
-      for (int s = 0; s < p.nsrc; ++s) {
-        if (pos[s] >= 0) acc = __fadd_rn(acc, p.src_val[s][pos[s] * p.row_len + j]);
-      }
-      out[j] = acc;
+      for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, rows[j][c]);
+      out[c] = acc;
     }
   }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) retain_kernel(RetainLaunch p) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (i >= p.nids) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t id = p.ids[i];
-  if (lane == 0) p.out_idx[i] = id;
-  int64_t j = -1;
-  if (p.src_dense_rows) {
-    j = id;
-  } else if (p.src_nnr > 0) {
-    const int64_t lb = lower_bound_i64(p.src_idx, p.src_nnr, id);
-    if (lb < p.src_nnr && p.src_idx[lb] == id) j = lb;
+struct MergeLayout {
+  size_t keys, keys_sorted, vals, vals_sorted, seg, temp, temp_bytes, total;
+};
+
+MergeLayout LayoutMerge(int64_t n) {
+  auto up = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  MergeLayout l;
+  const size_t k = up(static_cast<size_t>(n) * sizeof(int64_t));
+  const size_t v = up(static_cast<size_t>(n) * sizeof(uint32_t));
+  size_t t1 = 0, t2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, static_cast<const int64_t*>(nullptr),
+                                  static_cast<int64_t*>(nullptr), static_cast<const uint32_t*>(nullptr),
+                                  static_cast<uint32_t*>(nullptr), static_cast<int>(n));
+  cub::DeviceSelect::If(nullptr, t2, cub::CountingInputIterator<uint32_t>(0),
+                        static_cast<uint32_t*>(nullptr), static_cast<int64_t*>(nullptr),
+                        static_cast<int>(n), HeadPred{nullptr});
+  l.keys = 0;
+  l.keys_sorted = k;
+  l.vals = 2 * k;
+  l.vals_sorted = 2 * k + v;
+  l.seg = 2 * k + 2 * v;
+  l.temp = 2 * k + 3 * v;
+  l.temp_bytes = up(std::max(t1, t2));
+  l.total = l.temp + l.temp_bytes + 256;
+  return l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pull: batched unique + retain
+
+__device__ __forceinline__ int64_t load_id(const void* ids, int dtype, int64_t i) {
+  switch (dtype) {
+    case kInt64: return static_cast<const int64_t*>(ids)[i];
+    case kInt32: return static_cast<const int32_t*>(ids)[i];
+    case kFloat32: return static_cast<int64_t>(static_cast<const float*>(ids)[i]);
+    case kFloat64: return static_cast<int64_t>(static_cast<const double*>(ids)[i]);
+    case kUint8: return static_cast<const uint8_t*>(ids)[i];
+    case kInt8: return static_cast<const int8_t*>(ids)[i];
+    case kFloat16: return static_cast<int64_t>(__half2float(static_cast<const __half*>(ids)[i]));
+    default: return 0;
   }
-  float* out = p.out_val + i * p.row_len;
-  const float* src = j >= 0 ? p.src_val + j * p.row_len : nullptr;
-  const bool vec = (p.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out_val) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(p.src_val) & 15) == 0);
+}
+
+__device__ __forceinline__ int find_item(const RetainItem* items, int nitems, int64_t i) {
+  int lo = 0, hi = nitems - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].start <= i) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void retain_gather_kernel(const RetainItem* items, int nitems, int64_t total, int id_bits,
+                                     int64_t* comp) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = find_item(items, nitems, i);
+    const int64_t id = load_id(items[k].ids, items[k].ids_dtype, i - items[k].start);
+    comp[i] = (static_cast<int64_t>(k) << id_bits) | id;
+  }
+}
+
+__global__ void retain_bounds_kernel(const int64_t* uniq, const int64_t* d_count, int nitems,
+                                     int id_bits, int64_t* off) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nitems) return;
+  const int64_t n = *d_count;
+  if (k == nitems) { off[k] = n; return; }
+  const int64_t key = static_cast<int64_t>(k) << id_bits;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (uniq[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  off[k] = lo;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+retain_kernel(const RetainItem* items, int nitems, int64_t total, int id_bits, const int64_t* uniq,
+              const int64_t* off) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int k = find_item(items, nitems, i);
+  const RetainItem it = items[k];
+  const int64_t j = i - it.start;          // j-th unique id of item k
+  if (j >= off[k + 1] - off[k]) return;
+  const int64_t id = uniq[off[k] + j] & ((int64_t{1} << id_bits) - 1);
+  if (lane == 0) it.out_idx[j] = id;
+  int64_t srow = -1;
+  if (it.src_dense_rows) {
+    srow = id;
+  } else if (it.src_nnr > 0) {
+    const int64_t lb = warp_lower_bound(it.src_idx, it.src_nnr, id, lane);
+    if (lb < it.src_nnr && it.src_idx[lb] == id) srow = lb;
+  }
+  float* out = it.out_val + j * it.row_len;
+  const float* src = srow >= 0 ? it.src_val + srow * it.row_len : nullptr;
+  const bool vec = (it.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(it.out_val) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(it.src_val) & 15) == 0);
   if (vec) {
-    const int64_t nv = p.row_len / 4;
+    const int64_t nv = it.row_len / 4;
     for (int64_t v = lane; v < nv; v += 32) {
       const float4 x = src ? __ldcs(reinterpret_cast<const float4*>(src) + v)
                            : make_float4(0.f, 0.f, 0.f, 0.f);
       __stcs(reinterpret_cast<float4*>(out) + v, x);
     }
   } else {
-    for (int64_t c = lane; c < p.row_len; c += 32) out[c] = src ? src[c] : 0.f;
+    for (int64_t c = lane; c < it.row_len; c += 32) out[c] = src ? src[c] : 0.f;
   }
 }
 
-struct UnionLayout {
-  size_t off_concat, off_sorted, off_temp, temp_bytes, total;
+struct RetainLayout {
+  size_t items, comp, sorted, uniq, count, temp, temp_bytes, total;
 };
 
-UnionLayout Layout(int64_t n) {
-  UnionLayout l;
-  const size_t ids = (static_cast<size_t>(n) * sizeof(int64_t) + 255) & ~static_cast<size_t>(255);
+RetainLayout LayoutRetain(int nitems, int64_t n) {
+  auto up = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  RetainLayout l;
+  const size_t k = up(static_cast<size_t>(n) * sizeof(int64_t));
   size_t t1 = 0, t2 = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, t1, static_cast<const int64_t*>(nullptr),
                                  static_cast<int64_t*>(nullptr), static_cast<int>(n));
   cub::DeviceSelect::Unique(nullptr, t2, static_cast<const int64_t*>(nullptr),
                             static_cast<int64_t*>(nullptr), static_cast<int64_t*>(nullptr),
                             static_cast<int>(n));
-  l.off_concat = 0;
-  l.off_sorted = ids;
-  l.off_temp = 2 * ids;
-  l.temp_bytes = (std::max(t1, t2) + 255) & ~static_cast<size_t>(255);
-  l.total = l.off_temp + l.temp_bytes + 256;
+  l.items = 0;
+  l.comp = up(static_cast<size_t>(nitems) * sizeof(RetainItem));
+  l.sorted = l.comp + k;
+  l.uniq = l.sorted + k;
+  l.count = l.uniq + k;
+  l.temp = l.count + 256;
+  l.temp_bytes = up(std::max(t1, t2));
+  l.total = l.temp + l.temp_bytes + 256;
   return l;
+}
+
+int GridFor(int64_t n, int threads) {
+  return static_cast<int>(std::min<int64_t>((n + threads - 1) / threads, 148 * 8));
 }
 
 }  // namespace
@@ -191,58 +343,77 @@ void LaunchRspUpdate(const RspUpdateLaunch& p, cudaStream_t stream) {
   KV_CUDA(cudaGetLastError());
 }
 
-size_t RspUnionWorkspaceBytes(int64_t total_ids) { return Layout(std::max<int64_t>(total_ids, 1)).total; }
-size_t UniqueWorkspaceBytes(int64_t n) { return Layout(std::max<int64_t>(n, 1)).total; }
+size_t RspMergeWorkspaceBytes(int64_t total_ids) { return LayoutMerge(std::max<int64_t>(total_ids, 1)).total; }
 
-void LaunchUnique(const int64_t* ids, int64_t n, int64_t* out, int64_t* d_count, void* workspace,
-                  size_t workspace_bytes, cudaStream_t stream) {
-  if (n <= 0) {
-    KV_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), stream));
-    return;
-  }
-  KV_CHECK(n < (1LL << 31)) << "too many row ids";
-  UnionLayout l = Layout(n);
-  KV_CHECK(workspace_bytes >= l.total) << "unique: workspace too small";
+void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_t* out_idx,
+                    float* out_val, int64_t* d_nnr, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream) {
+  const int64_t total = srcs.start[srcs.nsrc];
+  KV_CHECK(srcs.nsrc >= 1 && srcs.nsrc <= kMaxSrc);
+  KV_CHECK(total > 0 && total < (1LL << 31)) << "row_sparse push: " << total << " row ids";
+  KV_CHECK(id_bits >= 1 && id_bits <= 63);
+  const MergeLayout l = LayoutMerge(total);
+  KV_CHECK(workspace_bytes >= l.total) << "rsp merge: workspace too small";
   char* ws = static_cast<char*>(workspace);
-  int64_t* sorted = reinterpret_cast<int64_t*>(ws + l.off_sorted);
+  int64_t* keys = reinterpret_cast<int64_t*>(ws + l.keys);
+  int64_t* keys_sorted = reinterpret_cast<int64_t*>(ws + l.keys_sorted);
+  uint32_t* vals = reinterpret_cast<uint32_t*>(ws + l.vals);
+  uint32_t* vals_sorted = reinterpret_cast<uint32_t*>(ws + l.vals_sorted);
+  uint32_t* seg = reinterpret_cast<uint32_t*>(ws + l.seg);
+  rsp_tag_kernel<<<GridFor(total, 256), 256, 0, stream>>>(srcs, keys, vals);
+  KV_CUDA(cudaGetLastError());
   size_t tb = l.temp_bytes;
-  KV_CUDA(cub::DeviceRadixSort::SortKeys(ws + l.off_temp, tb, ids, sorted, static_cast<int>(n), 0,
-                                         64, stream));
+  KV_CUDA(cub::DeviceRadixSort::SortPairs(ws + l.temp, tb, keys, keys_sorted, vals, vals_sorted,
+                                          static_cast<int>(total), 0, id_bits, stream));
   tb = l.temp_bytes;
-  KV_CUDA(cub::DeviceSelect::Unique(ws + l.off_temp, tb, sorted, out, d_count, static_cast<int>(n),
-                                    stream));
-}
-
-void LaunchRspUnion(const int64_t* const* src_idx, const int64_t* src_nrows, int nsrc,
-                    int64_t total_ids, int64_t* out_idx, int64_t* d_nnr, void* workspace,
-                    size_t workspace_bytes, cudaStream_t stream) {
-  // src_idx / src_nrows are HOST arrays of device pointers / counts here (gather by memcpy)
-  UnionLayout l = Layout(std::max<int64_t>(total_ids, 1));
-  KV_CHECK(workspace_bytes >= l.total) << "rsp union: workspace too small";
-  char* ws = static_cast<char*>(workspace);
-  int64_t* concat = reinterpret_cast<int64_t*>(ws + l.off_concat);
-  int64_t off = 0;
-  for (int s = 0; s < nsrc; ++s) {
-    if (src_nrows[s] == 0) continue;
-    KV_CUDA(cudaMemcpyAsync(concat + off, src_idx[s], src_nrows[s] * sizeof(int64_t),
-                            cudaMemcpyDefault, stream));
-    off += src_nrows[s];
-  }
-  LaunchUnique(concat, total_ids, out_idx, d_nnr, workspace, workspace_bytes, stream);
-}
-
-void LaunchRspSum(const RspSumLaunch& p, cudaStream_t stream) {
-  if (p.nnr <= 0 || p.row_len <= 0) return;
-  KV_CHECK(p.nsrc <= kMaxSrc);
-  const int blocks = static_cast<int>((p.nnr + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  rsp_sum_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p);
+  KV_CUDA(cub::DeviceSelect::If(ws + l.temp, tb, cub::CountingInputIterator<uint32_t>(0), seg, d_nnr,
+                                static_cast<int>(total), HeadPred{keys_sorted}, stream));
+  if (row_len <= 0) return;
+  MergeSum m{srcs, keys_sorted, vals_sorted, seg, d_nnr, out_idx, out_val, row_len};
+  const int blocks = static_cast<int>((total + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  rsp_sum_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(m);
   KV_CUDA(cudaGetLastError());
 }
 
-void LaunchRetain(const RetainLaunch& p, cudaStream_t stream) {
-  if (p.nids <= 0) return;
-  const int blocks = static_cast<int>((p.nids + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  retain_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(p);
+size_t RetainBatchWorkspaceBytes(int nitems, int64_t total_ids) {
+  return LayoutRetain(std::max(nitems, 1), std::max<int64_t>(total_ids, 1)).total;
+}
+
+void LaunchUniqueBatch(const RetainItem* h_items, int nitems, int64_t total, int id_bits,
+                       int64_t* d_off, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  KV_CHECK(nitems >= 1 && total > 0 && total < (1LL << 31));
+  int item_bits = 0;
+  while ((1 << item_bits) < nitems) ++item_bits;
+  KV_CHECK(id_bits >= 1 && id_bits + item_bits <= 62) << "row_sparse_pull: id space too large";
+  const RetainLayout l = LayoutRetain(nitems, total);
+  KV_CHECK(workspace_bytes >= l.total) << "retain batch: workspace too small";
+  char* ws = static_cast<char*>(workspace);
+  RetainItem* items = reinterpret_cast<RetainItem*>(ws + l.items);
+  int64_t* comp = reinterpret_cast<int64_t*>(ws + l.comp);
+  int64_t* sorted = reinterpret_cast<int64_t*>(ws + l.sorted);
+  int64_t* uniq = reinterpret_cast<int64_t*>(ws + l.uniq);
+  int64_t* count = reinterpret_cast<int64_t*>(ws + l.count);
+  KV_CUDA(cudaMemcpyAsync(items, h_items, nitems * sizeof(RetainItem), cudaMemcpyHostToDevice, stream));
+  retain_gather_kernel<<<GridFor(total, 256), 256, 0, stream>>>(items, nitems, total, id_bits, comp);
+  KV_CUDA(cudaGetLastError());
+  size_t tb = l.temp_bytes;
+  KV_CUDA(cub::DeviceRadixSort::SortKeys(ws + l.temp, tb, comp, sorted, static_cast<int>(total), 0,
+                                         id_bits + item_bits, stream));
+  tb = l.temp_bytes;
+  KV_CUDA(cub::DeviceSelect::Unique(ws + l.temp, tb, sorted, uniq, count, static_cast<int>(total),
+                                    stream));
+  retain_bounds_kernel<<<(nitems + 1 + 127) / 128, 128, 0, stream>>>(uniq, count, nitems, id_bits, d_off);
+  KV_CUDA(cudaGetLastError());
+}
+
+void LaunchRetainBatch(int nitems, int64_t total, int id_bits, const int64_t* d_off, void* workspace,
+                       cudaStream_t stream) {
+  const RetainLayout l = LayoutRetain(nitems, total);
+  char* ws = static_cast<char*>(workspace);
+  const RetainItem* items = reinterpret_cast<const RetainItem*>(ws + l.items);
+  const int64_t* uniq = reinterpret_cast<const int64_t*>(ws + l.uniq);
+  const int blocks = static_cast<int>((total + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  retain_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(items, nitems, total, id_bits, uniq, d_off);
   KV_CUDA(cudaGetLastError());
 }
 

@@ -42,9 +42,18 @@ def make_allgather_callback(group=None):
     return _ALLGATHER_PROTO(_cb)
 
 
+def nvls_wanted(world):
+    """B200KV_NVLS = 1 / 0 forces the in-switch reduce on / off; unset or 'auto' uses it from 8
+    ranks up (same rule as csrc/dense_group.cc)."""
+    z = os.environ.get('B200KV_NVLS', 'auto')
+    if z in ('', 'auto'):
+        return world >= 8
+    return z != '0'
+
+
 def init_peer_group(device_id=None, symmetric_memory=None):
     """Create the peer group for the calling torch.distributed job (idempotent).
-    symmetric_memory=True (default when B200KV_NVLS=1): take the arena from torch symmetric memory
+    symmetric_memory=True (default when nvls_wanted()): take the arena from torch symmetric memory
     so that an NVSwitch multicast mapping is available to the kernels."""
     import torch.distributed as dist
     if _state.get('inited'):
@@ -59,7 +68,7 @@ def init_peer_group(device_id=None, symmetric_memory=None):
     _state.update(cb=cb, group=cpu_group, inited=True, rank=rank, world=world, device=device_id,
                   multicast=False)
     if symmetric_memory is None:
-        symmetric_memory = os.environ.get('B200KV_NVLS', '0') not in ('', '0')
+        symmetric_memory = nvls_wanted(world)
     if symmetric_memory and _init_with_symmetric_memory(rank, world, device_id, cb):
         return
     check_call(_LIB.B200KVGroupInit(ctypes.c_int(rank), ctypes.c_int(world), ctypes.c_int(device_id),

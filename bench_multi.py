@@ -131,8 +131,10 @@ def run_multi_gpu(args):
                                       "fused reduce-scatter+update+all-gather kernel over IPC peer memory",
                        "value_formula": "n_gpus * size * 2(n-1)/n / time (tools/bandwidth/measure.py:137)",
                        "l2": "per-GPU working set > 126 MB L2, no flush needed",
-                       "nvls_in_switch_reduce": bool(os.environ.get("B200KV_NVLS", "0") not in ("", "0")
-                                                     and mx.dist.has_multicast()),
+                       "nvls_in_switch_reduce": bool(mx.dist.nvls_wanted(world) and mx.dist.has_multicast()),
+                       "parity_mode": ("1e-6 relative (in-switch summation order)"
+                                       if mx.dist.nvls_wanted(world) and mx.dist.has_multicast()
+                                       else "bit-exact vs the reference CPU store"),
                        "optimizer": SGD_KW if WORKLOADS[args.workload]["opt"] == "sgd" else ADAM_KW},
             "roofline": {"bound": "nvlink", "achieved": busbw, "peak": 900.0, "unit": "GB/s",
                          "frac": busbw / 900.0, "frac_of_measured_770": busbw / 770.0,

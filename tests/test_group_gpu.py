@@ -33,8 +33,7 @@ def _worker(rank, world, port, q, nvls=False):
     os.environ["MASTER_PORT"] = str(port)
     os.environ["LOCAL_RANK"] = str(rank)
     os.environ["B200KV_IPC_ARENA_MB"] = "512"
-    if nvls:
-        os.environ["B200KV_NVLS"] = "1"
+    os.environ["B200KV_NVLS"] = "1" if nvls else "0"
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     errors = []
