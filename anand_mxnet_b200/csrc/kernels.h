@@ -105,7 +105,8 @@ void LaunchRspUpdate(const RspUpdateLaunch& p, cudaStream_t stream);
 //   sum      one warp per segment: out_idx[r] = id, out_val[r] = 0.0f + rows in SOURCE ORDER
 //            (the stable sort keeps equal ids in concatenation = source order)
 // No binary searches, no host read of the count: the sum grid covers `total` rows and warps
-// beyond *d_nnr exit.
+// beyond *d_nnr exit. With `fused_update` the summed row is never written: the same warp applies
+// the lazy optimizer step to row `id` of w / state (out_idx, out_val unused).
 struct RspSources {
   const int64_t* idx[kMaxSrc];
   const float* val[kMaxSrc];
@@ -115,7 +116,7 @@ struct RspSources {
 size_t RspMergeWorkspaceBytes(int64_t total_ids);
 void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_t* out_idx,
                     float* out_val, int64_t* d_nnr, void* workspace, size_t workspace_bytes,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const RspUpdateLaunch* fused_update = nullptr);
 
 // row_sparse_pull for a batch of (row_ids, out) pairs that share an owner GPU
 // (kvstore_local.h:263-283 + kvstore_utils.cu:43-97 Unique + sparse_retain-inl.h:121-150,262-323):

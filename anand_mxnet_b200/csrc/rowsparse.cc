@@ -109,33 +109,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
   NDArray merged = NDArray::RowSparse(e.shape, Context::GPU(home), e.dtype);
   const int64_t row_len = static_cast<int64_t>(e.rsp.RowLength());
   const bool fused = opt_.enabled && (opt_.kind == kOptSGD || opt_.kind == kOptAdam);
-  NDArray d_nnr({1}, Context::GPU(home), kInt64);  // lives until the kernels that read it retire
-  if (total > 0) {
-    merged.CheckAndAllocRows(total);   // upper bound; nnr is set below when the host needs it
-    for (auto& s : srcs) eng->BeginRead(s.dev(), *s.var());
-    if (parts.size() > 1) eng->JoinStreams(parts);
-    DeviceGuard g(home);
-    cudaStream_t st = eng->Stream(home);
-    Scratch ws(home, RspMergeWorkspaceBytes(total));
-    LaunchRspMerge(S, BitsFor(e.shape[0]), row_len, merged.row_ids(), static_cast<float*>(merged.data()),
-                   static_cast<int64_t*>(d_nnr.data()), ws.p, ws.bytes, st);
-    eng->CountLaunch("rsp_merge(tag, sort, heads)", total * 24);
-    eng->CountLaunch("rsp_sum", static_cast<uint64_t>(total) * row_len * 4 * 2);
-    if (parts.size() > 1) eng->JoinStreams(parts);
-    uint64_t seq = eng->Issue(home);
-    eng->MarkWrite(home, seq, merged.var());
-    eng->MarkWrite(home, seq, d_nnr.var());
-    for (auto& s : srcs) {
-      uint64_t sq = s.dev() == home ? seq : eng->Issue(s.dev());
-      eng->MarkRead(s.dev(), sq, s.var());
-    }
-    if (!fused) {
-      CountFence f(home, 1);
-      f.Post(static_cast<const int64_t*>(d_nnr.data()), st);
-      merged.SetNnr(f.Wait()[0]);
-    }
-  }
-  // ---- consume the merged gradient
+  RspUpdateLaunch U;
   if (fused) {
     KV_CHECK(opt_.lazy_update) << "lazy_update=False for row_sparse gradients is a next-row item";
     KV_CHECK_EQ(e.rsp.nnr(), e.shape[0])
@@ -151,7 +125,6 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     auto wm = opt_.wd_mult.find(e.key);
     double lrd = opt_.lr * (lm == opt_.lr_mult.end() ? 1.0 : lm->second);
     double wdd = opt_.wd * (wm == opt_.wd_mult.end() ? 1.0 : wm->second);
-    RspUpdateLaunch U;
     DevState& s = e.dev[home];
     const std::vector<int64_t> dshape = e.shape;
     auto zero_state = [&](NDArray* a) {
@@ -182,21 +155,48 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     U.w = static_cast<float*>(e.rsp.data());
     U.s1 = s.s1.is_none() ? nullptr : static_cast<float*>(s.s1.data());
     U.s2 = s.s2.is_none() ? nullptr : static_cast<float*>(s.s2.data());
-    U.gidx = merged.row_ids();
-    U.gval = static_cast<const float*>(merged.data());
-    U.nrows = total;  // upper bound of the grid; the kernel reads the union's size on the device
-    U.d_nrows = static_cast<const int64_t*>(d_nnr.data());
     U.row_len = row_len;
-    DeviceGuard g(home);
-    eng->BeginWrite(home, *e.rsp.var());
-    LaunchRspUpdate(U, eng->Stream(home));
-    eng->CountLaunch("rsp_update", static_cast<uint64_t>(total) * row_len * 4 * 3);
-    uint64_t seq = eng->Issue(home);
-    eng->MarkWrite(home, seq, e.rsp.var());
-    eng->MarkRead(home, seq, merged.var());
-    eng->MarkRead(home, seq, d_nnr.var());
-    return;
   }
+  if (total > 0) {
+    NDArray d_nnr({1}, Context::GPU(home), kInt64);
+    // fused: the summed rows are consumed in registers by the optimizer step, nothing is stored
+    if (!fused) merged.CheckAndAllocRows(total);  // upper bound; nnr is set once the count is known
+    for (auto& s : srcs) eng->BeginRead(s.dev(), *s.var());
+    if (fused) {
+      eng->BeginWrite(home, *e.rsp.var());
+      DevState& ds = e.dev[home];
+      if (!ds.s1.is_none()) eng->BeginWrite(home, *ds.s1.var());
+      if (!ds.s2.is_none()) eng->BeginWrite(home, *ds.s2.var());
+    }
+    if (parts.size() > 1) eng->JoinStreams(parts);
+    DeviceGuard g(home);
+    cudaStream_t st = eng->Stream(home);
+    Scratch ws(home, RspMergeWorkspaceBytes(total));
+    LaunchRspMerge(S, BitsFor(e.shape[0]), row_len, fused ? nullptr : merged.row_ids(),
+                   fused ? nullptr : static_cast<float*>(merged.data()),
+                   static_cast<int64_t*>(d_nnr.data()), ws.p, ws.bytes, st, fused ? &U : nullptr);
+    eng->CountLaunch("rsp_merge(tag, sort, heads)", total * 24);
+    eng->CountLaunch(fused ? "rsp_sum+update" : "rsp_sum", static_cast<uint64_t>(total) * row_len * 4 * 2);
+    if (parts.size() > 1) eng->JoinStreams(parts);
+    uint64_t seq = eng->Issue(home);
+    eng->MarkWrite(home, seq, fused ? e.rsp.var() : merged.var());
+    eng->MarkWrite(home, seq, d_nnr.var());
+    if (fused) {
+      DevState& ds = e.dev[home];
+      if (!ds.s1.is_none()) eng->MarkWrite(home, seq, ds.s1.var());
+      if (!ds.s2.is_none()) eng->MarkWrite(home, seq, ds.s2.var());
+    }
+    for (auto& s : srcs) {
+      uint64_t sq = s.dev() == home ? seq : eng->Issue(s.dev());
+      eng->MarkRead(s.dev(), sq, s.var());
+    }
+    if (!fused) {
+      CountFence f(home, 1);
+      f.Post(static_cast<const int64_t*>(d_nnr.data()), st);
+      merged.SetNnr(f.Wait()[0]);
+    }
+  }
+  if (fused) return;
   if (updater_ != nullptr && !opt_.enabled) {
     NDArray* recv_h = new NDArray(merged);
     NDArray* local_h = new NDArray(e.rsp);

@@ -131,10 +131,14 @@ struct MergeSum {
   const uint32_t* vals;  // concatenation positions, source order inside equal ids
   const uint32_t* seg;   // segment starts
   const int64_t* d_nnr;
-  int64_t* out_idx; float* out_val;
+  int64_t* out_idx; float* out_val;  // the merged gradient (OPT < 0)
   int64_t row_len;
+  RspUpdateLaunch u;                 // OPT >= 0: the lazy optimizer step consumes the sum in registers
 };
 
+// OPT < 0: write the merged row_sparse gradient. OPT = kOptSGDSingle / kOptSGD / kOptAdam: the row
+// sum never touches memory -- the same warp applies the lazy update to row `id` of w (+ state).
+template <int OPT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t nnr = *p.d_nnr;
@@ -143,7 +147,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
   const int64_t total = p.s.start[p.s.nsrc];
   const uint32_t b = p.seg[r];
   const uint32_t e = r + 1 < nnr ? p.seg[r + 1] : static_cast<uint32_t>(total);
-  if (lane == 0) p.out_idx[r] = p.keys[b];
+  const int64_t id = p.keys[b];
+  if (OPT < 0 && lane == 0) p.out_idx[r] = id;
   // this row's sources, in source order; a row_sparse array holds an id at most once, so there
   // are at most nsrc <= kMaxSrc of them (anything beyond is a malformed input and is ignored)
   const int cnt = min(static_cast<int>(e - b), kMaxSrc);
@@ -158,8 +163,23 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
       rows[j] = nullptr;
     }
   }
-  float* out = p.out_val + r * p.row_len;
-  bool vec = (p.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out_val) & 15) == 0);
+  Hyper h{p.u.lr, p.u.wd, p.u.momentum, p.u.rescale, p.u.clip, p.u.beta1, p.u.beta2, p.u.eps};
+  float* out = OPT < 0 ? p.out_val + r * p.row_len : nullptr;
+  float* w = OPT < 0 ? nullptr : p.u.w + id * p.row_len;
+  float* s1 = (OPT == kOptSGD || OPT == kOptAdam) ? p.u.s1 + id * p.row_len : nullptr;
+  float* s2 = OPT == kOptAdam ? p.u.s2 + id * p.row_len : nullptr;
+  auto one = [&](float wv, float gv, float& a, float& c) -> float {
+    if (OPT == kOptAdam) return step_adam_lazy(wv, gv, a, c, h);
+    return step<(OPT < 0 ? kOptSGDSingle : OPT)>(wv, gv, a, c, OPT == kOptSGD, h);
+  };
+  bool vec = (p.row_len % 4 == 0);
+  if (OPT < 0) {
+    vec = vec && ((reinterpret_cast<uintptr_t>(p.out_val) & 15) == 0);
+  } else {
+    vec = vec && ((reinterpret_cast<uintptr_t>(p.u.w) & 15) == 0) &&
+          (!p.u.s1 || (reinterpret_cast<uintptr_t>(p.u.s1) & 15) == 0) &&
+          (!p.u.s2 || (reinterpret_cast<uintptr_t>(p.u.s2) & 15) == 0);
+  }
   for (int k = 0; k < p.s.nsrc; ++k) vec = vec && ((reinterpret_cast<uintptr_t>(p.s.val[k]) & 15) == 0);
   if (vec) {
     const int64_t nv = p.row_len / 4;
@@ -169,6 +189,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
       for (int j = 0; j < kMaxSrc; ++j) {
         if (j < cnt) x[j] = __ldcs(reinterpret_cast<const float4*>(rows[j]) + v);
       }
+      float4 wv = make_float4(0, 0, 0, 0), a = wv, c = wv;
+      if (OPT >= 0) wv = reinterpret_cast<float4*>(w)[v];
+      if (OPT == kOptSGD || OPT == kOptAdam) a = reinterpret_cast<float4*>(s1)[v];
+      if (OPT == kOptAdam) c = reinterpret_cast<float4*>(s2)[v];
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < kMaxSrc; ++j) {
@@ -177,13 +201,32 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
           acc.z = __fadd_rn(acc.z, x[j].z); acc.w = __fadd_rn(acc.w, x[j].w);
         }
       }
-      reinterpret_cast<float4*>(out)[v] = acc;
+      if (OPT < 0) {
+        reinterpret_cast<float4*>(out)[v] = acc;
+      } else {
+        wv.x = one(wv.x, acc.x, a.x, c.x);
+        wv.y = one(wv.y, acc.y, a.y, c.y);
+        wv.z = one(wv.z, acc.z, a.z, c.z);
+        wv.w = one(wv.w, acc.w, a.w, c.w);
+        reinterpret_cast<float4*>(w)[v] = wv;
+        if (OPT == kOptSGD || OPT == kOptAdam) reinterpret_cast<float4*>(s1)[v] = a;
+        if (OPT == kOptAdam) reinterpret_cast<float4*>(s2)[v] = c;
+      }
     }
   } else {
-    for (int64_t c = lane; c < p.row_len; c += 32) {
+    for (int64_t col = lane; col < p.row_len; col += 32) {
       float acc = 0.f;
-      for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, rows[j][c]);
-      out[c] = acc;
+      for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, rows[j][col]);
+      if (OPT < 0) {
+        out[col] = acc;
+      } else {
+        float a = 0.f, c = 0.f;
+        if (OPT == kOptSGD || OPT == kOptAdam) a = s1[col];
+        if (OPT == kOptAdam) c = s2[col];
+        w[col] = one(w[col], acc, a, c);
+        if (OPT == kOptSGD || OPT == kOptAdam) s1[col] = a;
+        if (OPT == kOptAdam) s2[col] = c;
+      }
     }
   }
 }
@@ -347,7 +390,7 @@ size_t RspMergeWorkspaceBytes(int64_t total_ids) { return LayoutMerge(std::max<i
 
 void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_t* out_idx,
                     float* out_val, int64_t* d_nnr, void* workspace, size_t workspace_bytes,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const RspUpdateLaunch* fused_update) {
   const int64_t total = srcs.start[srcs.nsrc];
   KV_CHECK(srcs.nsrc >= 1 && srcs.nsrc <= kMaxSrc);
   KV_CHECK(total > 0 && total < (1LL << 31)) << "row_sparse push: " << total << " row ids";
@@ -369,9 +412,20 @@ void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_
   KV_CUDA(cub::DeviceSelect::If(ws + l.temp, tb, cub::CountingInputIterator<uint32_t>(0), seg, d_nnr,
                                 static_cast<int>(total), HeadPred{keys_sorted}, stream));
   if (row_len <= 0) return;
-  MergeSum m{srcs, keys_sorted, vals_sorted, seg, d_nnr, out_idx, out_val, row_len};
+  MergeSum m{srcs, keys_sorted, vals_sorted, seg, d_nnr, out_idx, out_val, row_len, RspUpdateLaunch()};
   const int blocks = static_cast<int>((total + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  rsp_sum_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(m);
+  const int threads = kWarpsPerBlock * 32;
+  if (fused_update == nullptr) {
+    rsp_sum_kernel<-1><<<blocks, threads, 0, stream>>>(m);
+  } else {
+    m.u = *fused_update;
+    switch (m.u.opt) {
+      case kOptSGDSingle: rsp_sum_kernel<kOptSGDSingle><<<blocks, threads, 0, stream>>>(m); break;
+      case kOptSGD: rsp_sum_kernel<kOptSGD><<<blocks, threads, 0, stream>>>(m); break;
+      case kOptAdam: rsp_sum_kernel<kOptAdam><<<blocks, threads, 0, stream>>>(m); break;
+      default: KV_FATAL << "row_sparse push: unsupported optimizer kind " << m.u.opt;
+    }
+  }
   KV_CUDA(cudaGetLastError());
 }
 
