@@ -138,9 +138,15 @@ struct MergeSum {
 
 // OPT < 0: write the merged row_sparse gradient. OPT = kOptSGDSingle / kOptSGD / kOptAdam: the row
 // sum never touches memory -- the same warp applies the lazy update to row `id` of w (+ state).
+// One warp per union row. Lane j resolves the row pointer of the j-th contributing source (one
+// parallel step instead of a per-source pointer chase) and parks it in shared memory; the row is
+// then processed in tiles of 4 x 32 float4 so that every lane keeps 4 source loads (+ the weight /
+// state loads of the tile) in flight.
 template <int OPT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p) {
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  __shared__ const float* s_rows[kWarpsPerBlock][kMaxSrc];
+  const int warp = threadIdx.x >> 5;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + warp;
   const int64_t nnr = *p.d_nnr;
   if (r >= nnr) return;
   const int lane = threadIdx.x & 31;
@@ -152,17 +158,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
   // this row's sources, in source order; a row_sparse array holds an id at most once, so there
   // are at most nsrc <= kMaxSrc of them (anything beyond is a malformed input and is ignored)
   const int cnt = min(static_cast<int>(e - b), kMaxSrc);
-  const float* rows[kMaxSrc];
-#pragma unroll
-  for (int j = 0; j < kMaxSrc; ++j) {
-    if (j < cnt) {
-      const int64_t pos = p.vals[b + j];
-      const int k = find_segment(p.s.start, p.s.nsrc, pos);
-      rows[j] = p.s.val[k] + (pos - p.s.start[k]) * p.row_len;
-    } else {
-      rows[j] = nullptr;
-    }
+  if (lane < cnt) {
+    const int64_t pos = p.vals[b + lane];
+    const int k = find_segment(p.s.start, p.s.nsrc, pos);
+    s_rows[warp][lane] = p.s.val[k] + (pos - p.s.start[k]) * p.row_len;
   }
+  __syncwarp();
   Hyper h{p.u.lr, p.u.wd, p.u.momentum, p.u.rescale, p.u.clip, p.u.beta1, p.u.beta2, p.u.eps};
   float* out = OPT < 0 ? p.out_val + r * p.row_len : nullptr;
   float* w = OPT < 0 ? nullptr : p.u.w + id * p.row_len;
@@ -182,41 +183,56 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
   }
   for (int k = 0; k < p.s.nsrc; ++k) vec = vec && ((reinterpret_cast<uintptr_t>(p.s.val[k]) & 15) == 0);
   if (vec) {
+    constexpr int U = 4;
     const int64_t nv = p.row_len / 4;
-    for (int64_t v = lane; v < nv; v += 32) {
-      float4 x[kMaxSrc];
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t v0 = lane; v0 < nv; v0 += 32 * U) {
+      float4 wv[U], a[U], c[U], acc[U];
 #pragma unroll
-      for (int j = 0; j < kMaxSrc; ++j) {
-        if (j < cnt) x[j] = __ldcs(reinterpret_cast<const float4*>(rows[j]) + v);
-      }
-      float4 wv = make_float4(0, 0, 0, 0), a = wv, c = wv;
-      if (OPT >= 0) wv = reinterpret_cast<float4*>(w)[v];
-      if (OPT == kOptSGD || OPT == kOptAdam) a = reinterpret_cast<float4*>(s1)[v];
-      if (OPT == kOptAdam) c = reinterpret_cast<float4*>(s2)[v];
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < kMaxSrc; ++j) {
-        if (j < cnt) {
-          acc.x = __fadd_rn(acc.x, x[j].x); acc.y = __fadd_rn(acc.y, x[j].y);
-          acc.z = __fadd_rn(acc.z, x[j].z); acc.w = __fadd_rn(acc.w, x[j].w);
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + 32 * u;
+        acc[u] = zero; wv[u] = zero; a[u] = zero; c[u] = zero;
+        if (v < nv) {
+          if (OPT >= 0) wv[u] = reinterpret_cast<const float4*>(w)[v];
+          if (OPT == kOptSGD || OPT == kOptAdam) a[u] = reinterpret_cast<const float4*>(s1)[v];
+          if (OPT == kOptAdam) c[u] = reinterpret_cast<const float4*>(s2)[v];
         }
       }
-      if (OPT < 0) {
-        reinterpret_cast<float4*>(out)[v] = acc;
-      } else {
-        wv.x = one(wv.x, acc.x, a.x, c.x);
-        wv.y = one(wv.y, acc.y, a.y, c.y);
-        wv.z = one(wv.z, acc.z, a.z, c.z);
-        wv.w = one(wv.w, acc.w, a.w, c.w);
-        reinterpret_cast<float4*>(w)[v] = wv;
-        if (OPT == kOptSGD || OPT == kOptAdam) reinterpret_cast<float4*>(s1)[v] = a;
-        if (OPT == kOptAdam) reinterpret_cast<float4*>(s2)[v] = c;
+      for (int j = 0; j < cnt; ++j) {
+        const float4* row = reinterpret_cast<const float4*>(s_rows[warp][j]);
+        float4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t v = v0 + 32 * u;
+          x[u] = v < nv ? __ldcs(row + v) : zero;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          acc[u].x = __fadd_rn(acc[u].x, x[u].x); acc[u].y = __fadd_rn(acc[u].y, x[u].y);
+          acc[u].z = __fadd_rn(acc[u].z, x[u].z); acc[u].w = __fadd_rn(acc[u].w, x[u].w);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + 32 * u;
+        if (v >= nv) continue;
+        if (OPT < 0) {
+          reinterpret_cast<float4*>(out)[v] = acc[u];
+        } else {
+          wv[u].x = one(wv[u].x, acc[u].x, a[u].x, c[u].x);
+          wv[u].y = one(wv[u].y, acc[u].y, a[u].y, c[u].y);
+          wv[u].z = one(wv[u].z, acc[u].z, a[u].z, c[u].z);
+          wv[u].w = one(wv[u].w, acc[u].w, a[u].w, c[u].w);
+          reinterpret_cast<float4*>(w)[v] = wv[u];
+          if (OPT == kOptSGD || OPT == kOptAdam) reinterpret_cast<float4*>(s1)[v] = a[u];
+          if (OPT == kOptAdam) reinterpret_cast<float4*>(s2)[v] = c[u];
+        }
       }
     }
   } else {
     for (int64_t col = lane; col < p.row_len; col += 32) {
       float acc = 0.f;
-      for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, rows[j][col]);
+      for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, s_rows[warp][j][col]);
       if (OPT < 0) {
         out[col] = acc;
       } else {
