@@ -434,3 +434,188 @@ void kvo_dequantize_2bit(size_t n, float* out, const uint32_t* compressed, float
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* multi-tensor optimizer operators: LARS, AdamW, LAMB                          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* multi_sum_sq CPU, src/operator/contrib/multi_sum_sq.cc:64-78 (CalcSumSq): one float
+ * accumulator per array, elements in index order. kind: -1 fp32, 0 fp16, 1 bf16. For fp16 the
+ * reference multiplies in half_t (mshadow MSHADOW_HALF_OPERATOR: the product is rounded to half)
+ * and adds the rounded product in float. */
+float kvo_sum_sq(const void* x, size_t n, int kind) {
+  float sum = 0.f;
+  if (kind < 0) {
+    const float* a = (const float*)x;
+    for (size_t j = 0; j < n; ++j) sum += a[j] * a[j];
+  } else {
+    const uint16_t* a = (const uint16_t*)x;
+    for (size_t j = 0; j < n; ++j) {
+      const float v = kvo_half_to_float(a[j], kind);
+      sum += kvo_half_to_float(kvo_float_to_half(v * v, kind), kind);
+    }
+  }
+  return sum;
+}
+
+/* multi_lars, src/operator/contrib/multi_lars-inl.h:61-74 (MultiLARSKernel) */
+void kvo_multi_lars(size_t n, float* out, const float* lrs, const float* w_sum_sq,
+                    const float* g_sum_sq, const float* wds, float eta, float eps, float rescale) {
+  for (size_t i = 0; i < n; ++i) {
+    const float w_norm = sqrtf(w_sum_sq[i]);
+    const int valid = w_norm > 0. && g_sum_sq[i] > 0.;
+    out[i] = valid ? lrs[i] * eta * w_norm / (sqrtf(g_sum_sq[i]) * rescale + wds[i] * w_norm + eps)
+                   : lrs[i];
+  }
+}
+
+/* preloaded_multi_[mp_]sgd[_mom]_update: PreloadedMultiSGDKernel
+ * (src/operator/contrib/preloaded_multi_sgd-inl.h:170-203) is MultiSGDKernel with lr / wd read
+ * from arrays -- the same expression tree, so kvo_multi_sgd_update / kvo_multi_mp_sgd_update with
+ * lr = lrs[k], wd = wds[k] restate it (tests pin that against the reference FCompute). */
+
+/* _adamw_update fp32, src/operator/contrib/adamw-inl.h:176-208 (AdamWUpdate, mshadow expression
+ * templates). NOTE the reference writes the rescaled (and clipped) gradient back into `grad`. */
+void kvo_adamw_update(size_t n, float* out, float* mean, float* var, const float* w, float* g,
+                      float rescale, float clip, float beta1, float beta2, float eta, float lr,
+                      float wd, float eps) {
+  const float omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  for (size_t i = 0; i < n; ++i) {
+    float gr = rescale * g[i];
+    if (clip >= 0.0f) gr = clipf(gr, clip);
+    g[i] = gr;
+    mean[i] = beta1 * mean[i] + omb1 * gr;
+    var[i] = beta2 * var[i] + omb2 * (gr * gr);
+    out[i] = w[i] - eta * (lr * mean[i] / (sqrtf(var[i]) + eps) + wd * w[i]);
+  }
+}
+
+/* _mp_adamw_update, adamw-inl.h:108-131 (MPAdamWKernel): 16-bit weight/grad, fp32 master */
+void kvo_mp_adamw_update(size_t n, uint16_t* out, float* mean, float* var, float* w32,
+                         const uint16_t* g, int kind, float rescale, float clip, float beta1,
+                         float beta2, float eta, float lr, float wd, float eps) {
+  for (size_t i = 0; i < n; ++i) {
+    float w = w32[i];
+    float sg = rescale * kvo_half_to_float(g[i], kind);
+    if (clip >= 0.0f) sg = clipf(sg, clip);
+    const float m = mean[i] = beta1 * mean[i] + (1.0f - beta1) * sg;
+    const float v = var[i] = beta2 * var[i] + (1.0f - beta2) * (sg * sg);
+    w = w - eta * (lr * m / (sqrtf(v) + eps) + wd * w);
+    w32[i] = w;
+    out[i] = kvo_float_to_half(w, kind);
+  }
+}
+
+/* _multi_adamw_update / _multi_mp_adamw_update for ONE tensor, adamw-inl.h:340-372
+ * (MultiMPAdamWKernel): note the different association of the moment updates,
+ * mean = beta1*(mean - g) + g. w16/g16 != NULL selects the mixed-precision form. */
+void kvo_multi_adamw_update(size_t n, float* w, const float* g, uint16_t* w16, const uint16_t* g16,
+                            int kind, float* mean, float* var, float rescale, float clip,
+                            float beta1, float beta2, float eta, float lr, float wd, float eps) {
+  for (size_t i = 0; i < n; ++i) {
+    float wv = w[i]; /* fp32 weight, or the fp32 master copy */
+    float sg = rescale * (g16 ? kvo_half_to_float(g16[i], kind) : g[i]);
+    if (clip >= 0.0f) sg = clipf(sg, clip);
+    const float m = beta1 * (mean[i] - sg) + sg;
+    const float adj = sg * sg;
+    const float v = beta2 * (var[i] - adj) + adj;
+    mean[i] = m;
+    var[i] = v;
+    wv = wv - eta * (lr * m / (sqrtf(v) + eps) + wd * wv);
+    w[i] = wv;
+    if (w16) w16[i] = kvo_float_to_half(wv, kind);
+  }
+}
+
+/* lamb_update_phase1 / mp_lamb_update_phase1, optimizer_op-inl.h:1621-1648, 1772-1801.
+ * beta1_t / beta2_t = float(pow(double(beta), double(t))) (:1660-1661). The bias-corrected mean
+ * divides in DOUBLE (`1. - beta1_t`), the variance in float (`1 - beta2_t`).
+ * g16 != NULL: gradient is 16-bit and w is the fp32 master copy. */
+void kvo_lamb_phase1(size_t n, float* out, float* mean, float* var, const float* w, const float* g,
+                     const uint16_t* g16, int kind, float clip, float rescale, float beta1,
+                     float beta1_t, float beta2, float beta2_t, float wd, float eps,
+                     int bias_correction) {
+  for (size_t i = 0; i < n; ++i) {
+    float gr;
+    if (g16) {
+      /* `grad_data[i] * rescale_grad` with a half_t gradient is mshadow's half_t operator*: the
+       * product is rounded to half before it is widened to float (3rdparty/mshadow half.h) */
+      gr = kvo_half_to_float(kvo_float_to_half(kvo_half_to_float(g16[i], kind) * rescale, kind), kind);
+    } else {
+      gr = g[i] * rescale;
+    }
+    if (clip >= 0.f) gr = clipf(gr, clip);
+    mean[i] = beta1 * mean[i] + (1.f - beta1) * gr;
+    var[i] = beta2 * var[i] + (1.f - beta2) * gr * gr;
+    float r = mean[i] / (sqrtf(var[i]) + eps) + wd * w[i];
+    if (bias_correction) {
+      const float mean_hat = (float)((double)mean[i] / (1. - (double)beta1_t));
+      const float var_hat = var[i] / (1 - beta2_t);
+      r = mean_hat / (sqrtf(var_hat) + eps) + wd * w[i];
+    }
+    out[i] = r;
+  }
+}
+
+/* lamb_update_phase2 / mp_lamb_update_phase2, optimizer_op-inl.h:1705-1729, 1862-1886.
+ * out16 != NULL: mixed precision -- the reference writes ONLY the 16-bit output from
+ * weight32 - lr*g and leaves weight32 itself untouched. */
+void kvo_lamb_phase2(size_t n, float* out, uint16_t* out16, int kind, const float* w, const float* g,
+                     float r1, float r2, float lr, float lower_bound, float upper_bound) {
+  float new_r1 = r1;
+  if (lower_bound >= 0) new_r1 = new_r1 > lower_bound ? new_r1 : lower_bound;
+  if (upper_bound >= 0) new_r1 = new_r1 < upper_bound ? new_r1 : upper_bound;
+  if (new_r1 == 0.0f || r2 == 0.0f) {
+    lr = lr * 1.0f;
+  } else {
+    lr = lr * new_r1 / r2;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const float v = w[i] - lr * g[i];
+    if (out16) out16[i] = kvo_float_to_half(v, kind); else out[i] = v;
+  }
+}
+
+/* _multi_lamb_update step 1 for ONE tensor, src/operator/contrib/multi_lamb.cc:33-77
+ * (MultiLAMBKernelStep1); power::Map on floats is powf. w is fp32 (or the master copy). */
+void kvo_multi_lamb_step1(size_t n, float* temp_g, float* mean, float* var, const float* w,
+                          const float* g, const uint16_t* g16, int kind, float clip, float rescale,
+                          float beta1, float beta2, float eps, float wd, int step_count,
+                          int bias_correction) {
+  for (size_t i = 0; i < n; ++i) {
+    float sg = (g16 ? kvo_half_to_float(g16[i], kind) : g[i]) * rescale;
+    if (clip >= 0.0f) sg = clipf(sg, clip);
+    const float m = beta1 * mean[i] + (1.0f - beta1) * sg;
+    const float v = beta2 * var[i] + (1.0f - beta2) * sg * sg;
+    mean[i] = m;
+    var[i] = v;
+    float r;
+    if (bias_correction) {
+      const float mean_hat = m / (1.0f - powf(beta1, (float)step_count));
+      const float var_hat = v / (1.0f - powf(beta2, (float)step_count));
+      r = mean_hat / (sqrtf(var_hat) + eps) + wd * w[i];
+    } else {
+      r = m / (sqrtf(v) + eps) + wd * w[i];
+    }
+    temp_g[i] = r;
+  }
+}
+
+/* _multi_lamb_update step 2 for ONE tensor, multi_lamb.cc:79-118 (MultiLAMBKernelStep2) */
+void kvo_multi_lamb_step2(size_t n, float* w, uint16_t* w16, int kind, const float* temp_g,
+                          float sum_sq_w, float sum_sq_g, float lr, float lower_bound,
+                          float upper_bound) {
+  float r1 = sqrtf(sum_sq_w);
+  const float r2 = sqrtf(sum_sq_g);
+  if (lower_bound >= 0) r1 = r1 > lower_bound ? r1 : lower_bound;
+  if (upper_bound >= 0) r1 = r1 < upper_bound ? r1 : upper_bound;
+  float r;
+  if (r1 == 0.0f || r2 == 0.0f) r = 1.0f; else r = r1 / r2;
+  const float lr_adjusted = lr * r;
+  for (size_t i = 0; i < n; ++i) {
+    float wv = w[i];
+    wv -= lr_adjusted * temp_g[i];
+    w[i] = wv;
+    if (w16) w16[i] = kvo_float_to_half(wv, kind);
+  }
+}

@@ -102,6 +102,34 @@ void kvo_quantize_2bit(size_t n, uint32_t* compressed, const float* grad, float*
                        float threshold);
 void kvo_dequantize_2bit(size_t n, float* out, const uint32_t* compressed, float threshold);
 
+/* ---- multi-tensor optimizer operators ---------------------------------------- */
+/* see kvoracle.c for the reference file:line of each; kind: -1 fp32, 0 fp16, 1 bf16 */
+float kvo_sum_sq(const void* x, size_t n, int kind);
+void kvo_multi_lars(size_t n, float* out, const float* lrs, const float* w_sum_sq,
+                    const float* g_sum_sq, const float* wds, float eta, float eps, float rescale);
+void kvo_adamw_update(size_t n, float* out, float* mean, float* var, const float* w, float* g,
+                      float rescale, float clip, float beta1, float beta2, float eta, float lr,
+                      float wd, float eps);
+void kvo_mp_adamw_update(size_t n, uint16_t* out, float* mean, float* var, float* w32,
+                         const uint16_t* g, int kind, float rescale, float clip, float beta1,
+                         float beta2, float eta, float lr, float wd, float eps);
+void kvo_multi_adamw_update(size_t n, float* w, const float* g, uint16_t* w16, const uint16_t* g16,
+                            int kind, float* mean, float* var, float rescale, float clip,
+                            float beta1, float beta2, float eta, float lr, float wd, float eps);
+void kvo_lamb_phase1(size_t n, float* out, float* mean, float* var, const float* w, const float* g,
+                     const uint16_t* g16, int kind, float clip, float rescale, float beta1,
+                     float beta1_t, float beta2, float beta2_t, float wd, float eps,
+                     int bias_correction);
+void kvo_lamb_phase2(size_t n, float* out, uint16_t* out16, int kind, const float* w, const float* g,
+                     float r1, float r2, float lr, float lower_bound, float upper_bound);
+void kvo_multi_lamb_step1(size_t n, float* temp_g, float* mean, float* var, const float* w,
+                          const float* g, const uint16_t* g16, int kind, float clip, float rescale,
+                          float beta1, float beta2, float eps, float wd, int step_count,
+                          int bias_correction);
+void kvo_multi_lamb_step2(size_t n, float* w, uint16_t* w16, int kind, const float* temp_g,
+                          float sum_sq_w, float sum_sq_g, float lr, float lower_bound,
+                          float upper_bound);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,132 @@ class Oracle(object):
         L.kvo_adam_rsp_update.argtypes = [_SZ, _SZ, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F]
         L.kvo_quantize_2bit.argtypes = [_SZ, _P, _P, _P, _F]
         L.kvo_dequantize_2bit.argtypes = [_SZ, _P, _P, _F]
+        L.kvo_sum_sq.restype = _F
+        L.kvo_sum_sq.argtypes = [_P, _SZ, _I]
+        L.kvo_multi_lars.argtypes = [_SZ, _P, _P, _P, _P, _P, _F, _F, _F]
+        L.kvo_adamw_update.argtypes = [_SZ, _P, _P, _P, _P, _P] + [_F] * 8
+        L.kvo_mp_adamw_update.argtypes = [_SZ, _P, _P, _P, _P, _P, _I] + [_F] * 8
+        L.kvo_multi_adamw_update.argtypes = [_SZ, _P, _P, _P, _P, _I, _P, _P] + [_F] * 8
+        L.kvo_lamb_phase1.argtypes = [_SZ, _P, _P, _P, _P, _P, _P, _I] + [_F] * 8 + [_I]
+        L.kvo_lamb_phase2.argtypes = [_SZ, _P, _P, _I, _P, _P] + [_F] * 5
+        L.kvo_multi_lamb_step1.argtypes = [_SZ, _P, _P, _P, _P, _P, _P, _I] + [_F] * 6 + [_I, _I]
+        L.kvo_multi_lamb_step2.argtypes = [_SZ, _P, _P, _I, _P] + [_F] * 5
+
+    # ---- multi-tensor optimizer operators; arrays are updated in place ----------
+    @staticmethod
+    def _kind(a):
+        """-1 fp32, 0 fp16 (numpy float16 or uint16 bit patterns are both accepted as fp16)"""
+        return -1 if a.dtype == np.float32 else 0
+
+    def multi_sum_sq(self, arrays, kind=None):
+        out = np.empty(len(arrays), dtype=np.float32)
+        for i, a in enumerate(arrays):
+            a = np.ascontiguousarray(a)
+            out[i] = self.lib.kvo_sum_sq(_ptr(a), a.size, self._kind(a) if kind is None else kind)
+        return out
+
+    def multi_lars(self, lrs, w_sum_sq, g_sum_sq, wds, eta, eps, rescale_grad=1.0):
+        lrs, w_sum_sq, g_sum_sq, wds = _f32(lrs), _f32(w_sum_sq), _f32(g_sum_sq), _f32(wds)
+        out = np.empty_like(lrs)
+        self.lib.kvo_multi_lars(lrs.size, _ptr(out), _ptr(lrs), _ptr(w_sum_sq), _ptr(g_sum_sq),
+                                _ptr(wds), eta, eps, rescale_grad)
+        return out
+
+    def adamw_update(self, w, g, mean, var, rescale, lr, eta, beta1=0.9, beta2=0.999, eps=1e-8,
+                     wd=0.0, clip=None):
+        """_adamw_update; returns False (nothing touched) when rescale is 0 / inf / nan
+        (adamw-inl.h:449-461 PrepareInputBlobs). NOTE: g is overwritten with the scaled gradient."""
+        if not np.isfinite(np.float32(rescale)) or np.float32(rescale) == 0:
+            return False
+        self.lib.kvo_adamw_update(w.size, _ptr(w), _ptr(mean), _ptr(var), _ptr(w), _ptr(g),
+                                  rescale, self._clip(clip), beta1, beta2, eta, lr, wd, eps)
+        return True
+
+    def mp_adamw_update(self, w16, g16, mean, var, w32, kind, rescale, lr, eta, beta1=0.9,
+                        beta2=0.999, eps=1e-8, wd=0.0, clip=None):
+        if not np.isfinite(np.float32(rescale)) or np.float32(rescale) == 0:
+            return False
+        self.lib.kvo_mp_adamw_update(w32.size, _ptr(w16), _ptr(mean), _ptr(var), _ptr(w32),
+                                     _ptr(g16), kind, rescale, self._clip(clip), beta1, beta2, eta,
+                                     lr, wd, eps)
+        return True
+
+    def multi_adamw_update(self, ws, gs, means, vars_, rescale, lrs, wds, etas, beta1=0.9,
+                           beta2=0.999, eps=1e-8, clip=None, w32s=None, kind=0):
+        """_multi_adamw_update (w32s None) / _multi_mp_adamw_update (ws, gs 16-bit patterns)"""
+        if not np.isfinite(np.float32(rescale)) or np.float32(rescale) == 0:
+            return False
+        for k in range(len(ws)):
+            if w32s is None:
+                self.lib.kvo_multi_adamw_update(ws[k].size, _ptr(ws[k]), _ptr(gs[k]), None, None, 0,
+                                                _ptr(means[k]), _ptr(vars_[k]), rescale,
+                                                self._clip(clip), beta1, beta2, f32(etas[k]),
+                                                f32(lrs[k]), f32(wds[k]), eps)
+            else:
+                self.lib.kvo_multi_adamw_update(ws[k].size, _ptr(w32s[k]), None, _ptr(ws[k]),
+                                                _ptr(gs[k]), kind, _ptr(means[k]), _ptr(vars_[k]),
+                                                rescale, self._clip(clip), beta1, beta2,
+                                                f32(etas[k]), f32(lrs[k]), f32(wds[k]), eps)
+        return True
+
+    @staticmethod
+    def beta_pow(beta, t):
+        """DType(std::pow(param.beta, param.t)), optimizer_op-inl.h:1660-1661: float beta, int t ->
+        double pow -> float"""
+        return float(np.float32(math.pow(float(np.float32(beta)), int(t))))
+
+    def lamb_phase1(self, w, g, mean, var, t, beta1=0.9, beta2=0.999, eps=1e-6, wd=0.0,
+                    rescale=1.0, clip=None, bias_correction=True, g16=None, kind=0):
+        """lamb_update_phase1 (g16 None) / mp_lamb_update_phase1 (w = fp32 master, g16 patterns)"""
+        out = np.empty(w.shape, dtype=np.float32)
+        self.lib.kvo_lamb_phase1(w.size, _ptr(out), _ptr(mean), _ptr(var), _ptr(w),
+                                 _ptr(g) if g16 is None else None,
+                                 None if g16 is None else _ptr(g16), kind, self._clip(clip),
+                                 rescale, beta1, self.beta_pow(beta1, t), beta2,
+                                 self.beta_pow(beta2, t), wd, eps, int(bool(bias_correction)))
+        return out
+
+    def lamb_phase2(self, w, g, r1, r2, lr, lower_bound=None, upper_bound=None, out16_kind=None):
+        """lamb_update_phase2 -> new fp32 weight; with out16_kind: mp variant -> 16-bit patterns
+        (w is then the fp32 master copy, which the reference leaves unchanged)"""
+        lb = -1.0 if lower_bound is None else lower_bound
+        ub = -1.0 if upper_bound is None else upper_bound
+        if out16_kind is None:
+            out = np.empty(w.shape, dtype=np.float32)
+            self.lib.kvo_lamb_phase2(w.size, _ptr(out), None, 0, _ptr(w), _ptr(g), r1, r2, lr, lb, ub)
+        else:
+            out = np.empty(w.shape, dtype=np.uint16)
+            self.lib.kvo_lamb_phase2(w.size, None, _ptr(out), out16_kind, _ptr(w), _ptr(g), r1, r2,
+                                     lr, lb, ub)
+        return out
+
+    def multi_lamb_update(self, ws, gs, means, vars_, step_count, lrs, wds, beta1=0.9, beta2=0.999,
+                          eps=1e-6, rescale=1.0, lower_bound=None, upper_bound=None, clip=None,
+                          bias_correction=True, w32s=None, kind=0):
+        """_multi_lamb_update / _multi_mp_lamb_update (multi_lamb-inl.h:268-338 orchestration:
+        sum_sq(weights) -> step1 -> sum_sq(temp_g) -> step2); returns (r1_sumsq, r2_sumsq)"""
+        lb = -1.0 if lower_bound is None else lower_bound
+        ub = -1.0 if upper_bound is None else upper_bound
+        n = len(ws)
+        # MultiSumSqRun over the WEIGHT inputs (the 16-bit weights in the mp variant)
+        r1 = np.array([self.lib.kvo_sum_sq(_ptr(ws[k]), ws[k].size, -1 if w32s is None else kind)
+                       for k in range(n)], dtype=np.float32)
+        temp = [np.empty(ws[k].size, dtype=np.float32) for k in range(n)]
+        for k in range(n):
+            master = ws[k] if w32s is None else w32s[k]
+            self.lib.kvo_multi_lamb_step1(master.size, _ptr(temp[k]), _ptr(means[k]), _ptr(vars_[k]),
+                                          _ptr(master), _ptr(gs[k]) if w32s is None else None,
+                                          None if w32s is None else _ptr(gs[k]), kind,
+                                          self._clip(clip), rescale, beta1, beta2, eps, f32(wds[k]),
+                                          int(step_count[k]), int(bool(bias_correction)))
+        r2 = np.array([self.lib.kvo_sum_sq(_ptr(temp[k]), temp[k].size, -1) for k in range(n)],
+                      dtype=np.float32)
+        for k in range(n):
+            master = ws[k] if w32s is None else w32s[k]
+            self.lib.kvo_multi_lamb_step2(master.size, _ptr(master),
+                                          None if w32s is None else _ptr(ws[k]), kind, _ptr(temp[k]),
+                                          float(r1[k]), float(r2[k]), f32(lrs[k]), lb, ub)
+        return r1, r2
 
     # ---- dense reduce -------------------------------------------------------------------
     def reduce(self, srcs, order="local", nthreads=1):
@@ -250,6 +376,36 @@ class Ref(object):
     @staticmethod
     def _clip(c):
         return -1.0 if (c is None or c is False) else float(c)
+
+    _DT = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.float16): 2,
+           np.dtype(np.uint8): 3, np.dtype(np.int32): 4, np.dtype(np.int8): 5, np.dtype(np.int64): 6}
+
+    def op_invoke(self, op, inputs, outputs, **params):
+        """Run the reference's own FCompute<cpu> of `op` (oracle/ref_ops.cc). inputs / outputs are
+        C-contiguous numpy arrays (outputs are written in place; pass the same array as input and
+        output for in-place updates, as `out=weight` does). Parameters are stringified the way the
+        generated Python front-end does (python/mxnet/ndarray/register.py: str(value))."""
+        for a in list(inputs) + list(outputs):
+            assert a.flags['C_CONTIGUOUS']
+        ni, no = len(inputs), len(outputs)
+        ip = (ctypes.c_void_p * ni)(*[a.ctypes.data for a in inputs])
+        idt = (ctypes.c_int * ni)(*[self._DT[a.dtype] for a in inputs])
+        isz = (ctypes.c_int64 * ni)(*[a.size for a in inputs])
+        op_ = (ctypes.c_void_p * no)(*[a.ctypes.data for a in outputs])
+        odt = (ctypes.c_int * no)(*[self._DT[a.dtype] for a in outputs])
+        osz = (ctypes.c_int64 * no)(*[a.size for a in outputs])
+        keys = [k.encode() for k in params]
+        vals = [str(v).encode() for v in params.values()]
+        ck = (ctypes.c_char_p * len(keys))(*keys)
+        cv = (ctypes.c_char_p * len(vals))(*vals)
+        err = ctypes.create_string_buffer(2048)
+        rc = self.lib.mxref_op_invoke(op.encode(), ni, ip, idt, isz, no, op_, odt, osz, len(keys),
+                                      ck, cv, err, 2048)
+        if rc != 0:
+            raise RuntimeError(err.value.decode(errors='replace'))
+
+    def has_ops(self):
+        return hasattr(self.lib, 'mxref_op_invoke')
 
     def dmlc_stof(self, s):
         """the reference's own dmlc::stof"""
