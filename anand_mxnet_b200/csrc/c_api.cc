@@ -283,6 +283,12 @@ int MXNDArrayGetDataNDArray(NDArrayHandle handle, NDArrayHandle* out) {
   API_END();
 }
 
+int MXNDArraySlice(NDArrayHandle handle, uint32_t slice_begin, uint32_t slice_end, NDArrayHandle* out) {
+  API_BEGIN();
+  *out = new NDArray(ND(handle).Slice(slice_begin, slice_end));
+  API_END();
+}
+
 int MXNDArrayGetContext(NDArrayHandle handle, int* out_dev_type, int* out_dev_id) {
   API_BEGIN();
   NDArray& a = ND(handle);

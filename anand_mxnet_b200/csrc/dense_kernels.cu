@@ -240,6 +240,8 @@ struct KernelArgs {
   const KeyDesc* keys;
   const ChunkDesc* chunks;
   const float2* hyper;  // per key (lr, wd); re-uploaded only when a value changes
+  const float* lrs;     // preloaded_multi_*: per-key lr / wd live in two device arrays instead
+  const float* wds;
   int order;
   float momentum, rescale, clip, beta1, beta2, eps;
   // one-rank-per-GPU launches (group.h): IPC-mapped signal pads of every rank, or null
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(kThreads) dense_fused_kernel(const KernelArgs 
   }
   __syncthreads();
   Hyper h;
-  const float2 lw = a.hyper[c.key];
+  const float2 lw = a.lrs != nullptr ? make_float2(a.lrs[c.key], a.wds[c.key]) : a.hyper[c.key];
   h.lr = lw.x; h.wd = lw.y; h.momentum = a.momentum; h.rescale = a.rescale; h.clip = a.clip;
   h.beta1 = a.beta1; h.beta2 = a.beta2; h.eps = a.eps;
   const int n_src = sk.n_src, n_out = sk.n_out;
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(kThreads) dense_fused_kernel(const KernelArgs 
 
 template <typename T, int MAXSRC, int OPT>
 void launch_one(const DenseLaunch& p, cudaStream_t s) {
-  KernelArgs a{p.keys, p.chunks, reinterpret_cast<const float2*>(p.hyper), p.order, p.momentum,
+  KernelArgs a{p.keys, p.chunks, reinterpret_cast<const float2*>(p.hyper), p.lrs, p.wds, p.order, p.momentum,
                p.rescale, p.clip, p.beta1, p.beta2, p.eps, p.signal_pads, p.counter, p.rank, p.world,
                p.epoch, p.n_chunks};
   const int grid = p.n_chunks > 0 ? p.n_chunks : 1;  // a rank with no chunk still joins the barriers

@@ -62,6 +62,8 @@ struct DenseLaunch {
   const KeyDesc* keys = nullptr;      // device memory
   const ChunkDesc* chunks = nullptr;  // device memory
   const float* hyper = nullptr;       // device memory: (lr, wd) float pairs, one per key
+  const float* lrs = nullptr;         // preloaded_multi_* operators: per-key lr and wd in two
+  const float* wds = nullptr;         // device arrays (override hyper when set)
   int n_chunks = 0;
   int max_src = 0;     // max n_src over the keys (selects the unroll variant)
   int dtype = 0;       // key dtype: kFloat32 / kFloat16 / kBfloat16
@@ -79,7 +81,7 @@ struct DenseLaunch {
 void LaunchDenseFused(const DenseLaunch& p, cudaStream_t stream);
 
 // ---- small elementwise helpers for the imperative-op surface (updaters written in Python) ----
-enum EwOp : int { kEwCopy = 0, kEwAdd, kEwSub, kEwMul, kEwAddScalar, kEwMulScalar, kEwFill };
+enum EwOp : int { kEwCopy = 0, kEwAdd, kEwSub, kEwMul, kEwAddScalar, kEwMulScalar, kEwFill, kEwSqrt };
 void LaunchElementwise(int op, int dtype, void* out, const void* a, const void* b, float scalar,
                        size_t n, cudaStream_t stream);
 void LaunchCast(void* out, int out_dtype, const void* in, int in_dtype, size_t n, cudaStream_t stream);
@@ -137,6 +139,43 @@ void LaunchUniqueBatch(const RetainItem* h_items, int nitems, int64_t total_ids,
                        int64_t* d_off, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 void LaunchRetainBatch(int nitems, int64_t total_ids, int id_bits, const int64_t* d_off,
                        void* workspace, cudaStream_t stream);
+
+// ---- multi-tensor optimizer operators (multi_tensor_kernels.cu) ----
+constexpr int kMTChunk = 8192;      // elements per CTA
+constexpr int kMTMaxTensors = 64;   // tensors per launch (their scalars travel by value)
+struct MTTensor {
+  void* p[6];            // op-specific: w, g, mean, var, w32, out / temp_g (see each functor)
+  uint32_t size;         // elements
+  uint32_t vec_ok;       // every pointer 16-byte aligned (8 for 16-bit types): vector path allowed
+  uint32_t first_chunk;  // index of the tensor's first chunk partial
+  uint32_t aux;          // position of the tensor in the op's per-tensor outputs (sums of squares)
+};
+struct MTChunk { uint32_t tensor, off, len, pad; };
+struct MTScalars {
+  float4 t[kMTMaxTensors];  // per tensor, e.g. (lr, wd, eta, -)
+  float f[12];              // per launch
+  const float* d0;          // device scalars / arrays (rescale_grad, r1, sums of squares ...)
+  const float* d1;
+};
+enum MTOp : int { kMTSumSq = 0, kMTAdamW, kMTMultiAdamW, kMTLambPhase1, kMTLambPhase2,
+                  kMTMultiLambStep1, kMTMultiLambStep2 };
+struct MTLaunch {
+  int op = kMTSumSq;
+  int dtype = 0;         // DType (common.h) of the weight / gradient arrays; 0 = float32
+  bool mp = false;       // fp32 master copies present (16-bit weights)
+  const MTTensor* tensors = nullptr;
+  const MTChunk* chunks = nullptr;
+  int n_chunks = 0;
+  MTScalars s;
+  float* part0 = nullptr;  // per-chunk partial sums (reducing ops)
+  float* part1 = nullptr;
+};
+void LaunchMultiTensor(const MTLaunch& L, cudaStream_t stream);
+// out0[t.aux] (and out1) = the tensor's chunk partials summed in a fixed tree
+void LaunchMultiTensorFinalize(const MTTensor* tensors, int n_tensors, const float* part0,
+                               const float* part1, float* out0, float* out1, cudaStream_t stream);
+void LaunchMultiLars(int n, float* out, const float* lrs, const float* wsq, const float* gsq,
+                     const float* wds, float eta, float eps, float rescale, cudaStream_t stream);
 
 // ---- 2-bit gradient compression with residual (compress_kernels.cu;
 // src/kvstore/gradient_compression-inl.h:40-132, comm.h:552-596 ReduceCompressed) ----

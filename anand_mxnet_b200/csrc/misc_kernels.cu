@@ -45,6 +45,7 @@ __global__ void ew_kernel(int op, T* out, const T* a, const T* b, float scalar, 
       case kEwMul: r = __fmul_rn(x, ToF<T>(b[i])); break;
       case kEwAddScalar: r = __fadd_rn(x, scalar); break;
       case kEwMulScalar: r = __fmul_rn(x, scalar); break;
+      case kEwSqrt: r = __fsqrt_rn(x); break;
       default: r = scalar; break;
     }
     out[i] = FromF<T>(r);

@@ -132,6 +132,19 @@ NDArray NDArray::Reshaped(const std::vector<int64_t>& shape) const {
   return v;
 }
 
+NDArray NDArray::Slice(int64_t begin, int64_t end) const {
+  KV_CHECK_EQ(stype_, kDefaultStorage) << "Slice: only dense arrays can be sliced";
+  KV_CHECK(!shape().empty() && begin >= 0 && begin <= end && end <= shape()[0])
+      << "Slice: invalid range [" << begin << ", " << end << ") for axis of length "
+      << (shape().empty() ? 0 : shape()[0]);
+  NDArray v = *this;
+  std::vector<int64_t> sh = shape();
+  sh[0] = end - begin;
+  v.shape_ = sh;
+  v.byte_offset_ = byte_offset_ + static_cast<size_t>(begin) * RowLength() * DTypeSize(dtype_);
+  return v;
+}
+
 NDArray NDArray::FromDLPack(DLManagedTensorABI* t, bool transient) {
   const DLTensorABI& d = t->dl_tensor;
   NDArray a;

@@ -101,6 +101,8 @@ class NDArray {
   NDArray DataView() const;
   NDArray AuxView() const;
   NDArray Reshaped(const std::vector<int64_t>& shape) const;
+  // rows [begin, end) of the first axis, sharing storage (NDArray::Slice, src/ndarray/ndarray.cc)
+  NDArray Slice(int64_t begin, int64_t end) const;
 
   // Deep copy into a fresh array on ctx (NDArray::Copy, src/ndarray/ndarray.cc:...)
   NDArray Copy(Context ctx) const;

@@ -8,6 +8,7 @@
 #include <unordered_map>
 
 #include "kernels.h"
+#include "op_params.h"
 #include "scalar_parse.h"
 
 namespace b200kv {
@@ -17,8 +18,6 @@ void PlanChunks(uint64_t goff, size_t size, uint32_t key_slot, int ndev, int own
 
 namespace {
 
-typedef std::vector<std::pair<std::string, std::string>> Params;
-
 const std::map<std::string, OpInfo>& Registry() {
   static std::map<std::string, OpInfo> r;
   if (r.empty()) {
@@ -26,55 +25,17 @@ const std::map<std::string, OpInfo>& Registry() {
          {"sgd_update", "sgd_mom_update", "mp_sgd_update", "mp_sgd_mom_update", "multi_sgd_update",
           "multi_sgd_mom_update", "multi_mp_sgd_update", "multi_mp_sgd_mom_update", "adam_update",
           "_copyto", "_plus", "elemwise_add", "_minus", "elemwise_sub", "_mul", "elemwise_mul",
-          "_plus_scalar", "_mul_scalar", "_set_value", "cast", "Cast", "zeros_like"}) {
+          "_plus_scalar", "_mul_scalar", "_set_value", "cast", "Cast", "zeros_like", "sqrt",
+          // multi-tensor optimizer operators (multi_ops.cc)
+          "multi_sum_sq", "multi_lars", "preloaded_multi_sgd_update", "preloaded_multi_sgd_mom_update",
+          "preloaded_multi_mp_sgd_update", "preloaded_multi_mp_sgd_mom_update", "_adamw_update",
+          "_mp_adamw_update", "_multi_adamw_update", "_multi_mp_adamw_update", "lamb_update_phase1",
+          "lamb_update_phase2", "mp_lamb_update_phase1", "mp_lamb_update_phase2",
+          "_multi_lamb_update", "_multi_mp_lamb_update"}) {
       r[n] = OpInfo{n};
     }
   }
   return r;
-}
-
-const std::string* Find(const Params& p, const std::string& k) {
-  for (auto& kv : p) {
-    if (kv.first == k) return &kv.second;
-  }
-  return nullptr;
-}
-
-// scalar op parameter: dmlc::Parameter float field (dmlc::stof)
-float GetF(const Params& p, const std::string& k, float dflt) {
-  const std::string* v = Find(p, k);
-  return v ? DmlcStof(*v) : dflt;
-}
-
-int GetI(const Params& p, const std::string& k, int dflt) {
-  const std::string* v = Find(p, k);
-  return v ? std::atoi(v->c_str()) : dflt;
-}
-
-bool GetB(const Params& p, const std::string& k, bool dflt) {
-  const std::string* v = Find(p, k);
-  if (!v) return dflt;
-  return *v == "True" || *v == "true" || *v == "1";
-}
-
-// tuple op parameter "(0.1, 0.2)" / "[0.1, 0.2]": mxnet::Tuple<float> via istream >> float
-std::vector<float> GetTuple(const Params& p, const std::string& k) {
-  const std::string* v = Find(p, k);
-  KV_CHECK(v != nullptr) << "Required parameter " << k << " is missing";
-  std::vector<float> out;
-  const char* s = v->c_str();
-  while (*s) {
-    if (*s == '(' || *s == ')' || *s == '[' || *s == ']' || *s == ',' || *s == ' ' || *s == 'L') {
-      ++s;
-      continue;
-    }
-    char* end = nullptr;
-    float f = std::strtof(s, &end);
-    KV_CHECK(end != s) << "cannot parse tuple parameter " << k << "='" << *v << "'";
-    out.push_back(f);
-    s = end;
-  }
-  return out;
 }
 
 struct AdhocKey {
@@ -106,7 +67,8 @@ uint64_t Mix(uint64_t h, const void* p) {
 }
 
 // One fused launch over a list of (weight, grad, state...) tuples that live on one GPU.
-void RunAdhoc(int opt, std::vector<AdhocKey>& keys, const DenseLaunch& scalars) {
+void RunAdhoc(int opt, std::vector<AdhocKey>& keys, const DenseLaunch& scalars,
+              const NDArray* lrs = nullptr, const NDArray* wds = nullptr) {
   KV_CHECK(!keys.empty());
   const int dtype = keys[0].w.dtype();
   KV_CHECK(keys[0].w.on_gpu()) << "optimizer operators run on GPU arrays only (no CPU fallback)";
@@ -195,6 +157,18 @@ void RunAdhoc(int opt, std::vector<AdhocKey>& keys, const DenseLaunch& scalars) 
     }
   }
   DenseLaunch L = scalars;
+  if (lrs != nullptr) {
+    // preloaded_multi_*: per-tensor lr / wd are read from device arrays by the kernel
+    for (const NDArray* a : {lrs, wds}) {
+      KV_CHECK(a->on_gpu() && a->dev() == dev) << "lrs / wds must live on the weights' GPU";
+      KV_CHECK_EQ(a->dtype(), kFloat32) << "lrs / wds must be float32";
+      KV_CHECK_EQ(a->Size(), keys.size()) << "Number of learning rates / weight decays is "
+                                          << "inconsistent with num_weights parameter passed";
+      eng->BeginRead(dev, *a->var());
+    }
+    L.lrs = static_cast<const float*>(lrs->data());
+    L.wds = static_cast<const float*>(wds->data());
+  }
   L.keys = static_cast<const KeyDesc*>(plan->d_keys);
   L.chunks = static_cast<const ChunkDesc*>(plan->d_chunks);
   L.hyper = static_cast<const float*>(plan->d_hyper);
@@ -211,6 +185,10 @@ void RunAdhoc(int opt, std::vector<AdhocKey>& keys, const DenseLaunch& scalars) 
     for (const NDArray* a : {&k.s1, &k.s2, &k.w32}) {
       if (!a->is_none()) eng->MarkWrite(dev, seq, a->var());
     }
+  }
+  if (lrs != nullptr) {
+    eng->MarkRead(dev, seq, lrs->var());
+    eng->MarkRead(dev, seq, wds->var());
   }
 }
 
@@ -357,16 +335,25 @@ void InvokeOp(const OpInfo* op, const std::vector<NDArray>& in, std::vector<NDAr
     RunAdhoc(mom ? kOptSGD : kOptSGDSingle, keys, S);
     return;
   }
-  if (n.rfind("multi_", 0) == 0) {
+  if (MultiTensorOp(n, in, outputs, p)) return;  // multi_ops.cc: sum_sq, lars, adamw, lamb
+  if (n.rfind("multi_", 0) == 0 || n.rfind("preloaded_multi_", 0) == 0) {
+    // multi_[mp_]sgd[_mom]_update (optimizer_op-inl.h:207-380) and the preloaded_ forms
+    // (contrib/preloaded_multi_sgd-inl.h:154-330: same kernel, lrs / wds are two trailing INPUT
+    // arrays on the device instead of tuple attributes)
+    const bool preloaded = n.rfind("preloaded_", 0) == 0;
     const bool mp = n.find("_mp_") != std::string::npos;
     const bool mom = n.find("_mom_") != std::string::npos;
     const int stride = 2 + (mom ? 1 : 0) + (mp ? 1 : 0);
     const int num = GetI(p, "num_weights", 1);
-    KV_CHECK_EQ(static_cast<int>(in.size()), num * stride)
-        << n << ": expected num_weights*" << stride << " inputs";
-    std::vector<float> lrs = GetTuple(p, "lrs"), wds = GetTuple(p, "wds");
-    KV_CHECK_EQ(static_cast<int>(lrs.size()), num) << n << ": len(lrs) != num_weights";
-    KV_CHECK_EQ(static_cast<int>(wds.size()), num) << n << ": len(wds) != num_weights";
+    KV_CHECK_EQ(static_cast<int>(in.size()), num * stride + (preloaded ? 2 : 0))
+        << n << ": expected num_weights*" << stride << (preloaded ? " + 2" : "") << " inputs";
+    std::vector<float> lrs, wds;
+    if (!preloaded) {
+      lrs = GetTuple(p, "lrs");
+      wds = GetTuple(p, "wds");
+      KV_CHECK_EQ(static_cast<int>(lrs.size()), num) << n << ": len(lrs) != num_weights";
+      KV_CHECK_EQ(static_cast<int>(wds.size()), num) << n << ": len(wds) != num_weights";
+    }
     S.momentum = GetF(p, "momentum", 0.f);
     std::vector<AdhocKey> keys(num);
     for (int i = 0; i < num; ++i) {
@@ -376,8 +363,15 @@ void InvokeOp(const OpInfo* op, const std::vector<NDArray>& in, std::vector<NDAr
       int j = 2;
       if (mom) k.s1 = in[i * stride + j++];
       if (mp) k.w32 = in[i * stride + j++];
-      k.lr = lrs[i];
-      k.wd = wds[i];
+      k.lr = preloaded ? 0.f : lrs[i];
+      k.wd = preloaded ? 0.f : wds[i];
+    }
+    if (preloaded) {
+      for (auto& k : keys) {
+        KV_CHECK_EQ(k.w.dtype(), keys[0].w.dtype()) << n << ": all weights must share a dtype";
+      }
+      RunAdhoc(kOptSGD, keys, S, &in[num * stride], &in[num * stride + 1]);
+      return;
     }
     // group by dtype: one launch each (Updater aggregates by dtype anyway, optimizer.py:2104-2113)
     std::map<int, std::vector<AdhocKey>> by_dtype;
@@ -405,6 +399,12 @@ void InvokeOp(const OpInfo* op, const std::vector<NDArray>& in, std::vector<NDAr
     NDArray o = OutOrInput(outputs, 0, in[0]);
     Elementwise(n == "_plus_scalar" ? kEwAddScalar : kEwMulScalar, in[0], nullptr,
                 GetF(p, "scalar", 0.f), o);
+    return;
+  }
+  if (n == "sqrt") {
+    KV_CHECK_EQ(in.size(), 1u);
+    NDArray o = OutOrInput(outputs, 0, in[0]);
+    Elementwise(kEwSqrt, in[0], nullptr, 0.f, o);
     return;
   }
   if (n == "_set_value") {

@@ -21,4 +21,10 @@ const OpInfo* FindOp(const std::string& name);
 void InvokeOp(const OpInfo* op, const std::vector<NDArray>& inputs, std::vector<NDArray>* outputs,
               const std::vector<std::pair<std::string, std::string>>& params);
 
+// multi_ops.cc: the multi-tensor optimizer operators (multi_sum_sq, multi_lars, adamw, lamb);
+// returns false when `name` is not one of them
+bool MultiTensorOp(const std::string& name, const std::vector<NDArray>& inputs,
+                   std::vector<NDArray>* outputs,
+                   const std::vector<std::pair<std::string, std::string>>& params);
+
 }  // namespace b200kv

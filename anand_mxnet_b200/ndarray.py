@@ -234,6 +234,21 @@ class NDArray(object):
     def __imul__(self, other):
         return self._binary(other, '_mul', '_mul_scalar', out=self)
 
+    def __getitem__(self, key):
+        """a[b:e] on the first axis: a view sharing memory (MXNDArraySlice, ndarray.py:_slice)"""
+        if isinstance(key, int):
+            key = slice(key, key + 1)
+        if not isinstance(key, slice) or key.step not in (None, 1):
+            raise MXNetError('only contiguous slices of the first axis are supported')
+        begin, end, _ = key.indices(self.shape[0])
+        h = NDArrayHandle()
+        check_call(_LIB.MXNDArraySlice(self.handle, ctypes.c_uint(begin), ctypes.c_uint(end),
+                                       ctypes.byref(h)))
+        return NDArray(h)
+
+    def norm(self):
+        return norm(self)
+
     def __setitem__(self, key, value):
         if not (isinstance(key, slice) and key == slice(None)):
             raise MXNetError('only full-slice assignment (a[:] = v) is supported')
@@ -474,3 +489,106 @@ multi_mp_sgd_update = _op('multi_mp_sgd_update')
 multi_mp_sgd_mom_update = _op('multi_mp_sgd_mom_update')
 adam_update = _op('adam_update')
 cast = _op('cast')
+multi_sum_sq = _op('multi_sum_sq')
+multi_lars = _op('multi_lars')
+preloaded_multi_sgd_update = _op('preloaded_multi_sgd_update')
+preloaded_multi_sgd_mom_update = _op('preloaded_multi_sgd_mom_update')
+preloaded_multi_mp_sgd_update = _op('preloaded_multi_mp_sgd_update')
+preloaded_multi_mp_sgd_mom_update = _op('preloaded_multi_mp_sgd_mom_update')
+lamb_update_phase1 = _op('lamb_update_phase1')
+lamb_update_phase2 = _op('lamb_update_phase2')
+mp_lamb_update_phase1 = _op('mp_lamb_update_phase1')
+mp_lamb_update_phase2 = _op('mp_lamb_update_phase2')
+sqrt = _op('sqrt')
+
+
+def norm(data, out=None):
+    """L2 norm of the whole array as a (1,) float32 array (mx.nd.norm with its defaults, the form
+    the LAMB optimizer uses: optimizer.py:1304-1305, 1314-1315)."""
+    return _invoke('sqrt', [multi_sum_sq(data, num_arrays=1)], out=out)
+
+
+class _Internal(object):
+    _adamw_update = staticmethod(_op('_adamw_update'))
+    _mp_adamw_update = staticmethod(_op('_mp_adamw_update'))
+    _multi_adamw_update = staticmethod(_op('_multi_adamw_update'))
+    _multi_mp_adamw_update = staticmethod(_op('_multi_mp_adamw_update'))
+    _multi_lamb_update = staticmethod(_op('_multi_lamb_update'))
+    _multi_mp_lamb_update = staticmethod(_op('_multi_mp_lamb_update'))
+
+
+_internal = _Internal()
+
+
+def _flatten_list(nested_list):
+    return [item for sublist in nested_list for item in sublist]
+
+
+class _Contrib(object):
+    """python/mxnet/ndarray/contrib.py:557-680: argument marshalling of the AdamW / LAMB operators
+    (rescale_grad travels as an NDArray so that a dynamic loss scale never forces a host sync)."""
+
+    @staticmethod
+    def _rescale(rescale_grad, like):
+        if isinstance(rescale_grad, NDArray):
+            return rescale_grad
+        return full((1,), rescale_grad, ctx=like.context)
+
+    @staticmethod
+    def adamw_update(weight, grad, mean, var, rescale_grad, lr, eta, beta1=0.9, beta2=0.999,
+                     epsilon=1e-8, wd=0, clip_gradient=-1, out=None, **kwargs):
+        rs = _Contrib._rescale(rescale_grad, weight)
+        return _internal._adamw_update(weight, grad, mean, var, rs, out=out, lr=lr, eta=eta,
+                                       beta1=beta1, beta2=beta2, epsilon=epsilon, wd=wd,
+                                       clip_gradient=clip_gradient, **kwargs)
+
+    @staticmethod
+    def mp_adamw_update(weight, grad, mean, var, weight32, rescale_grad, lr, eta, beta1=0.9,
+                        beta2=0.999, epsilon=1e-8, wd=0, clip_gradient=-1, out=None, **kwargs):
+        rs = _Contrib._rescale(rescale_grad, weight32)
+        return _internal._mp_adamw_update(weight, grad, mean, var, weight32, rs, out=out, lr=lr,
+                                          eta=eta, beta1=beta1, beta2=beta2, epsilon=epsilon, wd=wd,
+                                          clip_gradient=clip_gradient, **kwargs)
+
+    @staticmethod
+    def multi_adamw_update(weights, grads, mean, var, rescale_grad, lrs, wds, etas, out=None,
+                           size=0, **kwargs):
+        if not size:
+            size = len(weights)
+        rs = _Contrib._rescale(rescale_grad, weights[0])
+        temp_list = _flatten_list(zip(weights, grads, mean, var)) + [rs]
+        return _internal._multi_adamw_update(*temp_list, out=out, num_weights=size, lrs=lrs,
+                                             wds=wds, etas=etas, **kwargs)
+
+    @staticmethod
+    def multi_mp_adamw_update(weights, grads, mean, var, weights32, rescale_grad, lrs, wds, etas,
+                              out=None, size=0, **kwargs):
+        if not size:
+            size = len(weights)
+        rs = _Contrib._rescale(rescale_grad, weights32[0])
+        temp_list = _flatten_list(zip(weights, grads, mean, var, weights32)) + [rs]
+        return _internal._multi_mp_adamw_update(*temp_list, out=out, num_weights=size, lrs=lrs,
+                                                wds=wds, etas=etas, **kwargs)
+
+    @staticmethod
+    def multi_lamb_update(weights, grads, mean, var, step_count, lrs, wds, out=None,
+                          num_tensors=0, **kwargs):
+        if not num_tensors:
+            num_tensors = len(weights)
+        temp_list = _flatten_list(zip(weights, grads, mean, var))
+        return _internal._multi_lamb_update(*temp_list, out=out, num_tensors=num_tensors,
+                                            step_count=step_count, learning_rates=lrs, wds=wds,
+                                            **kwargs)
+
+    @staticmethod
+    def multi_mp_lamb_update(weights, grads, mean, var, weights32, step_count, lrs, wds, out=None,
+                             num_tensors=0, **kwargs):
+        if not num_tensors:
+            num_tensors = len(weights)
+        temp_list = _flatten_list(zip(weights, grads, mean, var, weights32))
+        return _internal._multi_mp_lamb_update(*temp_list, out=out, num_tensors=num_tensors,
+                                               step_count=step_count, learning_rates=lrs, wds=wds,
+                                               **kwargs)
+
+
+contrib = _Contrib()

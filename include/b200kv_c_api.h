@@ -88,6 +88,9 @@ B200KV_DLL int MXNDArrayGetAuxType(NDArrayHandle handle, uint32_t i, int* out_ty
 B200KV_DLL int MXNDArrayGetAuxNDArray(NDArrayHandle handle, uint32_t i, NDArrayHandle* out); /* :1070 */
 B200KV_DLL int MXNDArrayGetDataNDArray(NDArrayHandle handle, NDArrayHandle* out);     /* :1090 */
 B200KV_DLL int MXNDArrayGetContext(NDArrayHandle handle, int* out_dev_type, int* out_dev_id); /* :1099 */
+/* view of rows [slice_begin, slice_end) of the first axis, sharing memory (LARS slices its lr array) */
+B200KV_DLL int MXNDArraySlice(NDArrayHandle handle, uint32_t slice_begin, uint32_t slice_end,
+                              NDArrayHandle* out);                                      /* :849 */
 /* zero-copy views of memory owned by another framework (torch) -- c_api.h:982-1026 */
 B200KV_DLL int MXNDArrayToDLPack(NDArrayHandle handle, DLManagedTensorHandle* out_dlpack);     /* :982 */
 B200KV_DLL int MXNDArrayFromDLPackEx(DLManagedTensorHandle dlpack, const bool transient_handle,
