@@ -171,16 +171,30 @@ size_t Engine::RoundSize(size_t bytes) {
   return (bytes + (2u << 20) - 1) & ~static_cast<size_t>((2u << 20) - 1);
 }
 
-void* Engine::Alloc(int dev, size_t bytes) {
+void* Engine::Alloc(int dev, size_t bytes, Var* fresh) {
   Init();
   KV_CHECK(dev >= 0 && dev < ndev_) << "invalid gpu id " << dev;
   DevMem& d = mem_[dev];
   size_t r = RoundSize(bytes);
   auto it = d.pool.find(r);
   if (it != d.pool.end()) {
-    void* p = it->second;
+    const Block b = it->second;
     d.pool.erase(it);
-    return p;
+    if (fresh != nullptr) {
+      // every pending op becomes a "reader" of the new array: its first writer waits for all
+      auto carry = [&](Tag t) {
+        if (t.dev < 0 || t.seq == 0 || lanes_[t.dev].completed >= t.seq) return;
+        fresh->reader_seq[t.dev] = std::max(fresh->reader_seq[t.dev], t.seq);
+        fresh->has_readers = true;
+      };
+      carry(b.pending.writer);
+      if (b.pending.has_readers) {
+        for (int e = 0; e < kMaxStreams; ++e) carry(Tag{e, b.pending.reader_seq[e]});
+      }
+    } else {
+      BeginWrite(dev, b.pending);
+    }
+    return b.p;
   }
   if (PeerGroup* grp = PeerGroup::Get()) {
     // one-rank-per-GPU mode: allocations come out of the IPC arena so peers can address them
@@ -196,7 +210,7 @@ void* Engine::Alloc(int dev, size_t bytes) {
     cudaGetLastError();
     // release the cache and retry once
     WaitAll();
-    for (auto& kv : d.pool) cudaFree(kv.second);
+    for (auto& kv : d.pool) cudaFree(kv.second.p);
     d.pool.clear();
     KV_CUDA(cudaMalloc(&p, r));
   }
@@ -204,9 +218,16 @@ void* Engine::Alloc(int dev, size_t bytes) {
   return p;
 }
 
-void Engine::Free(int dev, void* p, size_t bytes) {
+void Engine::Free(int dev, void* p, size_t bytes, const Var* last_use) {
   if (p == nullptr || !inited_) return;
-  mem_[dev].pool.emplace(RoundSize(bytes), p);
+  Block b;
+  b.p = p;
+  if (last_use != nullptr) {
+    b.pending = *last_use;
+  } else {
+    b.pending.writer = Tag{dev, lanes_[dev].issued};
+  }
+  mem_[dev].pool.emplace(RoundSize(bytes), b);
 }
 
 void* Engine::AllocPinned(size_t bytes) {

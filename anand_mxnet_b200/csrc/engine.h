@@ -71,8 +71,13 @@ class Engine {
 
   // ---- memory (pooled: blocks are cached per device and size class, never returned to the driver
   // before shutdown; the reference's GPUPooledStorageManager plays the same role)
-  void* Alloc(int dev, size_t bytes);
-  void Free(int dev, void* p, size_t bytes);
+  // A cached block remembers the device work that may still touch it (the dying array's last
+  // writer / readers, or "everything issued so far on the device's compute lane" for raw blocks).
+  // Re-use hands that record on: to the new array's Var (`fresh`: whichever lane -- copy lanes and
+  // peer GPUs included -- first writes the array waits for it), or, for raw blocks, to the
+  // compute lane of `dev` (raw blocks are tables / scratch of that lane's kernels).
+  void* Alloc(int dev, size_t bytes, Var* fresh = nullptr);
+  void Free(int dev, void* p, size_t bytes, const Var* last_use = nullptr);
   void* AllocPinned(size_t bytes);
   void FreePinned(void* p, size_t bytes);
   size_t BytesAllocated(int dev);
@@ -104,8 +109,12 @@ class Engine {
     uint64_t issued = 0, recorded = 0, completed = 0;
     uint64_t waited[kMaxStreams] = {0};  // waited[e]: this lane already waits for e's seq <= value
   };
+  struct Block {
+    void* p = nullptr;
+    Var pending;
+  };
   struct DevMem {
-    std::multimap<size_t, void*> pool;
+    std::multimap<size_t, Block> pool;
     size_t bytes = 0;
   };
   std::vector<Lane> lanes_;

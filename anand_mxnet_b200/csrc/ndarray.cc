@@ -13,8 +13,8 @@ Storage::~Storage() {
   Engine* e = Engine::Get();
   try {
     if (ctx.is_gpu()) {
-      e->Free(ctx.dev_id, dptr, bytes);
-      e->Free(ctx.dev_id, aux, aux_bytes);
+      e->Free(ctx.dev_id, dptr, bytes, &var);
+      e->Free(ctx.dev_id, aux, aux_bytes, &var);
     } else {
       // a pinned host block may still be the target/source of an in-flight async copy
       e->WaitToWrite(var);
@@ -31,9 +31,9 @@ static size_t Prod(const std::vector<int64_t>& s, size_t from = 0) {
   return n;
 }
 
-static void* AllocOn(Context ctx, size_t bytes) {
+static void* AllocOn(Context ctx, size_t bytes, Var* var) {
   Engine* e = Engine::Get();
-  if (ctx.is_gpu()) return e->Alloc(ctx.dev_id, bytes);
+  if (ctx.is_gpu()) return e->Alloc(ctx.dev_id, bytes, var);
   return e->AllocPinned(bytes);  // every host-side array is pinned so H2D/D2H copies are async DMA
 }
 
@@ -68,7 +68,7 @@ void NDArray::Alloc() const {
   if (st_->dptr != nullptr || stype_ != kDefaultStorage) return;
   size_t bytes = ByteSize();
   if (bytes == 0) return;
-  st_->dptr = AllocOn(st_->ctx, bytes);
+  st_->dptr = AllocOn(st_->ctx, bytes, &st_->var);
   st_->bytes = bytes;
 }
 
@@ -90,15 +90,15 @@ void NDArray::CheckAndAllocRows(int64_t nnr) const {
   size_t need = static_cast<size_t>(nnr) * RowLength() * DTypeSize(dtype_);
   size_t need_aux = static_cast<size_t>(nnr) * sizeof(int64_t);
   if (need > st_->bytes) {
-    if (st_->ctx.is_gpu()) e->Free(st_->ctx.dev_id, st_->dptr, st_->bytes);
+    if (st_->ctx.is_gpu()) e->Free(st_->ctx.dev_id, st_->dptr, st_->bytes, &st_->var);
     else { e->WaitToWrite(st_->var); e->FreePinned(st_->dptr, st_->bytes); }
-    st_->dptr = AllocOn(st_->ctx, need);
+    st_->dptr = AllocOn(st_->ctx, need, &st_->var);
     st_->bytes = need;
   }
   if (need_aux > st_->aux_bytes) {
-    if (st_->ctx.is_gpu()) e->Free(st_->ctx.dev_id, st_->aux, st_->aux_bytes);
+    if (st_->ctx.is_gpu()) e->Free(st_->ctx.dev_id, st_->aux, st_->aux_bytes, &st_->var);
     else { e->WaitToWrite(st_->var); e->FreePinned(st_->aux, st_->aux_bytes); }
-    st_->aux = AllocOn(st_->ctx, need_aux);
+    st_->aux = AllocOn(st_->ctx, need_aux, &st_->var);
     st_->aux_bytes = need_aux;
   }
   st_->nnr = nnr;

@@ -17,11 +17,16 @@ import warnings
 
 import numpy
 
-from .ndarray import (NDArray, zeros, sgd_update, sgd_mom_update, mp_sgd_update, mp_sgd_mom_update,
-                      multi_sgd_update, multi_sgd_mom_update, multi_mp_sgd_update,
-                      multi_mp_sgd_mom_update, adam_update, cast)
+from .ndarray import (NDArray, zeros, array, sgd_update, sgd_mom_update, mp_sgd_update,
+                      mp_sgd_mom_update, multi_sgd_update, multi_sgd_mom_update, multi_mp_sgd_update,
+                      multi_mp_sgd_mom_update, adam_update, cast, multi_sum_sq, multi_lars,
+                      preloaded_multi_sgd_update, preloaded_multi_sgd_mom_update,
+                      preloaded_multi_mp_sgd_update, preloaded_multi_mp_sgd_mom_update,
+                      lamb_update_phase1, lamb_update_phase2, mp_lamb_update_phase1,
+                      mp_lamb_update_phase2, contrib as _contrib)
 
-__all__ = ['Optimizer', 'SGD', 'Adam', 'Test', 'Updater', 'get_updater', 'create', 'register']
+__all__ = ['Optimizer', 'SGD', 'LARS', 'Adam', 'LAMB', 'Test', 'Updater', 'get_updater', 'create',
+           'register']
 
 
 def _flatten_list(nested_list):
@@ -276,6 +281,158 @@ class SGD(Optimizer):
         self._update_impl(index, weight, grad, state, multi_precision=use_mp)
 
 
+_NO_LARS_SUFFIXES = ('gamma', 'beta', 'bias')
+
+
+@register
+class LARS(Optimizer):
+    """Layer-wise adaptive rate scaling on top of SGD-momentum (optimizer.py:798-1055).
+    Per layer (except gamma / beta / bias parameters): lr *= eta * |w| / (|g| + wd * |w| + eps)
+    when both norms are positive. The dense path never leaves the device: two multi_sum_sq
+    launches, one multi_lars over the per-layer lr array, then preloaded_multi_*sgd* updates that
+    read lr / wd from device arrays."""
+
+    def __init__(self, momentum=0.0, lazy_update=True, eta=0.001, eps=0, momentum_correction=True,
+                 **kwargs):
+        super(LARS, self).__init__(**kwargs)
+        self.momentum = momentum
+        self.momentum_correction = momentum_correction
+        self.lazy_update = lazy_update
+        self.aggregate_num = int(os.getenv('MXNET_OPTIMIZER_AGGREGATION_SIZE', "4"))
+        self.eta = eta
+        self.eps = eps
+        self.skip = 0
+        self.last_lr = None
+        self.cur_lr = None
+
+    def _get_lrs(self, indices):
+        # also remembers the previous global lr for the momentum correction (optimizer.py:842-871)
+        if self.cur_lr is not None:
+            self.last_lr = self.cur_lr
+        lr = self.lr_scheduler(self.num_update) if self.lr_scheduler is not None else self.lr
+        if self.cur_lr is None:
+            self.last_lr = lr
+        self.cur_lr = lr
+        lrs = [lr for _ in indices]
+        for i, index in enumerate(indices):
+            if index in self.param_dict:
+                lrs[i] *= self.param_dict[index].lr_mult
+            elif index in self.lr_mult:
+                lrs[i] *= self.lr_mult[index]
+            elif index in self.idx2name:
+                lrs[i] *= self.lr_mult.get(self.idx2name[index], 1.0)
+        return lrs
+
+    def set_wd_mult(self, args_wd_mult):
+        # only *_weight parameters decay (optimizer.py:873-886)
+        self.wd_mult = {}
+        for n in self.idx2name.values():
+            if not n.endswith('_weight'):
+                self.wd_mult[n] = 0.0
+        if self.sym_info:
+            attr, arg_names = self.sym_info
+            for name in arg_names:
+                if name in attr and '__wd_mult__' in attr[name]:
+                    self.wd_mult[name] = float(attr[name]['__wd_mult__'])
+        self.wd_mult.update(args_wd_mult)
+
+    create_state_multi_precision = SGD.create_state_multi_precision
+
+    def create_state(self, index, weight):
+        if self.momentum == 0.0:
+            return None
+        return zeros(weight.shape, weight.context, dtype=weight.dtype)
+
+    def _name(self, i):
+        return self.idx2name[i] if i in self.idx2name else str(i)
+
+    def _l2norm(self, v, rescale=False):
+        norm = float(v.astype('float32').norm().asnumpy()[0])
+        return norm * self.rescale_grad if rescale else norm
+
+    def _get_lars(self, i, weight, g, lr, wd):
+        """per-layer learning rate of the non-aggregated (sparse) route (optimizer.py:919-933)"""
+        if self._name(i).endswith(_NO_LARS_SUFFIXES):
+            return lr
+        w_norm = self._l2norm(weight)
+        g_norm = self._l2norm(g, rescale=True)
+        if w_norm > 0.0 and g_norm > 0.0:
+            return self.eta * w_norm / (g_norm + wd * w_norm + self.eps) * lr
+        return lr
+
+    def _update_impl(self, indices, weights, grads, states, multi_precision=False):
+        aggregate = True
+        if not isinstance(indices, (tuple, list)):
+            indices, weights, grads, states = [indices], [weights], [grads], [states]
+        for weight, grad in zip(weights, grads):
+            assert isinstance(weight, NDArray)
+            assert isinstance(grad, NDArray)
+            aggregate = aggregate and weight.stype == 'default' and grad.stype == 'default'
+        self._update_count(indices)
+        lrs = self._get_lrs(indices)
+        wds = self._get_wds(indices)
+        kwargs = {'rescale_grad': self.rescale_grad}
+        if self.momentum > 0:
+            kwargs['momentum'] = (self.momentum * (self.cur_lr / self.last_lr)
+                                  if (self.momentum_correction and self.last_lr != 0)
+                                  else self.momentum)
+        if self.clip_gradient:
+            kwargs['clip_gradient'] = self.clip_gradient
+        if not aggregate:
+            lrs = [self._get_lars(i, w, g, lr, wd)
+                   for (i, w, g, lr, wd) in zip(indices, weights, grads, lrs, wds)]
+            for weight, grad, state, lr, wd in zip(weights, grads, states, lrs, wds):
+                if not multi_precision:
+                    if state is not None:
+                        sgd_mom_update(weight, grad, state, out=weight, lazy_update=self.lazy_update,
+                                       lr=lr, wd=wd, **kwargs)
+                    else:
+                        sgd_update(weight, grad, out=weight, lazy_update=self.lazy_update, lr=lr,
+                                   wd=wd, **kwargs)
+                elif state[0] is not None:
+                    mp_sgd_mom_update(weight, grad, state[0], state[1], out=weight, lr=lr, wd=wd,
+                                      **kwargs)
+                else:
+                    mp_sgd_update(weight, grad, state[1], out=weight, lr=lr, wd=wd, **kwargs)
+            return
+        # layers that get a LARS coefficient first, the rest (gamma / beta / bias) after them
+        n = len(indices)
+        skip = [self._name(i).endswith(_NO_LARS_SUFFIXES) for i in indices]
+        order = [k for k in range(n) if not skip[k]] + [k for k in range(n) if skip[k]]
+        nb_lars = n - sum(skip)
+        ctx = weights[0].context
+        new_lrs = array([lrs[k] for k in order], ctx=ctx, dtype='float32')
+        new_wds = array([wds[k] for k in order], ctx=ctx, dtype='float32')
+        ws = [weights[k] for k in order]
+        gs = [grads[k] for k in order]
+        sts = [states[k] for k in order]
+        if nb_lars > 0:
+            w_sum_sq = multi_sum_sq(*ws[:nb_lars], num_arrays=nb_lars)
+            g_sum_sq = multi_sum_sq(*gs[:nb_lars], num_arrays=nb_lars)
+            multi_lars(new_lrs[:nb_lars], w_sum_sq, g_sum_sq, new_wds[:nb_lars], eta=self.eta,
+                       eps=self.eps, rescale_grad=self.rescale_grad, out=new_lrs[:nb_lars])
+        for sidx in range(0, n, self.aggregate_num):
+            eidx = min(sidx + self.aggregate_num, n)
+            w, g, st = ws[sidx:eidx], gs[sidx:eidx], sts[sidx:eidx]
+            tail = [new_lrs[sidx:eidx], new_wds[sidx:eidx]]
+            if not multi_precision:
+                if self.momentum > 0:
+                    preloaded_multi_sgd_mom_update(*(_flatten_list(zip(w, g, st)) + tail), out=w,
+                                                   num_weights=len(w), **kwargs)
+                else:
+                    preloaded_multi_sgd_update(*(_flatten_list(zip(w, g)) + tail), out=w,
+                                               num_weights=len(w), **kwargs)
+            elif self.momentum > 0:
+                preloaded_multi_mp_sgd_mom_update(*(_flatten_list(zip(w, g, *zip(*st))) + tail),
+                                                  out=w, num_weights=len(w), **kwargs)
+            else:
+                preloaded_multi_mp_sgd_update(*(_flatten_list(zip(w, g, list(zip(*st))[1])) + tail),
+                                              out=w, num_weights=len(w), **kwargs)
+
+    update = SGD.update
+    update_multi_precision = SGD.update_multi_precision
+
+
 @register
 class Adam(Optimizer):
     """Adam (optimizer.py:1547-1629): bias correction folded into lr in python double."""
@@ -309,6 +466,96 @@ class Adam(Optimizer):
         mean, var = state
         adam_update(weight, grad, mean, var, out=weight, lazy_update=self.lazy_update, lr=lr, wd=wd,
                     **kwargs)
+
+
+@register
+class LAMB(Optimizer):
+    """LAMB (optimizer.py:1251-1370): Adam moments, then a per-layer trust ratio |w| / |g'|.
+    Lists of tensors take the fused _multi_[mp_]lamb_update operator (<= 45 tensors per call);
+    single tensors the two-phase operators with the norms computed in between."""
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-6, lower_bound=None,
+                 upper_bound=None, bias_correction=True, **kwargs):
+        super(LAMB, self).__init__(learning_rate=learning_rate, **kwargs)
+        self.beta1 = beta1
+        self.beta2 = beta2
+        self.epsilon = epsilon
+        self.lower_bound = lower_bound
+        self.upper_bound = upper_bound
+        self.bias_correction = bias_correction
+        self.aggregate_num = max(1, min(45, int(os.getenv('MXNET_OPTIMIZER_AGGREGATION_SIZE', "45"))))
+
+    def create_state(self, index, weight):
+        return (zeros(weight.shape, weight.context, dtype=weight.dtype),
+                zeros(weight.shape, weight.context, dtype=weight.dtype))
+
+    def _bounds(self):
+        kw = {}
+        if self.lower_bound:
+            kw['lower_bound'] = self.lower_bound
+        if self.upper_bound:
+            kw['upper_bound'] = self.upper_bound
+        return kw
+
+    def _update_impl(self, index, weight, grad, state, multi_precision=False):
+        kwargs = {'beta1': self.beta1, 'beta2': self.beta2, 'epsilon': self.epsilon,
+                  'bias_correction': self.bias_correction, 'rescale_grad': self.rescale_grad}
+        if self.clip_gradient:
+            kwargs['clip_gradient'] = self.clip_gradient
+        if self.aggregate_num <= 1 or not isinstance(index, (tuple, list)):
+            if isinstance(index, (tuple, list)):
+                assert len(index) == self.aggregate_num
+                index, weight, grad, state = index[0], weight[0], grad[0], state[0]
+            assert isinstance(weight, NDArray)
+            assert isinstance(grad, NDArray)
+            self._update_count(index)
+            lr = self._get_lr(index)
+            wd = self._get_wd(index)
+            kwargs['t'] = self._index_update_count[index]
+            if multi_precision:
+                weight32, (mean, var) = state[0], state[1]
+                g = mp_lamb_update_phase1(weight, grad, mean, var, weight32, wd=wd, **kwargs)
+                mp_lamb_update_phase2(weight, g, weight32.norm(), g.norm(), weight32, lr=lr,
+                                      out=weight, **self._bounds())
+            else:
+                mean, var = state
+                g = lamb_update_phase1(weight, grad, mean, var, wd=wd, **kwargs)
+                lamb_update_phase2(weight, g, weight.norm(), g.norm(), lr=lr, out=weight,
+                                   **self._bounds())
+            return
+        kwargs.update(self._bounds())
+        step_count, lrs, wds = [], [], []
+        for i, w_i, g_i in zip(index, weight, grad):
+            assert isinstance(w_i, NDArray)
+            assert isinstance(g_i, NDArray)
+            self._update_count(i)
+            step_count.append(self._index_update_count[i])
+            lrs.append(self._get_lr(i))
+            wds.append(self._get_wd(i))
+        for sidx in range(0, len(weight), self.aggregate_num):
+            eidx = min(sidx + self.aggregate_num, len(weight))
+            sl = slice(sidx, eidx)
+            if not multi_precision:
+                mean, var = list(zip(*state[sl]))
+                _contrib.multi_lamb_update(weight[sl], grad[sl], mean, var, out=weight[sl],
+                                           step_count=step_count[sl], lrs=lrs[sl], wds=wds[sl],
+                                           **kwargs)
+            else:
+                weights32, mean_var = list(zip(*state[sl]))
+                mean, var = list(zip(*mean_var))
+                _contrib.multi_mp_lamb_update(weight[sl], grad[sl], mean, var, weights32,
+                                              out=weight[sl], step_count=step_count[sl],
+                                              lrs=lrs[sl], wds=wds[sl], **kwargs)
+
+    def update(self, index, weight, grad, state):
+        self._update_impl(index, weight, grad, state, multi_precision=False)
+
+    def update_multi_precision(self, index, weight, grad, state):
+        if not isinstance(index, (tuple, list)):
+            use_mp = self.multi_precision and weight.dtype == numpy.float16
+        else:
+            use_mp = self.multi_precision and weight[0].dtype == numpy.float16
+        self._update_impl(index, weight, grad, state, multi_precision=use_mp)
 
 
 @register
