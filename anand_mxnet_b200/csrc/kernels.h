@@ -100,6 +100,17 @@ struct RspUpdateLaunch {
 };
 void LaunchRspUpdate(const RspUpdateLaunch& p, cudaStream_t stream);
 
+// standard (non-lazy) update over ALL `table_rows` rows of a dense weight; rows missing from the
+// row_sparse gradient (gidx / gval / nrows or d_nrows of `p`) use grad = 0. row_map: int32[table_rows]
+void LaunchRspStdUpdate(const RspUpdateLaunch& p, int64_t table_rows, int32_t* row_map,
+                        cudaStream_t stream);
+// storage casts: ids of the rows with any non-zero element (ascending) + count; scatter rows
+size_t NonzeroRowsWorkspaceBytes(int64_t rows);
+void LaunchNonzeroRows(const float* data, int64_t rows, int64_t row_len, int64_t* out_idx,
+                       int64_t* d_count, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+void LaunchRspScatterRows(const int64_t* idx, const float* val, int64_t nnr, int64_t row_len,
+                          float* dense, cudaStream_t stream);
+
 // union of row ids + in-order accumulation (ndarray_function.cc:59-175 semantics), one call:
 //   tag      keys[i] = id, vals[i] = i over the concatenation of the sources' id lists
 //   sort     stable radix sort of (key, val) on the low `id_bits` bits only

@@ -524,6 +524,7 @@ void KVStore::PullImpl(const std::vector<int>& keys, const std::vector<NDArray>&
   std::vector<uint64_t> sig;
   const bool cacheable = CallSignature(2, std::vector<int>(), std::vector<NDArray>(), &keys, &outs, &sig);
   if (cacheable && RunCachedCall(sig)) return;
+  bool cacheable_call = cacheable;
   std::vector<int> uniq;
   std::vector<std::vector<NDArray>> grouped;
   GroupKVPairs(keys, outs, &uniq, &grouped, [this, ignore_sparse](int key, const NDArray& nd) {
@@ -538,21 +539,33 @@ void KVStore::PullImpl(const std::vector<int>& keys, const std::vector<NDArray>&
   std::vector<DenseOp> pulls;
   for (size_t i = 0; i < uniq.size(); ++i) {
     KeyEntry& e = Entry(uniq[i]);
-    KV_CHECK_EQ(e.stype, kDefaultStorage)
-        << "pull of row_sparse key " << e.key << ": use row_sparse_pull";
-    for (auto& o : grouped[i]) {
-      KV_CHECK_EQ(o.stype(), kDefaultStorage)
-          << "pull(ignore_sparse=False) into a row_sparse array is not on this path";
+    bool plain = e.stype == kDefaultStorage;
+    for (auto& o : grouped[i]) plain = plain && o.stype() == kDefaultStorage;
+    if (!plain) {
+      // a row_sparse key or a row_sparse target: Comm::Broadcast degenerates to CopyFromTo with a
+      // storage cast (comm.h:598-616, ndarray.cc:1147-1196) -- the whole stored value travels
+      cacheable_call = false;
+      NDArray local;
+      if (e.stype == kRowSparseStorage) {
+        local = e.rsp;
+      } else {
+        const int dev = e.striped ? devset_[0] : (e.home >= 0 ? e.home : (devset_.empty() ? 0 : devset_[0]));
+        EnsureWhole(e, dev);
+        local = e.dev[e.home].w;
+      }
+      for (auto& o : grouped[i]) CopyFromTo(local, o);
+      continue;
     }
     DenseOp p;
     p.e = &e;
     p.outs = grouped[i];
     pulls.push_back(p);
   }
+  if (pulls.empty()) return;
   std::vector<Prepared> launches;
   PrepareDense(pulls, kOptPullOnly, true, &launches);
   for (auto& p : launches) RunPrepared(p);
-  if (cacheable) StoreCachedCall(sig, std::move(launches));
+  if (cacheable_call) StoreCachedCall(sig, std::move(launches));
 }
 
 // =================================================================================================

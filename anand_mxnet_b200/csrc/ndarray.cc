@@ -1,6 +1,8 @@
 // ndarray.cc -- see ndarray.h.
 #include "ndarray.h"
 
+#include "rowsparse.h"
+
 #include <cstring>
 
 namespace b200kv {
@@ -227,8 +229,10 @@ void CopyFromTo(const NDArray& from, const NDArray& to) {
   KV_CHECK(!from.is_none() && !to.is_none()) << "copy of an empty NDArray";
   if (from.SameStorage(to)) return;  // ndarray.cc:1199-1203
   KV_CHECK_EQ(from.dtype(), to.dtype()) << "CopyFromTo: dtype mismatch";
-  KV_CHECK_EQ(from.stype(), to.stype())
-      << "CopyFromTo: storage type conversion is not on the KVStore path";
+  if (from.stype() != to.stype()) {
+    CastStorageCopy(from, to);  // rowsparse.cc: dense <-> row_sparse (ndarray.cc:1147-1196)
+    return;
+  }
   if (from.stype() == kDefaultStorage) {
     KV_CHECK_EQ(from.Size(), to.Size()) << "CopyFromTo: operands shape mismatch";
     if (from.Size() == 0) return;

@@ -9,6 +9,7 @@
 
 #include "kernels.h"
 #include "op_params.h"
+#include "rowsparse.h"
 #include "scalar_parse.h"
 
 namespace b200kv {
@@ -285,9 +286,6 @@ void InvokeOp(const OpInfo* op, const std::vector<NDArray>& in, std::vector<NDAr
     KV_CHECK_EQ(in.size(), nin) << n << " expects " << nin << " inputs";
     NDArray w = in_place(0, 0);
     if (in[1].stype() == kRowSparseStorage) {
-      KV_CHECK(GetB(p, "lazy_update", true))
-          << n << ": lazy_update=False with a row_sparse gradient (standard update over all rows) "
-          << "is a next-row item";
       RspUpdateLaunch L;
       L.lr = GetF(p, "lr", 0.f);
       L.wd = GetF(p, "wd", 0.f);
@@ -297,8 +295,15 @@ void InvokeOp(const OpInfo* op, const std::vector<NDArray>& in, std::vector<NDAr
       L.beta1 = GetF(p, "beta1", 0.9f);
       L.beta2 = GetF(p, "beta2", 0.999f);
       L.eps = GetF(p, "epsilon", 1e-8f);
-      RunRspUpdate(adam ? kOptAdam : (mom ? kOptSGD : kOptSGDSingle), w, in[1],
-                   (mom || adam) ? in[2] : NDArray(), adam ? in[3] : NDArray(), L);
+      const int kind = adam ? kOptAdam : (mom ? kOptSGD : kOptSGDSingle);
+      if (GetB(p, "lazy_update", true)) {
+        RunRspUpdate(kind, w, in[1], (mom || adam) ? in[2] : NDArray(), adam ? in[3] : NDArray(), L);
+      } else {
+        // standard update: every row moves (SGDUpdateEx / SGDMomUpdateEx / AdamUpdateEx with
+        // lazy_update=False, optimizer_op-inl.h:540-565, 955-1004, 1520-1564)
+        L.opt = kind;
+        RunRspStdUpdate(w, in[1], (mom || adam) ? in[2] : NDArray(), adam ? in[3] : NDArray(), L);
+      }
       return;
     }
     AdhocKey k;

@@ -12,6 +12,7 @@
 #include <map>
 
 #include "kvstore.h"
+#include "rowsparse.h"
 #include "scalar_parse.h"
 
 namespace b200kv {
@@ -108,10 +109,12 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
   S.start[S.nsrc] = total;
   NDArray merged = NDArray::RowSparse(e.shape, Context::GPU(home), e.dtype);
   const int64_t row_len = static_cast<int64_t>(e.rsp.RowLength());
-  const bool fused = opt_.enabled && (opt_.kind == kOptSGD || opt_.kind == kOptAdam);
+  const bool on_store = opt_.enabled && (opt_.kind == kOptSGD || opt_.kind == kOptAdam);
+  // lazy: the optimizer step is fused into the row-sum kernel. standard (lazy_update=False): the
+  // merged gradient is materialised, then every row of the table is updated (RunRspStdUpdate).
+  const bool fused = on_store && opt_.lazy_update;
   RspUpdateLaunch U;
-  if (fused) {
-    KV_CHECK(opt_.lazy_update) << "lazy_update=False for row_sparse gradients is a next-row item";
+  if (on_store) {
     KV_CHECK_EQ(e.rsp.nnr(), e.shape[0])
         << "key " << e.key << ": the stored row_sparse weight must hold every row for sparse "
         << "optimizer updates (initialise it from a dense weight, as gluon does)";
@@ -120,7 +123,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     int c = (it == opt_.count.end() ? opt_.begin_num_update : it->second) + 1;
     opt_.count[e.key] = c;
     opt_.num_update = std::max(opt_.num_update, c);
-    if (total == 0) return;
+    if (total == 0 && fused) return;   // a lazy update with an all-zero gradient touches nothing
     auto lm = opt_.lr_mult.find(e.key);
     auto wm = opt_.wd_mult.find(e.key);
     double lrd = opt_.lr * (lm == opt_.lr_mult.end() ? 1.0 : lm->second);
@@ -197,6 +200,11 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     }
   }
   if (fused) return;
+  if (on_store) {
+    DevState& ds = e.dev[home];
+    RunRspStdUpdate(e.rsp, merged, ds.s1, ds.s2, U);
+    return;
+  }
   if (updater_ != nullptr && !opt_.enabled) {
     NDArray* recv_h = new NDArray(merged);
     NDArray* local_h = new NDArray(e.rsp);
@@ -339,6 +347,137 @@ void KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
     const NDArray& out = outs[which[k]];
     if (!out.on_gpu()) CopyFromTo(targets[k], out);
   }
+}
+
+// =================================================================================================
+// standard (non-lazy) updates and storage casts
+// =================================================================================================
+void RunRspStdUpdate(const NDArray& w, const NDArray& g, const NDArray& s1, const NDArray& s2,
+                     RspUpdateLaunch L) {
+  KV_CHECK(w.on_gpu() && g.on_gpu() && w.dev() == g.dev()) << "all operands must be on the same GPU";
+  KV_CHECK_EQ(w.dtype(), kFloat32) << "row_sparse optimizer updates are float32";
+  KV_CHECK_EQ(g.stype(), kRowSparseStorage);
+  const int dev = w.dev();
+  const int64_t rows = w.shape()[0];
+  if (w.stype() == kRowSparseStorage) {
+    // CheckAllRowsPresent (optimizer_op-inl.h:532-536)
+    KV_CHECK_EQ(w.nnr(), rows) << "standard sparse update: the row_sparse weight must hold every row";
+  }
+  Engine* eng = Engine::Get();
+  DeviceGuard guard(dev);
+  NDArray row_map({rows}, Context::GPU(dev), kInt32);
+  eng->BeginRead(dev, *g.var());
+  eng->BeginWrite(dev, *w.var());
+  eng->BeginWrite(dev, *row_map.var());
+  if (!s1.is_none()) eng->BeginWrite(dev, *s1.var());
+  if (!s2.is_none()) eng->BeginWrite(dev, *s2.var());
+  L.w = static_cast<float*>(w.data());
+  L.s1 = s1.is_none() ? nullptr : static_cast<float*>(s1.data());
+  L.s2 = s2.is_none() ? nullptr : static_cast<float*>(s2.data());
+  L.gidx = g.storage_initialized() ? g.row_ids() : nullptr;
+  L.gval = g.storage_initialized() ? static_cast<const float*>(g.data()) : nullptr;
+  L.nrows = g.nnr();
+  L.d_nrows = nullptr;
+  L.row_len = static_cast<int64_t>(w.RowLength());
+  LaunchRspStdUpdate(L, rows, static_cast<int32_t*>(row_map.data()), eng->Stream(dev));
+  eng->CountLaunch("rsp_std_update", static_cast<uint64_t>(rows) * L.row_len * 8);
+  uint64_t seq = eng->Issue(dev);
+  eng->MarkRead(dev, seq, g.var());
+  eng->MarkWrite(dev, seq, w.var());
+  eng->MarkWrite(dev, seq, row_map.var());
+  if (!s1.is_none()) eng->MarkWrite(dev, seq, s1.var());
+  if (!s2.is_none()) eng->MarkWrite(dev, seq, s2.var());
+}
+
+void CastStorageCopy(const NDArray& from_in, const NDArray& to) {
+  KV_CHECK(from_in.stype() == kDefaultStorage || to.stype() == kDefaultStorage)
+      << "Copying ndarray of stype = " << from_in.stype() << " to stype = " << to.stype()
+      << " is not supported";
+  KV_CHECK_EQ(from_in.dtype(), kFloat32) << "storage casts are float32 on this path";
+  KV_CHECK(from_in.shape() == to.shape()) << "CopyFromTo: operands shape mismatch";
+  Engine* eng = Engine::Get();
+  const int dev = from_in.on_gpu() ? from_in.dev() : (to.on_gpu() ? to.dev() : 0);
+  NDArray from = from_in.on_gpu() && from_in.dev() == dev ? from_in : from_in.Copy(Context::GPU(dev));
+  const int64_t rows = from.shape()[0];
+  const int64_t row_len = static_cast<int64_t>(from.RowLength());
+  DeviceGuard guard(dev);
+  cudaStream_t st = eng->Stream(dev);
+  if (to.stype() == kDefaultStorage) {
+    // row_sparse -> dense (CastStorageRspDnsImpl): zeros, then the stored rows
+    NDArray target = to.on_gpu() && to.dev() == dev ? to : NDArray(to.shape(), Context::GPU(dev), to.dtype());
+    eng->BeginRead(dev, *from.var());
+    eng->BeginWrite(dev, *target.var());
+    KV_CUDA(cudaMemsetAsync(target.data(), 0, target.ByteSize(), st));
+    if (from.storage_initialized()) {
+      LaunchRspScatterRows(from.row_ids(), static_cast<const float*>(from.data()), from.nnr(), row_len,
+                           static_cast<float*>(target.data()), st);
+    }
+    eng->CountLaunch("cast_storage(rsp->dns)", target.ByteSize());
+    uint64_t seq = eng->Issue(dev);
+    eng->MarkRead(dev, seq, from.var());
+    eng->MarkWrite(dev, seq, target.var());
+    if (!target.SameStorage(to)) CopyFromTo(target, to);
+    return;
+  }
+  // dense -> row_sparse (CastStorageDnsRspImpl): rows with any element != 0, ascending
+  NDArray target = to.on_gpu() && to.dev() == dev ? to : NDArray::RowSparse(to.shape(), Context::GPU(dev), to.dtype());
+  if (rows == 0 || row_len == 0) {
+    eng->WaitToWrite(*to.var());
+    to.SetNnr(0);
+    return;
+  }
+  NDArray ids({rows}, Context::GPU(dev), kInt64);
+  NDArray cnt({1}, Context::GPU(dev), kInt64);
+  NDArray ws({static_cast<int64_t>(NonzeroRowsWorkspaceBytes(rows))}, Context::GPU(dev), kUint8);
+  eng->BeginRead(dev, *from.var());
+  for (const NDArray* a : {&ids, &cnt, &ws}) eng->BeginWrite(dev, *a->var());
+  LaunchNonzeroRows(static_cast<const float*>(from.data()), rows, row_len,
+                    static_cast<int64_t*>(ids.data()), static_cast<int64_t*>(cnt.data()), ws.data(),
+                    ws.ByteSize(), st);
+  eng->CountLaunch("cast_storage(nonzero rows)", from.ByteSize());
+  uint64_t seq = eng->Issue(dev);
+  eng->MarkRead(dev, seq, from.var());
+  for (const NDArray* a : {&ids, &cnt, &ws}) eng->MarkWrite(dev, seq, a->var());
+  CountFence f(dev, 1);
+  f.Post(static_cast<const int64_t*>(cnt.data()), st);
+  const int64_t nnr = f.Wait()[0];
+  eng->WaitToWrite(*target.var());
+  if (nnr == 0) {
+    target.SetNnr(0);
+  } else {
+    target.CheckAndAllocRows(nnr);
+    // gather = retain with a source that holds every row
+    RetainItem it;
+    it.ids = ids.data();
+    it.ids_dtype = kInt64;
+    it.n = nnr;
+    it.start = 0;
+    it.src_idx = nullptr;
+    it.src_val = static_cast<const float*>(from.data());
+    it.src_nnr = rows;
+    it.src_dense_rows = 1;
+    it.row_len = row_len;
+    it.out_idx = target.row_ids();
+    it.out_val = static_cast<float*>(target.data());
+    NDArray off({2}, Context::GPU(dev), kInt64);
+    NDArray rws({static_cast<int64_t>(RetainBatchWorkspaceBytes(1, nnr))}, Context::GPU(dev), kUint8);
+    eng->BeginRead(dev, *from.var());
+    eng->BeginRead(dev, *ids.var());
+    eng->BeginWrite(dev, *target.var());
+    eng->BeginWrite(dev, *off.var());
+    eng->BeginWrite(dev, *rws.var());
+    const int id_bits = BitsFor(rows);
+    LaunchUniqueBatch(&it, 1, nnr, id_bits, static_cast<int64_t*>(off.data()), rws.data(), rws.ByteSize(), st);
+    LaunchRetainBatch(1, nnr, id_bits, static_cast<const int64_t*>(off.data()), rws.data(), st);
+    eng->CountLaunch("cast_storage(dns->rsp gather)", static_cast<uint64_t>(nnr) * row_len * 8);
+    uint64_t sq = eng->Issue(dev);
+    eng->MarkRead(dev, sq, from.var());
+    eng->MarkRead(dev, sq, ids.var());
+    eng->MarkWrite(dev, sq, target.var());
+    eng->MarkWrite(dev, sq, off.var());
+    eng->MarkWrite(dev, sq, rws.var());
+  }
+  if (!target.SameStorage(to)) CopyFromTo(target, to);
 }
 
 }  // namespace b200kv

@@ -247,6 +247,114 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// standard (non-lazy) updates: EVERY weight row moves (weight decay / momentum / Adam moments),
+// rows absent from the gradient see grad = 0 (optimizer_op-inl.h:505-528, optimizer_op.cc:108-139,
+// 195-229). row_map[r] = position of row r in the gradient, or -1.
+
+__global__ void row_map_scatter_kernel(const int64_t* gidx, int64_t nnr_bound, const int64_t* d_nnr,
+                                       int32_t* row_map) {
+  const int64_t nnr = d_nnr ? *d_nnr : nnr_bound;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nnr;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    row_map[gidx[i]] = static_cast<int32_t>(i);
+  }
+}
+
+// AdamStdDnsRspDnsKernel<req,cpu> (optimizer_op.cc:195-229): absent rows use g' = w*wd, and the
+// variance squares first -- (1-beta2)*(g'*g') -- with or without clipping
+__device__ __forceinline__ float step_adam_std(float w, float g, bool present, float& s1, float& s2,
+                                               const Hyper& h) {
+  float gr = present ? __fadd_rn(__fmul_rn(g, h.rescale), __fmul_rn(w, h.wd)) : __fmul_rn(w, h.wd);
+  if (h.clip >= 0.f) gr = clipf(gr, h.clip);
+  s1 = __fadd_rn(__fmul_rn(h.beta1, s1), __fmul_rn(__fsub_rn(1.f, h.beta1), gr));
+  s2 = __fadd_rn(__fmul_rn(h.beta2, s2), __fmul_rn(__fsub_rn(1.f, h.beta2), __fmul_rn(gr, gr)));
+  return __fsub_rn(w, __fdiv_rn(__fmul_rn(h.lr, s1), __fadd_rn(__fsqrt_rn(s2), h.eps)));
+}
+
+template <int OPT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_std_update_kernel(RspUpdateLaunch p,
+                                                                             const int32_t* row_map,
+                                                                             int64_t table_rows) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= table_rows) return;
+  const int lane = threadIdx.x & 31;
+  Hyper h{p.lr, p.wd, p.momentum, p.rescale, p.clip, p.beta1, p.beta2, p.eps};
+  const int32_t gi = row_map[row];
+  const bool present = gi >= 0;
+  float* w = p.w + row * p.row_len;
+  float* s1 = p.s1 ? p.s1 + row * p.row_len : nullptr;
+  float* s2 = p.s2 ? p.s2 + row * p.row_len : nullptr;
+  const float* g = present ? p.gval + static_cast<int64_t>(gi) * p.row_len : nullptr;
+  auto one = [&](float wv, float gv, float& a, float& b) -> float {
+    if (OPT == kOptAdam) return step_adam_std(wv, gv, present, a, b, h);
+    if (OPT == kOptSGD) return step<kOptSGD>(wv, gv, a, b, true, h);  // grad = 0 when absent
+    // sgd_update: the whole weight is scaled by (1 - lr*wd); present rows then take the
+    // SGDDnsRspKernel step with wd = 0, i.e. (1.f - lr*0.f)*w' - ... = w' - ...
+    const float scaled = __fmul_rn(wv, __fsub_rn(1.f, __fmul_rn(h.lr, h.wd)));
+    if (!present) return scaled;
+    if (h.clip >= 0.f) return __fsub_rn(scaled, __fmul_rn(h.lr, clipf(__fmul_rn(h.rescale, gv), h.clip)));
+    return __fsub_rn(scaled, __fmul_rn(__fmul_rn(h.lr, h.rescale), gv));
+  };
+  const bool vec = (p.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.w) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(p.gval) & 15) == 0) &&
+                   (!p.s1 || (reinterpret_cast<uintptr_t>(p.s1) & 15) == 0) &&
+                   (!p.s2 || (reinterpret_cast<uintptr_t>(p.s2) & 15) == 0);
+  if (vec) {
+    const int64_t nv = p.row_len / 4;
+    for (int64_t v = lane; v < nv; v += 32) {
+      float4 wv = reinterpret_cast<float4*>(w)[v];
+      const float4 gv = present ? __ldcs(reinterpret_cast<const float4*>(g) + v)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+      if (OPT == kOptSGD || OPT == kOptAdam) a = reinterpret_cast<float4*>(s1)[v];
+      if (OPT == kOptAdam) b = reinterpret_cast<float4*>(s2)[v];
+      wv.x = one(wv.x, gv.x, a.x, b.x);
+      wv.y = one(wv.y, gv.y, a.y, b.y);
+      wv.z = one(wv.z, gv.z, a.z, b.z);
+      wv.w = one(wv.w, gv.w, a.w, b.w);
+      reinterpret_cast<float4*>(w)[v] = wv;
+      if (OPT == kOptSGD || OPT == kOptAdam) reinterpret_cast<float4*>(s1)[v] = a;
+      if (OPT == kOptAdam) reinterpret_cast<float4*>(s2)[v] = b;
+    }
+  } else {
+    for (int64_t j = lane; j < p.row_len; j += 32) {
+      float a = 0.f, b = 0.f;
+      if (OPT == kOptSGD || OPT == kOptAdam) a = s1[j];
+      if (OPT == kOptAdam) b = s2[j];
+      w[j] = one(w[j], present ? g[j] : 0.f, a, b);
+      if (OPT == kOptSGD || OPT == kOptAdam) s1[j] = a;
+      if (OPT == kOptAdam) s2[j] = b;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// storage casts (src/operator/tensor/cast_storage-inl.h:74-140): dense -> row_sparse keeps the
+// rows with any element != 0; row_sparse -> dense scatters the rows over zeros
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+row_nonzero_flag_kernel(const float* data, int64_t rows, int64_t row_len, uint8_t* flags) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* r = data + row * row_len;
+  bool any = false;
+  for (int64_t j = lane; j < row_len; j += 32) any = any || (r[j] != 0.f);
+  any = __any_sync(0xffffffffu, any);
+  if (lane == 0) flags[row] = any ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rsp_scatter_rows_kernel(const int64_t* idx, const float* val, int64_t nnr, int64_t row_len, float* dense) {
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= nnr) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = val + r * row_len;
+  float* dst = dense + idx[r] * row_len;
+  for (int64_t j = lane; j < row_len; j += 32) dst[j] = src[j];
+}
+
 struct MergeLayout {
   size_t keys, keys_sorted, vals, vals_sorted, seg, temp, temp_bytes, total;
 };
@@ -484,6 +592,57 @@ void LaunchRetainBatch(int nitems, int64_t total, int id_bits, const int64_t* d_
   const int64_t* uniq = reinterpret_cast<const int64_t*>(ws + l.uniq);
   const int blocks = static_cast<int>((total + kWarpsPerBlock - 1) / kWarpsPerBlock);
   retain_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(items, nitems, total, id_bits, uniq, d_off);
+  KV_CUDA(cudaGetLastError());
+}
+
+void LaunchRspStdUpdate(const RspUpdateLaunch& p, int64_t table_rows, int32_t* row_map,
+                        cudaStream_t stream) {
+  if (table_rows <= 0 || p.row_len <= 0) return;
+  KV_CHECK(p.nrows < (1LL << 31));
+  KV_CUDA(cudaMemsetAsync(row_map, 0xff, static_cast<size_t>(table_rows) * sizeof(int32_t), stream));
+  if (p.nrows > 0) {
+    row_map_scatter_kernel<<<GridFor(p.nrows, 256), 256, 0, stream>>>(p.gidx, p.nrows, p.d_nrows, row_map);
+    KV_CUDA(cudaGetLastError());
+  }
+  const int blocks = static_cast<int>((table_rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const int threads = kWarpsPerBlock * 32;
+  switch (p.opt) {
+    case kOptSGDSingle: rsp_std_update_kernel<kOptSGDSingle><<<blocks, threads, 0, stream>>>(p, row_map, table_rows); break;
+    case kOptSGD: rsp_std_update_kernel<kOptSGD><<<blocks, threads, 0, stream>>>(p, row_map, table_rows); break;
+    case kOptAdam: rsp_std_update_kernel<kOptAdam><<<blocks, threads, 0, stream>>>(p, row_map, table_rows); break;
+    default: KV_FATAL << "standard row_sparse update: unsupported optimizer kind " << p.opt;
+  }
+  KV_CUDA(cudaGetLastError());
+}
+
+size_t NonzeroRowsWorkspaceBytes(int64_t rows) {
+  size_t t = 0;
+  cub::DeviceSelect::Flagged(nullptr, t, cub::CountingInputIterator<int64_t>(0),
+                             static_cast<const uint8_t*>(nullptr), static_cast<int64_t*>(nullptr),
+                             static_cast<int64_t*>(nullptr), static_cast<int>(std::max<int64_t>(rows, 1)));
+  return ((static_cast<size_t>(std::max<int64_t>(rows, 1)) + 255) & ~static_cast<size_t>(255)) + t + 256;
+}
+
+void LaunchNonzeroRows(const float* data, int64_t rows, int64_t row_len, int64_t* out_idx,
+                       int64_t* d_count, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  KV_CHECK(rows > 0 && rows < (1LL << 31));
+  KV_CHECK(workspace_bytes >= NonzeroRowsWorkspaceBytes(rows));
+  uint8_t* flags = static_cast<uint8_t*>(workspace);
+  const size_t off = (static_cast<size_t>(rows) + 255) & ~static_cast<size_t>(255);
+  const int blocks = static_cast<int>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  row_nonzero_flag_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(data, rows, row_len, flags);
+  KV_CUDA(cudaGetLastError());
+  size_t tb = workspace_bytes - off;
+  KV_CUDA(cub::DeviceSelect::Flagged(static_cast<char*>(workspace) + off, tb,
+                                     cub::CountingInputIterator<int64_t>(0), flags, out_idx, d_count,
+                                     static_cast<int>(rows), stream));
+}
+
+void LaunchRspScatterRows(const int64_t* idx, const float* val, int64_t nnr, int64_t row_len,
+                          float* dense, cudaStream_t stream) {
+  if (nnr <= 0 || row_len <= 0) return;
+  const int blocks = static_cast<int>((nnr + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  rsp_scatter_rows_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(idx, val, nnr, row_len, dense);
   KV_CUDA(cudaGetLastError());
 }
 

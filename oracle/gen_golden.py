@@ -108,6 +108,32 @@ def main():
         d["rsp_adam_%s_out" % tag] = np.stack([w2, m2, v2])
     np.savez_compressed(os.path.join(GOLD, "rowsparse_updates.npz"), **d)
 
+    # ---- standard (non-lazy) updates with a row_sparse gradient (8f-f3) ----
+    d = {}
+    rows, rl = 37, 24
+    rng3 = np.random.default_rng(0xB200 + 3)       # own stream: the fixtures above / below stay as is
+    for tag, clip in (("noclip", None), ("clip", 0.3)):
+        w, m, v = u(rng3, rows, rl), u(rng3, rows, rl), np.abs(u(rng3, rows, rl))
+        gi = np.sort(rng3.choice(rows, 11, replace=False)).astype(np.int64)
+        gi[0], gi[-1] = 0, rows - 1               # first and last row present
+        gi = np.unique(gi)
+        gv = u(rng3, gi.size, rl)
+        d["std_%s_in" % tag] = np.stack([w, m, v])
+        d["std_%s_gidx" % tag], d["std_%s_gval" % tag] = gi, gv
+        d["std_sgd_%s_out" % tag] = r.sgd_std_rsp_update(w.copy(), gi, gv, 0.1, 1e-3, 0.5, clip)
+        w2, m2 = w.copy(), m.copy()
+        r.sgd_mom_std_rsp_update(w2, m2, gi, gv, 0.1, 0.9, 1e-3, 0.5, clip)
+        d["std_sgdmom_%s_out" % tag] = np.stack([w2, m2])
+        w2, m2, v2 = w.copy(), m.copy(), v.copy()
+        r.adam_std_rsp_update(w2, m2, v2, gi, gv, 1e-3, wd=0.01, clip=clip)
+        d["std_adam_%s_out" % tag] = np.stack([w2, m2, v2])
+        # an all-zero gradient (no rows) still decays / moves every row
+        e_i, e_v = np.zeros(0, np.int64), np.zeros((0, rl), np.float32)
+        w2, m2 = w.copy(), m.copy()
+        r.sgd_mom_std_rsp_update(w2, m2, e_i, e_v, 0.1, 0.9, 1e-3, 0.5, clip)
+        d["std_sgdmom_%s_empty_out" % tag] = np.stack([w2, m2])
+    np.savez_compressed(os.path.join(GOLD, "rowsparse_std_updates.npz"), **d)
+
     # ---- 2-bit compression ----
     g = u(rng, 1003)
     res = np.zeros_like(g)

@@ -619,3 +619,63 @@ void kvo_multi_lamb_step2(size_t n, float* w, uint16_t* w16, int kind, const flo
     if (w16) w16[i] = kvo_float_to_half(wv, kind);
   }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* standard (non-lazy) updates with a row_sparse gradient                        */
+/* ------------------------------------------------------------------------------------------ */
+
+/* sgd_update, lazy_update=False (optimizer_op-inl.h:505-528): the whole weight is scaled by
+ * DType(1 - lr*wd), then SGDDnsRspKernel runs over the gradient's rows with wd = 0. */
+void kvo_sgd_std_rsp_update(size_t num_rows, size_t row_len, float* w, const int64_t* gidx,
+                            const float* gval, size_t nnr, float clip, float lr, float wd,
+                            float rescale) {
+  const float scale = (float)(1 - lr * wd);
+  for (size_t i = 0; i < num_rows * row_len; ++i) w[i] = w[i] * scale;
+  kvo_sgd_rsp_update(nnr, row_len, w, gidx, gval, clip, lr, 0.f, rescale);
+}
+
+/* sgd_mom_update, lazy_update=False (optimizer_op.cc:108-139 SGDMomStdDnsRspDnsKernel<req,cpu>):
+ * every row is updated; rows absent from the gradient use grad = 0. */
+void kvo_sgd_mom_std_rsp_update(size_t num_rows, size_t row_len, float* w, float* mom,
+                                const int64_t* gidx, const float* gval, size_t nnr, float clip,
+                                float momentum, float lr, float wd, float rescale) {
+  const float rate = lr * wd;
+  size_t k = 0; /* gradient rows are ascending: walk them alongside the weight rows */
+  for (size_t r = 0; r < num_rows; ++r) {
+    const int present = k < nnr && (size_t)gidx[k] == r;
+    const float* g = present ? gval + k * row_len : NULL;
+    for (size_t j = 0; j < row_len; ++j) {
+      const size_t i = r * row_len + j;
+      const float grad = present ? g[j] : 0.f;
+      if (clip >= 0.0f) {
+        mom[i] = momentum * mom[i] - rate * w[i] - lr * clipf(rescale * grad, clip);
+      } else {
+        mom[i] = momentum * mom[i] - rate * w[i] - lr * rescale * grad;
+      }
+      w[i] = w[i] + mom[i];
+    }
+    if (present) ++k;
+  }
+}
+
+/* adam_update, lazy_update=False (optimizer_op.cc:195-229 AdamStdDnsRspDnsKernel<req,cpu>):
+ * absent rows see grad_rescaled = w*wd; the variance squares first: (1-beta2)*(g'*g'). */
+void kvo_adam_std_rsp_update(size_t num_rows, size_t row_len, float* w, float* mean, float* var,
+                             const int64_t* gidx, const float* gval, size_t nnr, float clip,
+                             float beta1, float beta2, float lr, float wd, float eps,
+                             float rescale) {
+  size_t k = 0;
+  for (size_t r = 0; r < num_rows; ++r) {
+    const int present = k < nnr && (size_t)gidx[k] == r;
+    const float* g = present ? gval + k * row_len : NULL;
+    for (size_t j = 0; j < row_len; ++j) {
+      const size_t i = r * row_len + j;
+      float gr = present ? (g[j] * rescale + w[i] * wd) : (w[i] * wd);
+      if (clip >= 0.0f) gr = clipf(gr, clip);
+      mean[i] = beta1 * mean[i] + (1.f - beta1) * gr;
+      var[i] = beta2 * var[i] + (1.f - beta2) * (gr * gr);
+      w[i] = w[i] - lr * mean[i] / (sqrtf(var[i]) + eps);
+    }
+    if (present) ++k;
+  }
+}

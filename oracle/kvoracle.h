@@ -130,6 +130,18 @@ void kvo_multi_lamb_step2(size_t n, float* w, uint16_t* w16, int kind, const flo
                           float sum_sq_w, float sum_sq_g, float lr, float lower_bound,
                           float upper_bound);
 
+/* ---- standard (non-lazy) updates with a row_sparse gradient over a dense weight (8f-f3) ------ */
+void kvo_sgd_std_rsp_update(size_t num_rows, size_t row_len, float* w, const int64_t* gidx,
+                            const float* gval, size_t nnr, float clip, float lr, float wd,
+                            float rescale);
+void kvo_sgd_mom_std_rsp_update(size_t num_rows, size_t row_len, float* w, float* mom,
+                                const int64_t* gidx, const float* gval, size_t nnr, float clip,
+                                float momentum, float lr, float wd, float rescale);
+void kvo_adam_std_rsp_update(size_t num_rows, size_t row_len, float* w, float* mean, float* var,
+                             const int64_t* gidx, const float* gval, size_t nnr, float clip,
+                             float beta1, float beta2, float lr, float wd, float eps,
+                             float rescale);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,9 @@ class Oracle(object):
         L.kvo_adam_rsp_update.argtypes = [_SZ, _SZ, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F]
         L.kvo_quantize_2bit.argtypes = [_SZ, _P, _P, _P, _F]
         L.kvo_dequantize_2bit.argtypes = [_SZ, _P, _P, _F]
+        L.kvo_sgd_std_rsp_update.argtypes = [_SZ, _SZ, _P, _P, _P, _SZ, _F, _F, _F, _F]
+        L.kvo_sgd_mom_std_rsp_update.argtypes = [_SZ, _SZ, _P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F]
+        L.kvo_adam_std_rsp_update.argtypes = [_SZ, _SZ, _P, _P, _P, _P, _P, _SZ] + [_F] * 7
         L.kvo_sum_sq.restype = _F
         L.kvo_sum_sq.argtypes = [_P, _SZ, _I]
         L.kvo_multi_lars.argtypes = [_SZ, _P, _P, _P, _P, _P, _F, _F, _F]
@@ -89,6 +92,28 @@ class Oracle(object):
         L.kvo_lamb_phase2.argtypes = [_SZ, _P, _P, _I, _P, _P] + [_F] * 5
         L.kvo_multi_lamb_step1.argtypes = [_SZ, _P, _P, _P, _P, _P, _P, _I] + [_F] * 6 + [_I, _I]
         L.kvo_multi_lamb_step2.argtypes = [_SZ, _P, _P, _I, _P] + [_F] * 5
+
+    # ---- standard (non-lazy) updates, row_sparse gradient over a dense (rows, row_len) weight ----
+    def sgd_std_rsp_update(self, w, gidx, gval, lr, wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        self.lib.kvo_sgd_std_rsp_update(w.shape[0], w[0].size, _ptr(w), _ptr(gidx), _ptr(gval),
+                                        gidx.size, self._clip(clip), lr, wd, rescale)
+        return w
+
+    def sgd_mom_std_rsp_update(self, w, mom, gidx, gval, lr, momentum, wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        self.lib.kvo_sgd_mom_std_rsp_update(w.shape[0], w[0].size, _ptr(w), _ptr(mom), _ptr(gidx),
+                                            _ptr(gval), gidx.size, self._clip(clip), momentum, lr,
+                                            wd, rescale)
+        return w
+
+    def adam_std_rsp_update(self, w, mean, var, gidx, gval, lr, beta1=0.9, beta2=0.999, eps=1e-8,
+                            wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        self.lib.kvo_adam_std_rsp_update(w.shape[0], w[0].size, _ptr(w), _ptr(mean), _ptr(var),
+                                         _ptr(gidx), _ptr(gval), gidx.size, self._clip(clip), beta1,
+                                         beta2, lr, wd, eps, rescale)
+        return w
 
     # ---- multi-tensor optimizer operators; arrays are updated in place ----------
     @staticmethod
@@ -403,6 +428,31 @@ class Ref(object):
                                       ck, cv, err, 2048)
         if rc != 0:
             raise RuntimeError(err.value.decode(errors='replace'))
+
+    def sgd_std_rsp_update(self, w, gidx, gval, lr, wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        f = self.lib.mxref_sgd_std_rsp_update
+        f.argtypes = [ctypes.c_int64, ctypes.c_int64, _P, _P, _P, ctypes.c_int64, _F, _F, _F, _F]
+        f(w.shape[0], w[0].size, _ptr(w), _ptr(gidx), _ptr(gval), gidx.size, self._clip(clip), lr, wd,
+          rescale)
+        return w
+
+    def sgd_mom_std_rsp_update(self, w, mom, gidx, gval, lr, momentum, wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        f = self.lib.mxref_sgd_mom_std_rsp_update
+        f.argtypes = [ctypes.c_int64, ctypes.c_int64, _P, _P, _P, _P, ctypes.c_int64, _F, _F, _F, _F, _F]
+        f(w.shape[0], w[0].size, _ptr(w), _ptr(mom), _ptr(gidx), _ptr(gval), gidx.size,
+          self._clip(clip), momentum, lr, wd, rescale)
+        return w
+
+    def adam_std_rsp_update(self, w, mean, var, gidx, gval, lr, beta1=0.9, beta2=0.999, eps=1e-8,
+                            wd=0.0, rescale=1.0, clip=None):
+        gidx = np.ascontiguousarray(gidx, dtype=np.int64)
+        f = self.lib.mxref_adam_std_rsp_update
+        f.argtypes = [ctypes.c_int64, ctypes.c_int64, _P, _P, _P, _P, _P, ctypes.c_int64] + [_F] * 7
+        f(w.shape[0], w[0].size, _ptr(w), _ptr(mean), _ptr(var), _ptr(gidx), _ptr(gval), gidx.size,
+          self._clip(clip), beta1, beta2, lr, wd, eps, rescale)
+        return w
 
     def has_ops(self):
         return hasattr(self.lib, 'mxref_op_invoke')

@@ -15,6 +15,9 @@
 //   _adamw_update / _mp_adamw_update    src/operator/contrib/adamw-inl.h:108-215, adamw.cc:117-141
 //   _multi_adamw_update / _multi_mp_..  src/operator/contrib/adamw-inl.h:322-497
 //   lamb_update_phase1/2, mp_lamb_...   src/operator/optimizer_op-inl.h:1566-1930
+//   standard (non-lazy) sparse updates   src/operator/optimizer_op.cc:108-139, 195-229 (the
+//       <req,cpu> kernels; their Impl functions need NDArray / Resource objects, so the row-flag
+//       prefix sum of optimizer_op.cc:173-182 is rebuilt here and the kernels are called per row)
 //   _multi_lamb_update / _multi_mp_..   src/operator/contrib/multi_lamb.cc:33-170 (Step1/Step2
 //       kernels; the temp-space orchestration of multi_lamb-inl.h:268-338 needs the engine's
 //       Resource manager and is restated below with a plain workspace)
@@ -54,6 +57,7 @@ struct FakeOp {
 }  // namespace mxref
 #undef NNVM_REGISTER_OP
 #define NNVM_REGISTER_OP(OpName) static ::mxref::FakeOp __fake_op_##OpName = ::mxref::FakeOp()
+#include "operator/optimizer_op.cc"   // SGDMomStdDnsRspDnsKernel<req,cpu>, AdamStdDnsRspDnsKernel<req,cpu>
 #include "operator/contrib/multi_sum_sq.cc"
 #include "operator/contrib/multi_lars.cc"
 #include "operator/contrib/preloaded_multi_sgd.cc"
@@ -65,8 +69,6 @@ using namespace mxnet;
 // Glue the reference keeps in translation units this harness does not compile:
 //  * the OMP thread-count policy object consulted by Kernel<OP,cpu>::Launch (src/engine/openmp.cc):
 //    here simply a harness-controlled number (mxref_set_omp_threads), default 1;
-//  * the parameter-manager singletons of the LAMB phase ops (DMLC_REGISTER_PARAMETER lines of
-//    src/operator/optimizer_op.cc:46-47).
 static int g_omp_threads = 1;
 namespace mxnet {
 namespace engine {
@@ -77,10 +79,20 @@ OpenMP* OpenMP::Get() {
 }
 int OpenMP::GetRecommendedOMPThreadCount(bool) const { return g_omp_threads; }
 }  // namespace engine
+// optimizer_op.cc's FComputeEx functions (never called here) reference a few libmxnet symbols;
+// the library must still load, so they get aborting definitions.
 namespace op {
-DMLC_REGISTER_PARAMETER(LambUpdatePhaseOneParam);
-DMLC_REGISTER_PARAMETER(LambUpdatePhaseTwoParam);
+namespace mxnet_op {
+template <>
+bool tuned_op<set_to_int<0>, int64_t>::UseOMP(size_t, size_t) { return false; }
+}  // namespace mxnet_op
 }  // namespace op
+Storage* Storage::Get() { LOG(FATAL) << "mxref: Storage is not part of the harness"; return nullptr; }
+void NDArray::SetTBlob() const { LOG(FATAL) << "mxref: NDArray is not part of the harness"; }
+void* Resource::get_space_internal(size_t) const {
+  LOG(FATAL) << "mxref: Resource is not part of the harness";
+  return nullptr;
+}
 }  // namespace mxnet
 
 namespace {
@@ -192,6 +204,51 @@ int mxref_op_invoke(const char* op, int nin, void** in_ptr, const int* in_dtype,
       err[errlen - 1] = '\0';
     }
     return -1;
+  }
+}
+
+// standard (non-lazy) updates with a row_sparse gradient over a dense weight of `num_rows` rows:
+// prefix_sum as optimizer_op.cc:173-182 (row flags, inclusive scan), then one Map per weight row.
+static std::vector<nnvm::dim_t> RowPrefixSum(int64_t num_rows, const int64_t* gidx, int64_t nnr) {
+  std::vector<nnvm::dim_t> ps(num_rows, 0);
+  for (int64_t i = 0; i < nnr; ++i) ps[gidx[i]] = 1;
+  for (int64_t i = 1; i < num_rows; ++i) ps[i] += ps[i - 1];
+  return ps;
+}
+
+void mxref_sgd_mom_std_rsp_update(int64_t num_rows, int64_t row_len, float* w, float* mom,
+                                  const int64_t* gidx, const float* gval, int64_t nnr, float clip,
+                                  float momentum, float lr, float wd, float rescale) {
+  std::vector<nnvm::dim_t> ps = RowPrefixSum(num_rows, gidx, nnr);
+  for (int64_t i = 0; i < num_rows; ++i) {
+    op::SGDMomStdDnsRspDnsKernel<kWriteInplace, cpu>::Map(static_cast<int>(i), row_len, w, mom, w, gidx,
+                                                        gval, ps.data(), clip, momentum, lr, wd, rescale);
+  }
+}
+
+void mxref_adam_std_rsp_update(int64_t num_rows, int64_t row_len, float* w, float* mean, float* var,
+                               const int64_t* gidx, const float* gval, int64_t nnr, float clip,
+                               float beta1, float beta2, float lr, float wd, float eps, float rescale) {
+  std::vector<nnvm::dim_t> ps = RowPrefixSum(num_rows, gidx, nnr);
+  for (int64_t i = 0; i < num_rows; ++i) {
+    op::AdamStdDnsRspDnsKernel<kWriteInplace, cpu>::Map(static_cast<int>(i), row_len, w, mean, var, w, gidx,
+                                                      gval, ps.data(), clip, beta1, beta2, lr, wd, eps,
+                                                      rescale);
+  }
+}
+
+// non-lazy sgd_update (optimizer_op-inl.h:505-528): whole-weight scale by DType(1 - lr*wd) through
+// the reference's op_with_req<mul> kernel, then SGDDnsRspKernel<req,cpu> with wd = 0 on the rows
+void mxref_sgd_std_rsp_update(int64_t num_rows, int64_t row_len, float* w, const int64_t* gidx,
+                              const float* gval, int64_t nnr, float clip, float lr, float wd,
+                              float rescale) {
+  const float scale = static_cast<float>(1 - lr * wd);
+  for (int64_t i = 0; i < num_rows * row_len; ++i) {
+    op::mxnet_op::op_with_req<op::mshadow_op::mul, kWriteInplace>::Map(static_cast<int>(i), w, w, scale);
+  }
+  for (int64_t r = 0; r < nnr; ++r) {
+    op::SGDDnsRspKernel<kWriteInplace, cpu>::Map(static_cast<int>(r), row_len, w, w, gidx, gval, clip, lr,
+                                                 0.f, rescale);
   }
 }
 

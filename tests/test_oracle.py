@@ -117,6 +117,38 @@ def test_rowsparse_updates_golden(oracle, golden, tag, clip):
     assert eq(np.stack([w2, m2, v2]), g["rsp_adam_%s_out" % tag])
 
 
+@pytest.mark.parametrize("tag,clip", (("noclip", None), ("clip", 0.3)))
+def test_rowsparse_std_updates_golden_and_live(oracle, golden, tag, clip):
+    """non-lazy updates: restatement vs the golden outputs of the reference's
+    <req,cpu> std kernels, and vs the live harness when it is built here"""
+    g = golden("rowsparse_std_updates")
+    w, m, v = g["std_%s_in" % tag]
+    gi, gv = g["std_%s_gidx" % tag], g["std_%s_gval" % tag]
+    backends = [(oracle, True)]
+    if K.ref() is not None and K.ref().has_ops():
+        backends.append((K.ref(), False))
+    for b, _ in backends:
+        assert eq(b.sgd_std_rsp_update(w.copy(), gi, gv, 0.1, 1e-3, 0.5, clip), g["std_sgd_%s_out" % tag])
+        w2, m2 = w.copy(), m.copy()
+        b.sgd_mom_std_rsp_update(w2, m2, gi, gv, 0.1, 0.9, 1e-3, 0.5, clip)
+        assert eq(np.stack([w2, m2]), g["std_sgdmom_%s_out" % tag])
+        w2, m2, v2 = w.copy(), m.copy(), v.copy()
+        b.adam_std_rsp_update(w2, m2, v2, gi, gv, 1e-3, wd=0.01, clip=clip)
+        assert eq(np.stack([w2, m2, v2]), g["std_adam_%s_out" % tag])
+        w2, m2 = w.copy(), m.copy()
+        b.sgd_mom_std_rsp_update(w2, m2, np.zeros(0, np.int64), np.zeros((0, w.shape[1]), np.float32),
+                                 0.1, 0.9, 1e-3, 0.5, clip)
+        assert eq(np.stack([w2, m2]), g["std_sgdmom_%s_empty_out" % tag])
+    # std SGD / SGD-momentum equal the DENSE kernels on the densified gradient (what the CUDA path uses)
+    dense = np.zeros_like(w)
+    dense[gi] = gv
+    assert eq(oracle.sgd_update(w.copy().ravel(), dense.ravel(), 0.1, 1e-3, 0.5, clip).reshape(w.shape),
+              g["std_sgd_%s_out" % tag])
+    w2, m2 = w.copy().ravel(), m.copy().ravel()
+    oracle.sgd_mom_update(w2, dense.ravel(), m2, 0.1, 0.9, 1e-3, 0.5, clip)
+    assert eq(np.stack([w2.reshape(w.shape), m2.reshape(w.shape)]), g["std_sgdmom_%s_out" % tag])
+
+
 def test_twobit_golden(oracle, golden):
     g = golden("twobit")
     res = np.zeros_like(g["grad"])

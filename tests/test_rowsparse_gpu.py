@@ -197,3 +197,104 @@ def test_host_resident_sparse_values(mx, oracle):
     for _, i, v in srcs:
         dense[i] += v
     assert np.array_equal(out.asnumpy(), dense)     # small integers: exact
+
+
+# ---------------------------------------------------------------------------------- SURVEY 8f-f3
+@pytest.mark.parametrize("tag,clip", [("noclip", None), ("clip", 0.3)])
+def test_std_update_ops_golden(mx, golden, tag, clip):
+    """lazy_update=False: every row moves. Against the reference's own <req,cpu> std kernels
+    (optimizer_op.cc:108-139, 195-229; tests/golden/rowsparse_std_updates.npz), bit for bit."""
+    g = golden("rowsparse_std_updates")
+    dev = mx.gpu(0)
+    w, m, v = g["std_%s_in" % tag]
+    gi, gv = g["std_%s_gidx" % tag], g["std_%s_gval" % tag]
+    grad = mx.nd.sparse.row_sparse_array((gv, gi), shape=w.shape, ctx=dev)
+    kw = dict(clip_gradient=clip) if clip else {}
+    wn = mx.nd.array(w, dev)
+    mx.nd.sgd_update(wn, grad, out=wn, lr=0.1, wd=1e-3, rescale_grad=0.5, lazy_update=False, **kw)
+    assert eq(wn.asnumpy(), g["std_sgd_%s_out" % tag])
+    wn, mn = mx.nd.array(w, dev), mx.nd.array(m, dev)
+    mx.nd.sgd_mom_update(wn, grad, mn, out=wn, lr=0.1, momentum=0.9, wd=1e-3, rescale_grad=0.5,
+                         lazy_update=False, **kw)
+    assert eq(np.stack([wn.asnumpy(), mn.asnumpy()]), g["std_sgdmom_%s_out" % tag])
+    wn, mn, vn = mx.nd.array(w, dev), mx.nd.array(m, dev), mx.nd.array(v, dev)
+    mx.nd.adam_update(wn, grad, mn, vn, out=wn, lr=1e-3, wd=0.01, lazy_update=False, **kw)
+    assert eq(np.stack([wn.asnumpy(), mn.asnumpy(), vn.asnumpy()]), g["std_adam_%s_out" % tag])
+    # an all-zero gradient still decays / moves every row
+    wn, mn = mx.nd.array(w, dev), mx.nd.array(m, dev)
+    empty = mx.nd.sparse.zeros('row_sparse', w.shape, dev)
+    mx.nd.sgd_mom_update(wn, empty, mn, out=wn, lr=0.1, momentum=0.9, wd=1e-3, rescale_grad=0.5,
+                         lazy_update=False, **kw)
+    assert eq(np.stack([wn.asnumpy(), mn.asnumpy()]), g["std_sgdmom_%s_empty_out" % tag])
+
+
+@pytest.mark.parametrize("optname", ['sgd', 'sgd_mom', 'adam'])
+def test_store_std_sparse_update(mx, oracle, optname):
+    """optimizer on the store with lazy_update=False and row_sparse pushes"""
+    rng = np.random.default_rng(15)
+    shape = (300, 20)
+    w = rng.uniform(-1, 1, shape).astype(np.float32)
+    kv = mx.kv.create('device')
+    kv.init(0, mx.nd.array(w, mx.gpu(0)).tostype('row_sparse'))
+    if optname.startswith('sgd'):
+        mom = 0.9 if optname == 'sgd_mom' else 0.0
+        kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=mom, wd=1e-3, rescale_grad=0.5,
+                                          lazy_update=False))
+    else:
+        kv.set_optimizer(mx.optimizer.Adam(learning_rate=1e-3, wd=0.01, rescale_grad=0.5,
+                                           lazy_update=False))
+    sp = K.scalar_param
+    m, v = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+    for t in range(1, 4):
+        srcs = [make_rsp(mx, rng, shape, 40, mx.gpu(0)) for _ in range(3)]
+        kv.push(0, [s[0] for s in srcs])
+        gi, gv = oracle.rsp_reduce([s[1] for s in srcs], [s[2] for s in srcs])
+        if optname == 'sgd':
+            oracle.sgd_std_rsp_update(w, gi, gv, sp(0.1), sp(1e-3), sp(0.5))
+        elif optname == 'sgd_mom':
+            oracle.sgd_mom_std_rsp_update(w, m, gi, gv, sp(0.1), sp(0.9), sp(1e-3), sp(0.5))
+        else:
+            oracle.adam_std_rsp_update(w, m, v, gi, gv, sp(K.adam_lr(1e-3, 0.9, 0.999, t)), sp(0.9),
+                                       sp(0.999), sp(1e-8), sp(0.01), sp(0.5))
+        out = mx.nd.sparse.zeros('row_sparse', shape, mx.gpu(0))
+        kv.row_sparse_pull(0, out=out, row_ids=mx.nd.array(np.arange(shape[0]), mx.gpu(0), np.int64))
+        assert eq(out.asnumpy(), w), t
+
+
+def test_pull_with_storage_casts(mx):
+    """pull(ignore_sparse=False) (kvstore.py:233-319; comm Broadcast -> CopyFromTo casts,
+    ndarray.cc:1147-1196, cast_storage-inl.h:74-140)"""
+    rng = np.random.default_rng(21)
+    shape = (50, 8)
+    dense = rng.uniform(-1, 1, shape).astype(np.float32)
+    dense[[0, 7, 8, 33, 49]] = 0          # dense -> row_sparse drops all-zero rows
+    dense[5, 3] = -0.0                    # ... a negative zero is still zero
+    dense[5, :3] = 0
+    dense[5, 4:] = 0
+    kv = mx.kv.create('device')
+    kv.init('d', mx.nd.array(dense, mx.gpu(0)))
+    out = mx.nd.sparse.zeros('row_sparse', shape, mx.gpu(0))
+    kv.pull('d', out=out, ignore_sparse=False)
+    keep = np.array([r for r in range(shape[0]) if np.any(dense[r] != 0)], np.int64)
+    assert np.array_equal(out.indices.asnumpy(), keep)
+    assert eq(out.data.asnumpy(), dense[keep])
+    # ignore_sparse=True (default): a row_sparse target of a pull is skipped
+    untouched = mx.nd.sparse.zeros('row_sparse', shape, mx.gpu(0))
+    kv.pull('d', out=untouched)
+    assert untouched.indices.shape[0] == 0
+    # row_sparse key: full copy into a row_sparse target, scatter into a dense one
+    idx = np.array([2, 3, 11, 48], np.int64)
+    val = rng.uniform(-1, 1, (4, 8)).astype(np.float32)
+    kv.init('r', mx.nd.sparse.row_sparse_array((val, idx), shape=shape, ctx=mx.gpu(0)))
+    out_r = mx.nd.sparse.zeros('row_sparse', shape, mx.gpu(0))
+    kv.pull('r', out=out_r, ignore_sparse=False)
+    assert np.array_equal(out_r.indices.asnumpy(), idx) and eq(out_r.data.asnumpy(), val)
+    out_d = mx.nd.array(np.full(shape, 9, np.float32), mx.gpu(0))
+    kv.pull('r', out=out_d, ignore_sparse=False)
+    want = np.zeros(shape, np.float32)
+    want[idx] = val
+    assert eq(out_d.asnumpy(), want)
+    # copyto across storage types and devices (host target)
+    host = mx.nd.zeros(shape, mx.cpu())
+    out_r.copyto(host)
+    assert eq(host.asnumpy(), want)
