@@ -47,6 +47,8 @@ std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>
       continue;
     }
     pl->dev = pdev;
+    if (!from.on_gpu()) { pl->host_io = true; pl->lane = Engine::CopyInLane(pdev); }
+    if (!to.on_gpu()) { pl->host_io = true; pl->lane = Engine::CopyOutLane(pdev); }
     const char* s = static_cast<const char*>(from.data());
     char* d = static_cast<char*>(to.data());
     const uint64_t n = from.ByteSize();
@@ -59,29 +61,36 @@ std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>
   *pairs = rest;
   if (items.empty()) return nullptr;
   Engine* eng = Engine::Get();
+  if (pl->lane < 0) pl->lane = pl->dev;
   pl->n_items = static_cast<int>(items.size());
   pl->bytes_items = items.size() * sizeof(PackItem);
   pl->d_items = eng->Alloc(pl->dev, pl->bytes_items);
   DeviceGuard g(pl->dev);
   KV_CUDA(cudaMemcpyAsync(pl->d_items, items.data(), pl->bytes_items, cudaMemcpyHostToDevice,
                           eng->Stream(pl->dev)));
+  if (pl->lane != pl->dev) {
+    // the item table was uploaded on the compute lane; the copy lane must see it
+    const uint64_t seq = eng->Issue(pl->dev);
+    eng->StreamWait(pl->lane, Tag{pl->dev, seq});
+  }
   return pl;
 }
 
 void RunPackList(PackList& pl) {
   Engine* eng = Engine::Get();
-  const int dev = pl.dev;
+  const int lane = pl.lane;
   for (auto& pr : pl.pairs) {
-    eng->BeginRead(dev, *pr.first.var());
-    eng->BeginWrite(dev, *pr.second.var());
+    eng->BeginRead(lane, *pr.first.var());
+    eng->BeginWrite(lane, *pr.second.var());
   }
-  DeviceGuard g(dev);
-  LaunchPackBulk(static_cast<const PackItem*>(pl.d_items), pl.n_items, pl.total_bytes, eng->Stream(dev));
+  DeviceGuard g(pl.dev);
+  LaunchPackBulk(static_cast<const PackItem*>(pl.d_items), pl.n_items, pl.total_bytes, eng->Stream(lane),
+                 pl.host_io ? 32 : 0);
   eng->CountLaunch("pack_bulk(tma)", 2 * pl.total_bytes);
-  const uint64_t seq = eng->Issue(dev);
+  const uint64_t seq = eng->Issue(lane);
   for (auto& pr : pl.pairs) {
-    eng->MarkRead(dev, seq, pr.first.var());
-    eng->MarkWrite(dev, seq, pr.second.var());
+    eng->MarkRead(lane, seq, pr.first.var());
+    eng->MarkWrite(lane, seq, pr.second.var());
   }
 }
 
@@ -204,10 +213,14 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
     static const int kHostMode = []() {
       const char* z = std::getenv("B200KV_HOST_MODE");
       const std::string m = z ? z : "zc";
-      return m == "staged" ? 0 : m == "in_dma" ? 2 : m == "in_tma" ? 3 : 1;
+      return m == "staged" ? 0 : m == "in_dma" ? 2 : m == "in_tma" ? 3 : m == "pipe" ? 4 : 1;
     }();
+    // pipe: TMA pack kernels on the two copy lanes move each bucket in / out (one launch per
+    // bucket and direction) while the compute lane runs the fused kernel of the bucket between
     auto direct_in = [&](const NDArray& a) { return a.on_gpu() || (kHostMode == 1 && a.kernel_visible_host()); };
-    auto direct_out = [&](const NDArray& a) { return a.on_gpu() || (kHostMode >= 1 && a.kernel_visible_host()); };
+    auto direct_out = [&](const NDArray& a) {
+      return a.on_gpu() || (kHostMode >= 1 && kHostMode <= 3 && a.kernel_visible_host());
+    };
     size_t staged = 0;
     for (auto& s : op.srcs) if (!direct_in(s)) staged += s.ByteSize();
     for (auto& o : op.outs) if (!direct_out(o)) staged += o.ByteSize();
@@ -260,9 +273,11 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
       KV_CHECK_EQ(enabled, static_cast<int>(P.parts.size() * (P.parts.size() - 1)))
           << "GPU peer access is not available between all participating devices";
     }
-    if (std::getenv("B200KV_HOST_MODE") && std::string(std::getenv("B200KV_HOST_MODE")) == "in_tma") {
+    const char* hm = std::getenv("B200KV_HOST_MODE");
+    if (hm != nullptr && (std::string(hm) == "in_tma" || std::string(hm) == "pipe")) {
       P.pack_in = BuildPackList(&P.stage_in);
     }
+    if (hm != nullptr && std::string(hm) == "pipe") P.pack_out = BuildPackList(&P.stage_out);
     out->push_back(std::move(P));
   }
 }

@@ -33,7 +33,17 @@ void KVStore::PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::ve
   KV_CHECK(g != nullptr);
   const int dev = g->dev();
   const bool is_push = opt_kind != kOptPullOnly;
-  std::map<int, Prepared> groups;  // by dtype
+  // Launch groups by (dtype, bucket). Operands outside this rank's arena (host memory, a
+  // framework's own tensors) are staged; such a call is cut into buckets of ~16 MB of key bytes so
+  // that the transfer in of bucket b+1 (H2D lane), the fused kernel of bucket b (compute lane) and
+  // the transfer out of bucket b-1 (D2H lane) overlap. Calls whose operands all live in the arena
+  // stay ONE launch.
+  static const size_t kBucketBytes = []() {
+    const char* z = std::getenv("B200KV_GROUP_BUCKET_MB");
+    return static_cast<size_t>(z ? std::max(1, std::atoi(z)) : 16) << 20;
+  }();
+  std::map<std::pair<int, int>, Prepared> groups;
+  std::map<int, std::pair<int, size_t>> bucket_of;  // dtype -> (bucket, bytes in it)
   auto arena_copy = [&](const NDArray& a) { return a.on_gpu() && a.dev() == dev && g->InArena(a.data()); };
   for (auto& op : ops) {
     KeyEntry& e = *op.e;
@@ -43,7 +53,19 @@ void KVStore::PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::ve
         << "one-rank-per-GPU store: at most " << kMaxLocalOut << " pull targets per key per rank";
     if (e.home < 0) EnsureOnDevice(e, dev);
     KV_CHECK_EQ(e.home, dev) << "key " << e.key << " lives on another GPU than this rank's";
-    Prepared& P = groups[e.dtype];
+    bool staged = false;
+    for (auto& s : op.srcs) staged = staged || !arena_copy(s);
+    for (auto& o : op.outs) staged = staged || !arena_copy(o);
+    auto& bk = bucket_of[e.dtype];
+    const size_t kbytes = e.size * DTypeSize(e.dtype);
+    if (staged) {
+      if (bk.second > 0 && bk.second + kbytes > kBucketBytes) {
+        ++bk.first;
+        bk.second = 0;
+      }
+      bk.second += kbytes;
+    }
+    Prepared& P = groups[std::make_pair(e.dtype, bk.first)];
     DenseOp dop = op;
     for (size_t i = 0; i < dop.srcs.size(); ++i) {
       KV_CHECK_EQ(dop.srcs[i].Size(), e.size) << "push: shape mismatch for key " << e.key;
@@ -69,7 +91,7 @@ void KVStore::PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::ve
   for (auto& kv : groups) {
     Prepared& P = kv.second;
     P.opt_kind = opt_kind;
-    P.dtype = kv.first;
+    P.dtype = kv.first.first;
     P.is_push = is_push;
     P.group = true;
     P.owners = {dev};
@@ -136,7 +158,23 @@ std::shared_ptr<Plan> KVStore::GetPlanGroup(const std::vector<DenseOp>& ops, int
   if (it != plans_.end()) return it->second;
   if (plans_.size() > 256) plans_.clear();
 
-  // ---- collective: everybody's operand offsets inside its IPC arena
+  // ---- collective: first make sure every rank plans the SAME launch (same keys, same cut into
+  // buckets) -- a mismatch would otherwise pair up all-gathers of different sizes or dead-lock the
+  // kernels' barriers
+  {
+    uint64_t kh = 0x9b;
+    for (auto& op : ops) kh = Mix(kh, static_cast<uint64_t>(op.e->key));
+    const std::vector<int64_t> hdr = g->AllGatherI64(
+        {static_cast<int64_t>(ops.size()), static_cast<int64_t>(kh >> 1), static_cast<int64_t>(opt_kind)});
+    for (int r = 0; r < W; ++r) {
+      KV_CHECK(hdr[3 * r] == hdr[3 * R] && hdr[3 * r + 1] == hdr[3 * R + 1] && hdr[3 * r + 2] == hdr[3 * R + 2])
+          << "one-rank-per-GPU store: rank " << r << " issued a different call than rank " << R << " ("
+          << hdr[3 * r] << " vs " << hdr[3 * R] << " keys in this launch). Every rank must push / pull "
+          << "the same keys in the same order, with the same kind of arrays (library arrays vs foreign "
+          << "/ host memory decides how a call is cut into buckets)";
+    }
+  }
+  // ---- everybody's operand offsets inside its IPC arena
   std::vector<int64_t> mine(ops.size() * kFields, -1);
   for (size_t k = 0; k < ops.size(); ++k) {
     const DenseOp& op = ops[k];

@@ -201,6 +201,7 @@ void LaunchDequantizeSum2Bit(const uint32_t* const* d_compressed /* device array
 // ---- TMA bulk-copy packing of many small arrays into one fusion buffer (pack_kernels.cu) ----
 constexpr int kPackTileBytes = 16384;  // one TMA bulk copy; items passed to the kernel are <= this
 struct PackItem { const void* src; void* dst; uint64_t bytes; };
-void LaunchPackBulk(const PackItem* d_items, int n_items, uint64_t max_bytes, cudaStream_t stream);
+void LaunchPackBulk(const PackItem* d_items, int n_items, uint64_t max_bytes, cudaStream_t stream,
+                    int max_ctas = 0);
 
 }  // namespace b200kv

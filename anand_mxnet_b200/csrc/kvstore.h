@@ -103,6 +103,11 @@ struct PackList {
   size_t bytes_items = 0;
   int n_items = 0;
   uint64_t total_bytes = 0;
+  // engine lane the launch runs on: the compute lane for device-to-device lists; lists with a
+  // pinned-host side run on the H2D / D2H copy lane, so a bucket's transfer in, its fused kernel
+  // and the previous bucket's transfer out overlap (ordering comes from the arrays' dependencies)
+  int lane = -1;
+  bool host_io = false;
   ~PackList();
 };
 

@@ -128,13 +128,17 @@ __global__ void __launch_bounds__(kPackThreads) pack_bulk_kernel(const PackItem*
 
 }  // namespace
 
-void LaunchPackBulk(const PackItem* d_items, int n_items, uint64_t, cudaStream_t stream) {
+void LaunchPackBulk(const PackItem* d_items, int n_items, uint64_t, cudaStream_t stream, int max_ctas) {
   if (n_items <= 0) return;
   const int smem = kStages * kPackTileBytes;
   // per-device attribute: set on every launch (cheap) so multi-GPU processes are covered
   KV_CUDA(cudaFuncSetAttribute(pack_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   // 3 CTAs of 64 KB fit an SM; enough CTAs to cover all 148 SMs, each looping over its tiles
-  const int grid = n_items < 148 * 3 ? n_items : 148 * 3;
+  // (PCIe-bound lists get a small grid: 64 KB in flight per CTA already covers the link's
+  // bandwidth-delay product many times over, and the SMs stay free for the fused kernel that runs
+  // beside the transfer)
+  const int cap = max_ctas > 0 ? max_ctas : 148 * 3;
+  const int grid = n_items < cap ? n_items : cap;
   pack_bulk_kernel<<<grid, kPackThreads, smem, stream>>>(d_items, n_items);
   KV_CUDA(cudaGetLastError());
 }

@@ -350,7 +350,7 @@ def run_single_gpu(args):
     peaks, peak_src = measured_peaks()
     achieved = alg / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": _ncu_traffic(), "kernel":
+                "frac": achieved / peaks["hbm_gbs"], "traffic": _ncu_traffic(args.workload), "kernel":
                 "dense_fused_kernel<float,1,SGD>" if WORKLOADS[args.workload]["opt"] == "sgd"
                 else "dense_fused_kernel<float,1,Adam>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_kernel}
@@ -424,8 +424,11 @@ def run_single_gpu(args):
     print(json.dumps(line))
 
 
-def _ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def _ncu_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of THIS workload
+    (profiles/r01_dense_fused_traffic.json holds the ResNet-50 SGD-momentum launch), else None."""
+    if workload != "resnet50_sgd":
+        return None
     p = os.path.join(ROOT, "profiles", "r01_dense_fused_traffic.json")
     if os.path.exists(p):
         try:
