@@ -34,13 +34,17 @@ void KVStore::PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::ve
   const int dev = g->dev();
   const bool is_push = opt_kind != kOptPullOnly;
   // Launch groups by (dtype, bucket). Operands outside this rank's arena (host memory, a
-  // framework's own tensors) are staged; such a call is cut into buckets of ~16 MB of key bytes so
-  // that the transfer in of bucket b+1 (H2D lane), the fused kernel of bucket b (compute lane) and
-  // the transfer out of bucket b-1 (D2H lane) overlap. Calls whose operands all live in the arena
-  // stay ONE launch.
+  // framework's own tensors) are staged by TMA pack launches on the copy lanes. With
+  // B200KV_GROUP_BUCKET_MB=n such a call is cut into buckets of ~n MB of key bytes so that the
+  // transfer in of bucket b+1, the fused kernel of bucket b and the transfer out of bucket b-1
+  // overlap. Off by default: measured on B200 (profiles/r01_run10_e2e_pipeline.txt) the link
+  // sustains ~40 GB/s per direction when both directions are busy, so the (B+1)-stage pipeline
+  // (3.7 ms at 2 ranks, 16 MB buckets) does not beat one launch per direction (3.5 ms) -- every
+  // bucket also costs a cross-rank barrier. Calls whose operands all live in the arena are always
+  // ONE launch.
   static const size_t kBucketBytes = []() {
     const char* z = std::getenv("B200KV_GROUP_BUCKET_MB");
-    return static_cast<size_t>(z ? std::max(1, std::atoi(z)) : 16) << 20;
+    return z ? static_cast<size_t>(std::max(1, std::atoi(z))) << 20 : ~static_cast<size_t>(0) >> 1;
   }();
   std::map<std::pair<int, int>, Prepared> groups;
   std::map<int, std::pair<int, size_t>> bucket_of;  // dtype -> (bucket, bytes in it)
