@@ -13,6 +13,9 @@
 
 #include "engine.h"
 #include "group.h"
+#include <cstdio>
+#include <cstring>
+
 #include "kvstore.h"
 #include "ndarray.h"
 #include "ops.h"
@@ -280,6 +283,98 @@ int MXNDArrayGetAuxNDArray(NDArrayHandle handle, uint32_t i, NDArrayHandle* out)
 int MXNDArrayGetDataNDArray(NDArrayHandle handle, NDArrayHandle* out) {
   API_BEGIN();
   *out = new NDArray(ND(handle).DataView());
+  API_END();
+}
+
+// ---- serialization (python pickling of optimizer states, mx.nd.save / load)
+thread_local std::string g_raw_bytes;
+thread_local std::vector<std::string> g_name_store;
+thread_local std::vector<const char*> g_name_ptrs;
+
+int MXNDArraySaveRawBytes(NDArrayHandle handle, size_t* out_size, const char** out_buf) {
+  API_BEGIN();
+  KVStore::FlushAll();
+  g_raw_bytes.clear();
+  ND(handle).SaveRaw(&g_raw_bytes);
+  *out_size = g_raw_bytes.size();
+  *out_buf = g_raw_bytes.data();
+  API_END();
+}
+
+int MXNDArrayLoadFromRawBytes(const void* buf, size_t size, NDArrayHandle* out) {
+  API_BEGIN();
+  *out = new NDArray(NDArray::LoadRaw(static_cast<const char*>(buf), size, nullptr));
+  API_END();
+}
+
+// list file: uint64 0x112, uint64 0, vector<NDArray>, vector<string> (ndarray.cc:1829-1857; dmlc
+// serializes a vector as uint64 count + elements, a string as uint64 length + bytes)
+int MXNDArraySave(const char* fname, uint32_t num_args, NDArrayHandle* args, const char** keys) {
+  API_BEGIN();
+  KVStore::FlushAll();
+  std::string o;
+  auto put64 = [&](uint64_t v) { o.append(reinterpret_cast<const char*>(&v), 8); };
+  put64(0x112);
+  put64(0);
+  put64(num_args);
+  for (uint32_t i = 0; i < num_args; ++i) ND(args[i]).SaveRaw(&o);
+  put64(keys != nullptr ? num_args : 0);
+  if (keys != nullptr) {
+    for (uint32_t i = 0; i < num_args; ++i) {
+      put64(std::strlen(keys[i]));
+      o.append(keys[i]);
+    }
+  }
+  FILE* f = std::fopen(fname, "wb");
+  KV_CHECK(f != nullptr) << "cannot open " << fname << " for writing";
+  const size_t w = std::fwrite(o.data(), 1, o.size(), f);
+  std::fclose(f);
+  KV_CHECK_EQ(w, o.size()) << "short write to " << fname;
+  API_END();
+}
+
+int MXNDArrayLoad(const char* fname, uint32_t* out_size, NDArrayHandle** out_arr, uint32_t* out_name_size,
+                  const char*** out_names) {
+  API_BEGIN();
+  FILE* f = std::fopen(fname, "rb");
+  KV_CHECK(f != nullptr) << "cannot open " << fname;
+  std::string buf;
+  char tmp[1 << 16];
+  size_t n;
+  while ((n = std::fread(tmp, 1, sizeof(tmp), f)) > 0) buf.append(tmp, n);
+  std::fclose(f);
+  size_t pos = 0;
+  auto get64 = [&]() {
+    KV_CHECK(pos + 8 <= buf.size()) << "Invalid NDArray file format";
+    uint64_t v;
+    std::memcpy(&v, buf.data() + pos, 8);
+    pos += 8;
+    return v;
+  };
+  KV_CHECK_EQ(get64(), 0x112u) << "Invalid NDArray file format";
+  get64();
+  const uint64_t cnt = get64();
+  g_out_handles.clear();
+  for (uint64_t i = 0; i < cnt; ++i) {
+    size_t used = 0;
+    g_out_handles.push_back(new NDArray(NDArray::LoadRaw(buf.data() + pos, buf.size() - pos, &used)));
+    pos += used;
+  }
+  const uint64_t nn = get64();
+  KV_CHECK(nn == 0 || nn == cnt) << "Invalid NDArray file format";
+  g_name_store.clear();
+  g_name_ptrs.clear();
+  for (uint64_t i = 0; i < nn; ++i) {
+    const uint64_t len = get64();
+    KV_CHECK(pos + len <= buf.size()) << "Invalid NDArray file format";
+    g_name_store.emplace_back(buf.data() + pos, len);
+    pos += len;
+  }
+  for (auto& sname : g_name_store) g_name_ptrs.push_back(sname.c_str());
+  *out_size = static_cast<uint32_t>(cnt);
+  *out_arr = g_out_handles.data();
+  *out_name_size = static_cast<uint32_t>(nn);
+  *out_names = g_name_ptrs.data();
   API_END();
 }
 

@@ -254,4 +254,134 @@ void CopyFromTo(const NDArray& from, const NDArray& to) {
           static_cast<size_t>(nnr) * sizeof(int64_t));
 }
 
+// ---------------------------------------------------------------------------------------------
+// serialization
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr uint32_t kV1Magic = 0xF993fac8, kV2Magic = 0xF993fac9, kV3Magic = 0xF993faca;
+
+template <typename T> void Put(std::string* o, T v) { o->append(reinterpret_cast<const char*>(&v), sizeof(T)); }
+void PutShape(std::string* o, const std::vector<int64_t>& s) {   // Tuple::Save (tuple.h:704-713)
+  Put<int32_t>(o, static_cast<int32_t>(s.size()));
+  for (int64_t d : s) Put<int64_t>(o, d);
+}
+struct Reader {
+  const char* p;
+  size_t left;
+  template <typename T> T Get() {
+    KV_CHECK(left >= sizeof(T)) << "Invalid NDArray file format";
+    T v;
+    std::memcpy(&v, p, sizeof(T));
+    p += sizeof(T);
+    left -= sizeof(T);
+    return v;
+  }
+  std::vector<int64_t> Shape() {
+    const int32_t nd = Get<int32_t>();
+    KV_CHECK(nd >= 0 && nd <= 32) << "Invalid NDArray file format";
+    std::vector<int64_t> s(nd);
+    for (auto& d : s) d = Get<int64_t>();
+    return s;
+  }
+  const char* Take(size_t n) {
+    KV_CHECK(left >= n) << "Invalid NDArray file format";
+    const char* q = p;
+    p += n;
+    left -= n;
+    return q;
+  }
+};
+
+// device (or pinned host) bytes -> host string, through the copy lanes
+void AppendBytes(std::string* o, const void* src, Context ctx, Var* var, size_t bytes) {
+  if (bytes == 0) return;
+  const size_t at = o->size();
+  o->resize(at + bytes);
+  Var dst;
+  RawCopy(&(*o)[at], Context::CPU(), &dst, src, ctx, var, bytes);
+  Engine::Get()->WaitToRead(dst);
+}
+}  // namespace
+
+void NDArray::SaveRaw(std::string* o) const {
+  Put<uint32_t>(o, kV2Magic);
+  Put<int32_t>(o, is_none() ? 0 : stype_);
+  const bool rsp = !is_none() && stype_ == kRowSparseStorage;
+  if (rsp) {
+    std::vector<int64_t> ss = shape();
+    ss[0] = nnr();
+    PutShape(o, ss);
+  }
+  PutShape(o, is_none() ? std::vector<int64_t>() : shape());
+  if (is_none()) return;
+  // context: host-side arrays are plain cpu(0) to the outside (their pinning is an implementation detail)
+  Put<int32_t>(o, st_->ctx.is_gpu() ? kGPU : kCPU);
+  Put<int32_t>(o, st_->ctx.is_gpu() ? st_->ctx.dev_id : 0);
+  Put<int32_t>(o, dtype_);
+  if (rsp) {
+    Put<int32_t>(o, kInt64);
+    PutShape(o, {nnr()});
+  }
+  const size_t data_bytes = rsp ? static_cast<size_t>(nnr()) * RowLength() * DTypeSize(dtype_) : ByteSize();
+  if (data_bytes) AppendBytes(o, data(), st_->ctx, &st_->var, data_bytes);
+  if (rsp && nnr() > 0) AppendBytes(o, row_ids(), st_->ctx, &st_->var, static_cast<size_t>(nnr()) * sizeof(int64_t));
+}
+
+NDArray NDArray::LoadRaw(const char* buf, size_t size, size_t* consumed) {
+  Reader r{buf, size};
+  const uint32_t magic = r.Get<uint32_t>();
+  KV_CHECK(magic != kV3Magic) << "ndarray was saved in np shape semantics, which this path does not use";
+  int32_t stype = kDefaultStorage;
+  std::vector<int64_t> sshape, shape;
+  if (magic == kV2Magic) {
+    stype = r.Get<int32_t>();
+    KV_CHECK(stype == kDefaultStorage || stype == kRowSparseStorage) << "unsupported storage type " << stype;
+    if (stype == kRowSparseStorage) sshape = r.Shape();
+    shape = r.Shape();
+  } else if (magic == kV1Magic) {
+    shape = r.Shape();
+  } else {
+    // legacy TShape: the word just read is ndim, dims follow as uint32 (ndarray.cc:1672-1687)
+    KV_CHECK(magic <= 32) << "Invalid NDArray file format";
+    shape.resize(magic);
+    for (auto& d : shape) d = r.Get<uint32_t>();
+  }
+  NDArray out;
+  if (shape.empty()) {
+    if (consumed) *consumed = size - r.left;
+    return out;
+  }
+  const int32_t dev_type = r.Get<int32_t>(), dev_id = r.Get<int32_t>();
+  const int32_t dtype = r.Get<int32_t>();
+  int64_t nnr = 0;
+  if (stype == kRowSparseStorage) {
+    const int32_t aux_type = r.Get<int32_t>();
+    KV_CHECK_EQ(aux_type, kInt64) << "row_sparse index type";
+    const std::vector<int64_t> as = r.Shape();
+    KV_CHECK(as.size() == 1 && !sshape.empty() && sshape[0] == as[0]) << "Invalid NDArray file format";
+    nnr = as[0];
+  }
+  Context ctx = Context::CPU();
+  if (dev_type == kGPU && dev_id < Engine::Get()->NumDevices()) ctx = Context::GPU(dev_id);
+  auto fill = [&](void* dst, Var* var, size_t bytes) {
+    if (bytes == 0) return;
+    const char* src = r.Take(bytes);
+    RawCopy(dst, ctx, var, src, Context::CPU(), nullptr, bytes);
+    Engine::Get()->WaitToRead(*var);  // `buf` belongs to the caller
+  };
+  if (stype == kDefaultStorage) {
+    out = NDArray(shape, ctx, dtype);
+    fill(out.data(), out.var(), out.ByteSize());
+  } else {
+    out = NDArray::RowSparse(shape, ctx, dtype);
+    if (nnr > 0) {
+      out.CheckAndAllocRows(nnr);
+      fill(out.data(), out.var(), static_cast<size_t>(nnr) * out.RowLength() * DTypeSize(dtype));
+      fill(out.row_ids(), out.var(), static_cast<size_t>(nnr) * sizeof(int64_t));
+    }
+  }
+  if (consumed) *consumed = size - r.left;
+  return out;
+}
+
 }  // namespace b200kv

@@ -5,6 +5,7 @@
 #pragma once
 #include <functional>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "common.h"
@@ -103,6 +104,12 @@ class NDArray {
   NDArray Reshaped(const std::vector<int64_t>& shape) const;
   // rows [begin, end) of the first axis, sharing storage (NDArray::Slice, src/ndarray/ndarray.cc)
   NDArray Slice(int64_t begin, int64_t end) const;
+
+  // NDArray::Save / Load (src/ndarray/ndarray.cc:1596-1670, 1672-1827): the V2 binary format --
+  // magic 0xF993fac9, stype, [storage shape], shape (int32 ndim + int64 dims), context, type
+  // flag, [aux type + shape], data, [aux data]. Load also accepts the V1 / legacy layouts.
+  void SaveRaw(std::string* out) const;
+  static NDArray LoadRaw(const char* buf, size_t size, size_t* consumed);
 
   // Deep copy into a fresh array on ctx (NDArray::Copy, src/ndarray/ndarray.cc:...)
   NDArray Copy(Context ctx) const;

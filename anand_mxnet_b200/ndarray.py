@@ -277,17 +277,30 @@ class NDArray(object):
         return '\n%s\n<%s %s @%s>' % (str(self.asnumpy()), self.__class__.__name__,
                                       'x'.join(str(x) for x in self.shape), self.context)
 
-    # pickling (optimizer-state checkpoints, optimizer.py:2143-2161)
+    # pickling (optimizer-state checkpoints, optimizer.py:2143-2161): the state is the array's
+    # NDArray::Save bytes under the key 'handle', exactly as python/mxnet/ndarray/ndarray.py does
     def __getstate__(self):
-        return {'np': self.asnumpy(), 'ctx': (self.context.device_type, self.context.device_id),
-                'dtype': self.dtype if isinstance(self.dtype, str) else np.dtype(self.dtype).name}
+        length = ctypes.c_size_t()
+        cptr = ctypes.POINTER(ctypes.c_char)()
+        check_call(_LIB.MXNDArraySaveRawBytes(self.handle, ctypes.byref(length), ctypes.byref(cptr)))
+        return {'handle': bytearray(ctypes.string_at(cptr, length.value))}
 
     def __setstate__(self, state):
-        a = array(state['np'], Context(*state['ctx']), state['dtype'])
-        self.handle = a.handle
-        self._hv = a.handle.value
+        if 'handle' in state:
+            buf = state['handle']
+            raw = (ctypes.c_char * len(buf)).from_buffer(buf if isinstance(buf, bytearray) else bytearray(buf))
+            h = NDArrayHandle()
+            check_call(_LIB.MXNDArrayLoadFromRawBytes(raw, ctypes.c_size_t(len(buf)), ctypes.byref(h)))
+        else:  # states written by earlier versions of this package
+            a = array(state['np'], Context(*state['ctx']), state['dtype'])
+            h, a.handle = a.handle, ctypes.c_void_p(None)
+        self.handle = h
+        self._hv = h.value
         self._keepalive = None
-        a.handle = ctypes.c_void_p(None)
+        st = ctypes.c_int()
+        check_call(_LIB.MXNDArrayGetStorageType(h, ctypes.byref(st)))
+        if st.value == 1 and type(self) is NDArray:
+            self.__class__ = RowSparseNDArray
 
 
 class RowSparseNDArray(NDArray):
@@ -432,6 +445,32 @@ class _Sparse(object):
 
 
 sparse = _Sparse()
+
+
+def save(fname, data):
+    """mx.nd.save (python/mxnet/ndarray/utils.py:222-273): a list of arrays or a dict name -> array"""
+    if isinstance(data, NDArray):
+        data = [data]
+    if isinstance(data, dict):
+        keys, arrs = list(data.keys()), list(data.values())
+        ckeys = c_str_array(keys)
+    else:
+        arrs, ckeys = list(data), None
+    handles = (ctypes.c_void_p * len(arrs))(*[a.handle.value for a in arrs])
+    check_call(_LIB.MXNDArraySave(fname.encode(), ctypes.c_uint(len(arrs)), handles, ckeys))
+
+
+def load(fname):
+    """mx.nd.load (utils.py:149-182): list, or dict when the file holds names"""
+    n, nn = ctypes.c_uint(), ctypes.c_uint()
+    harr = ctypes.POINTER(ctypes.c_void_p)()
+    names = ctypes.POINTER(ctypes.c_char_p)()
+    check_call(_LIB.MXNDArrayLoad(fname.encode(), ctypes.byref(n), ctypes.byref(harr), ctypes.byref(nn),
+                                  ctypes.byref(names)))
+    arrs = [_wrap(NDArrayHandle(harr[i])) for i in range(n.value)]
+    if nn.value == 0:
+        return arrs
+    return {names[i].decode(): arrs[i] for i in range(n.value)}
 
 
 def waitall():

@@ -88,6 +88,14 @@ B200KV_DLL int MXNDArrayGetAuxType(NDArrayHandle handle, uint32_t i, int* out_ty
 B200KV_DLL int MXNDArrayGetAuxNDArray(NDArrayHandle handle, uint32_t i, NDArrayHandle* out); /* :1070 */
 B200KV_DLL int MXNDArrayGetDataNDArray(NDArrayHandle handle, NDArrayHandle* out);     /* :1090 */
 B200KV_DLL int MXNDArrayGetContext(NDArrayHandle handle, int* out_dev_type, int* out_dev_id); /* :1099 */
+/* NDArray::Save binary format (src/ndarray/ndarray.cc:1596-1857): what python pickles of NDArrays --
+ * hence Updater.get_states() optimizer checkpoints -- and mx.nd.save files contain */
+B200KV_DLL int MXNDArrayLoadFromRawBytes(const void* buf, size_t size, NDArrayHandle* out);   /* :701 */
+B200KV_DLL int MXNDArraySaveRawBytes(NDArrayHandle handle, size_t* out_size, const char** out_buf); /* :711 */
+B200KV_DLL int MXNDArraySave(const char* fname, uint32_t num_args, NDArrayHandle* args,
+                             const char** keys);                                               /* :722 */
+B200KV_DLL int MXNDArrayLoad(const char* fname, uint32_t* out_size, NDArrayHandle** out_arr,
+                             uint32_t* out_name_size, const char*** out_names);                /* :735 */
 /* view of rows [slice_begin, slice_end) of the first axis, sharing memory (LARS slices its lr array) */
 B200KV_DLL int MXNDArraySlice(NDArrayHandle handle, uint32_t slice_begin, uint32_t slice_end,
                               NDArrayHandle* out);                                      /* :849 */

@@ -134,6 +134,23 @@ def main():
         d["std_sgdmom_%s_empty_out" % tag] = np.stack([w2, m2])
     np.savez_compressed(os.path.join(GOLD, "rowsparse_std_updates.npz"), **d)
 
+    # ---- NDArray::Save bytes (8f-f4: what pickled optimizer states / mx.nd.save files hold) ----
+    rng4 = np.random.default_rng(0xB200 + 4)
+    d = {}
+    a = u(rng4, 3, 5)
+    d["dense_f32_gpu0_in"] = a
+    d["dense_f32_gpu0_bytes"] = np.frombuffer(r.ndarray_save_bytes(a.shape, a, ctx=(2, 0)), np.uint8)
+    h = u(rng4, 7).astype(np.float16)
+    d["dense_f16_cpu_in"] = h
+    d["dense_f16_cpu_bytes"] = np.frombuffer(r.ndarray_save_bytes(h.shape, h, ctx=(1, 0)), np.uint8)
+    i64 = rng4.integers(-5, 5, (2, 2, 2)).astype(np.int64)
+    d["dense_i64_cpu_in"] = i64
+    d["dense_i64_cpu_bytes"] = np.frombuffer(r.ndarray_save_bytes(i64.shape, i64, ctx=(1, 0)), np.uint8)
+    rows, idx = u(rng4, 2, 4), np.array([1, 4], np.int64)
+    d["rsp_f32_gpu0_rows"], d["rsp_f32_gpu0_idx"] = rows, idx
+    d["rsp_f32_gpu0_bytes"] = np.frombuffer(r.ndarray_save_bytes((6, 4), rows, ctx=(2, 0), idx=idx), np.uint8)
+    np.savez_compressed(os.path.join(GOLD, "ndarray_raw_bytes.npz"), **d)
+
     # ---- 2-bit compression ----
     g = u(rng, 1003)
     res = np.zeros_like(g)

@@ -454,6 +454,29 @@ class Ref(object):
           self._clip(clip), beta1, beta2, lr, wd, eps, rescale)
         return w
 
+    def ndarray_save(self, a, ctx=(1, 0), idx=None):
+        """bytes of NDArray::Save for a dense array `a` (or a row_sparse one: a = stored rows, idx =
+        their ids, shape0 = table height via a.shape0 attribute of the call) -- see ref_ops.cc"""
+        raise NotImplementedError
+
+    def ndarray_save_bytes(self, shape, data, ctx=(1, 0), idx=None):
+        data = np.ascontiguousarray(data)
+        shp = (ctypes.c_int64 * len(shape))(*shape)
+        f = self.lib.mxref_ndarray_save
+        f.restype = ctypes.c_size_t
+        f.argtypes = [_I, _P, _I, _I, _I, _P, ctypes.c_size_t, ctypes.c_int64, _P, _P, ctypes.c_size_t]
+        nnr = -1 if idx is None else len(idx)
+        ip = None
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, dtype=np.int64)
+            ip = _ptr(idx)
+        cap = 256 + data.nbytes + (0 if idx is None else idx.nbytes)
+        out = ctypes.create_string_buffer(cap)
+        n = f(len(shape), shp, ctx[0], ctx[1], self._DT[data.dtype], _ptr(data), data.nbytes, nnr, ip,
+              out, cap)
+        assert n <= cap
+        return out.raw[:n]
+
     def has_ops(self):
         return hasattr(self.lib, 'mxref_op_invoke')
 

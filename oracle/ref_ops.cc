@@ -39,6 +39,7 @@
 #include <vector>
 #include <omp.h>
 #include <dmlc/logging.h>
+#include <dmlc/memory_io.h>
 #include <mshadow/tensor.h>
 #include <nnvm/op.h>
 #include "operator/optimizer_op-inl.h"
@@ -250,6 +251,43 @@ void mxref_sgd_std_rsp_update(int64_t num_rows, int64_t row_len, float* w, const
     op::SGDDnsRspKernel<kWriteInplace, cpu>::Map(static_cast<int>(r), row_len, w, w, gidx, gval, clip, lr,
                                                  0.f, rescale);
   }
+}
+
+// NDArray::Save (src/ndarray/ndarray.cc:1596-1670) for a CPU-resident value, field by field in the
+// reference's order; the sub-structures are written by the reference's own TShape::Save
+// (include/mxnet/tuple.h:704-713) and Context::Save (include/mxnet/base.h:157-160). NDArray itself
+// needs libmxnet (storage, engine), hence the restated composition. nnr < 0: dense.
+// Returns the number of bytes written (or needed, when `cap` is too small).
+size_t mxref_ndarray_save(int ndim, const int64_t* shape, int dev_type, int dev_id, int type_flag,
+                          const void* data, size_t data_bytes, int64_t nnr, const int64_t* idx,
+                          char* out, size_t cap) {
+  std::string buf;
+  dmlc::MemoryStringStream strm(&buf);
+  const uint32_t magic = 0xF993fac9;  // NDARRAY_V2_MAGIC (ndarray.cc:1590)
+  strm.Write(&magic, sizeof(magic));
+  int32_t stype = nnr < 0 ? kDefaultStorage : kRowSparseStorage;
+  strm.Write(&stype, sizeof(stype));
+  mxnet::TShape tshape(shape, shape + ndim);
+  if (nnr >= 0) {
+    mxnet::TShape sshape = tshape;
+    sshape[0] = nnr;
+    sshape.Save(&strm);
+  }
+  tshape.Save(&strm);
+  Context ctx = Context::Create(static_cast<Context::DeviceType>(dev_type), dev_id);
+  ctx.Save(&strm);
+  int32_t tf = type_flag;
+  strm.Write(&tf, sizeof(tf));
+  if (nnr >= 0) {
+    int32_t aux = mshadow::kInt64;
+    strm.Write(&aux, sizeof(aux));
+    mxnet::TShape ashape(1, nnr);
+    ashape.Save(&strm);
+  }
+  strm.Write(data, data_bytes);
+  if (nnr > 0) strm.Write(idx, static_cast<size_t>(nnr) * sizeof(int64_t));
+  if (buf.size() <= cap) std::memcpy(out, buf.data(), buf.size());
+  return buf.size();
 }
 
 void mxref_set_omp_threads(int n) { g_omp_threads = n < 1 ? 1 : n; }
