@@ -340,9 +340,6 @@ class RowSparseNDArray(NDArray):
             return _invoke('_copyto', [self], out=out)
         return _invoke('_copyto', [self], out=other)
 
-    def __getstate__(self):
-        raise MXNetError('pickling row_sparse arrays is not supported')
-
 
 def _wrap(handle):
     s = ctypes.c_int()
