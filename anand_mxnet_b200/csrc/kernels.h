@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <climits>
 
 namespace b200kv {
 
@@ -129,7 +130,8 @@ struct RspSources {
 size_t RspMergeWorkspaceBytes(int64_t total_ids);
 void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_t* out_idx,
                     float* out_val, int64_t* d_nnr, void* workspace, size_t workspace_bytes,
-                    cudaStream_t stream, const RspUpdateLaunch* fused_update = nullptr);
+                    cudaStream_t stream, const RspUpdateLaunch* fused_update = nullptr,
+                    int64_t lo = 0, int64_t hi = INT64_MAX);  // [lo, hi): only ids of this row range
 
 // row_sparse_pull for a batch of (row_ids, out) pairs that share an owner GPU
 // (kvstore_local.h:263-283 + kvstore_utils.cu:43-97 Unique + sparse_retain-inl.h:121-150,262-323):
@@ -142,6 +144,9 @@ struct RetainItem {
   const int64_t* src_idx; const float* src_val; int64_t src_nnr; int src_dense_rows;
   int64_t row_len;
   int64_t* out_idx; float* out_val;
+  // table sharded by row range over several GPUs: device array of "virtual bases"
+  // (shard base - first_row*row_len, so that vbase[id / rows_per_shard] + id*row_len is row id)
+  const float* const* shard_vbase; int64_t rows_per_shard;
 };
 size_t RetainBatchWorkspaceBytes(int nitems, int64_t total_ids);
 // d_items: device copy of `nitems` RetainItem (inside the workspace, filled by the callee from

@@ -62,6 +62,15 @@ struct KeyEntry {
   std::map<int, DevState> dev;
   NDArray merged;       // reduce target of the updater-callback path (on `home`)
   NDArray rsp;          // row_sparse stored value (on `home` or host)
+  // Row-range sharding of a row_sparse table whose stored value holds every row and whose
+  // optimizer runs fused on the store (the embedding-training case): GPU rsp_devs[j]
+  // owns rows [j*rsp_rows_per, (j+1)*rsp_rows_per) of the weight and of the optimizer state.
+  // While sharded, `rsp` is stale; UnshardRsp() folds everything back onto `home`.
+  std::vector<int> rsp_devs;
+  std::vector<NDArray> rsp_shards;          // dense [rows_j, row_len]
+  std::vector<DevState> rsp_shard_state;    // s1 / s2 per shard
+  int64_t rsp_rows_per = 0;
+  std::map<int, NDArray> rsp_vbase;         // per launching GPU: device table of shard virtual bases
   std::vector<NDArray> stage_src, stage_out;  // device staging of host-resident values / outs
   // 2-bit gradient compression: per source slot residual (fp32) and compressed words, both on the
   // source's GPU; decoded sum on `home`
@@ -216,6 +225,11 @@ class KVStore {
 
   // row_sparse machinery (rowsparse.cc)
   void PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs);
+  bool PushRowSparseSharded(KeyEntry& e, const std::vector<NDArray>& srcs, const std::vector<int>& parts,
+                            RspUpdateLaunch U);
+  void ShardRsp(KeyEntry& e, const std::vector<int>& devs);
+  void UnshardRsp(KeyEntry& e);
+  const float* const* RspShardTable(KeyEntry& e, int dev);
   void PullRowSparseGroup(int home, const std::vector<size_t>& which, const std::vector<int>& keys,
                           const std::vector<NDArray>& outs, const std::vector<NDArray>& row_ids);
 

@@ -547,6 +547,7 @@ void KVStore::PullImpl(const std::vector<int>& keys, const std::vector<NDArray>&
       cacheable_call = false;
       NDArray local;
       if (e.stype == kRowSparseStorage) {
+        UnshardRsp(e);
         local = e.rsp;
       } else {
         const int dev = e.striped ? devset_[0] : (e.home >= 0 ? e.home : (devset_.empty() ? 0 : devset_[0]));
@@ -902,6 +903,7 @@ NDArray KVStore::GetOptimizerState(int key, int state_id) {
 
 void KVStore::SetOptimizerState(int key, int state_id, const NDArray& v) {
   KeyEntry& e = Entry(key);
+  if (!e.rsp_devs.empty()) UnshardRsp(e);
   int dev = e.striped ? devset_[0] : e.home;
   if (e.striped) EnsureWhole(e, dev);
   if (dev < 0) {

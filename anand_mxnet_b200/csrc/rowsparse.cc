@@ -115,7 +115,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
   const bool fused = on_store && opt_.lazy_update;
   RspUpdateLaunch U;
   if (on_store) {
-    KV_CHECK_EQ(e.rsp.nnr(), e.shape[0])
+    KV_CHECK(!e.rsp_devs.empty() || e.rsp.nnr() == e.shape[0])
         << "key " << e.key << ": the stored row_sparse weight must hold every row for sparse "
         << "optimizer updates (initialise it from a dense weight, as gluon does)";
     // Optimizer._update_count, then SGD._update_impl's non-aggregated branch / Adam.update
@@ -130,8 +130,9 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     double wdd = opt_.wd * (wm == opt_.wd_mult.end() ? 1.0 : wm->second);
     DevState& s = e.dev[home];
     const std::vector<int64_t> dshape = e.shape;
+    const bool sharded_now = !e.rsp_devs.empty();   // state then lives with the shards
     auto zero_state = [&](NDArray* a) {
-      if (!a->is_none()) return;
+      if (!a->is_none() || sharded_now) return;
       *a = NDArray(dshape, Context::GPU(home), kFloat32);
       DeviceGuard g(home);
       KV_CUDA(cudaMemsetAsync(a->data(), 0, a->ByteSize(), eng->Stream(home)));
@@ -155,10 +156,21 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     U.wd = ScalarParam(wdd);
     U.rescale = ScalarParam(opt_.rescale);
     U.clip = opt_.clip != 0.0 ? ScalarParam(opt_.clip) : -1.f;
-    U.w = static_cast<float*>(e.rsp.data());
+    U.w = sharded_now ? nullptr : static_cast<float*>(e.rsp.data());
     U.s1 = s.s1.is_none() ? nullptr : static_cast<float*>(s.s1.data());
     U.s2 = s.s2.is_none() ? nullptr : static_cast<float*>(s.s2.data());
     U.row_len = row_len;
+  }
+  if (fused && total > 0 && parts.size() >= 2 && std::getenv("B200KV_RSP_SHARD_OFF") == nullptr) {
+    // sources on several GPUs: every GPU merges and updates its own row range of the table
+    if (PushRowSparseSharded(e, srcs, parts, U)) return;
+  }
+  if (!e.rsp_devs.empty()) UnshardRsp(e);
+  if (fused) {   // (re)bind the update to the whole table on `home`
+    DevState& hs = e.dev[home];
+    U.w = static_cast<float*>(e.rsp.data());
+    U.s1 = hs.s1.is_none() ? nullptr : static_cast<float*>(hs.s1.data());
+    U.s2 = hs.s2.is_none() ? nullptr : static_cast<float*>(hs.s2.data());
   }
   if (total > 0) {
     NDArray d_nnr({1}, Context::GPU(home), kInt64);
@@ -246,20 +258,22 @@ void KVStore::PullRowSparse(const std::vector<int>& keys, const std::vector<NDAr
     KV_CHECK_EQ(e.stype, kRowSparseStorage) << "PullRowSparse expects row_sparse src NDArray";
     const NDArray& out = outs[i];
     if (e.home < 0) e.home = out.on_gpu() ? out.dev() : (row_ids[i].on_gpu() ? row_ids[i].dev() : 0);
-    if (!e.rsp.on_gpu()) e.rsp = e.rsp.Copy(Context::GPU(e.home));
+    const bool sharded = !e.rsp_devs.empty();
+    if (!sharded && !e.rsp.on_gpu()) e.rsp = e.rsp.Copy(Context::GPU(e.home));
     KV_CHECK(out.shape() == e.shape) << "row_sparse_pull: out shape mismatch for key " << e.key;
     KV_CHECK_EQ(out.dtype(), e.dtype) << "row_sparse_pull: out dtype mismatch for key " << e.key;
     if (out.SameStorage(e.rsp)) {
       std::cerr << "The output of row_sparse_pull() on key " << e.key << " refers to the same NDArray "
                 << "as the one stored in KVStore. Consider a new NDArray buffer for the output.\n";
     }
-    if (row_ids[i].Size() == 0 || !e.rsp.storage_initialized()) {
+    if (row_ids[i].Size() == 0 || (!sharded && !e.rsp.storage_initialized())) {
       // FillZerosRspImpl (sparse_retain-inl.h:271-275)
       eng->WaitToWrite(*out.var());
       out.SetNnr(0);
       continue;
     }
-    by_home[e.home].push_back(i);
+    // a sharded table has no single owner: the gather runs where the output lives
+    by_home[sharded && out.on_gpu() ? out.dev() : e.home].push_back(i);
   }
   for (auto& kv : by_home) PullRowSparseGroup(kv.first, kv.second, keys, outs, row_ids);
 }
@@ -295,11 +309,22 @@ void KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
     it.ids_dtype = ids[k].dtype();
     it.n = n;
     it.start = total;
-    it.src_idx = e.rsp.row_ids();
-    it.src_val = static_cast<const float*>(e.rsp.data());
-    it.src_nnr = e.rsp.nnr();
-    it.src_dense_rows = e.rsp.nnr() == e.shape[0] ? 1 : 0;  // sparse_retain-inl.h:290
-    it.row_len = static_cast<int64_t>(e.rsp.RowLength());
+    if (!e.rsp_devs.empty()) {
+      it.src_idx = nullptr;
+      it.src_val = nullptr;
+      it.src_nnr = e.shape[0];
+      it.src_dense_rows = 1;
+      it.shard_vbase = RspShardTable(e, home);
+      it.rows_per_shard = e.rsp_rows_per;
+      it.row_len = static_cast<int64_t>(e.rsp_shards[0].RowLength());
+      for (int d : e.rsp_devs) add_part(d);
+    } else {
+      it.src_idx = e.rsp.row_ids();
+      it.src_val = static_cast<const float*>(e.rsp.data());
+      it.src_nnr = e.rsp.nnr();
+      it.src_dense_rows = e.rsp.nnr() == e.shape[0] ? 1 : 0;  // sparse_retain-inl.h:290
+      it.row_len = static_cast<int64_t>(e.rsp.RowLength());
+    }
     it.out_idx = targets[k].row_ids();
     it.out_val = static_cast<float*>(targets[k].data());
     total += n;
@@ -312,7 +337,12 @@ void KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
   }
   for (int k = 0; k < nitems; ++k) {
     eng->BeginRead(ids[k].dev(), *ids[k].var());
-    eng->BeginRead(home, *Entry(keys[which[k]]).rsp.var());
+    KeyEntry& ek = Entry(keys[which[k]]);
+    if (ek.rsp_devs.empty()) {
+      eng->BeginRead(home, *ek.rsp.var());
+    } else {
+      for (auto& sh : ek.rsp_shards) eng->BeginRead(home, *sh.var());
+    }
     eng->BeginWrite(targets[k].dev(), *targets[k].var());
   }
   if (parts.size() > 1) eng->JoinStreams(parts);
@@ -336,7 +366,12 @@ void KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
   eng->MarkWrite(home, seq, d_off.var());
   eng->MarkWrite(home, seq, ws.var());
   for (int k = 0; k < nitems; ++k) {
-    eng->MarkRead(home, seq, Entry(keys[which[k]]).rsp.var());
+    KeyEntry& ek = Entry(keys[which[k]]);
+    if (ek.rsp_devs.empty()) {
+      eng->MarkRead(home, seq, ek.rsp.var());
+    } else {
+      for (auto& sh : ek.rsp_shards) eng->MarkRead(home, seq, sh.var());
+    }
     eng->MarkRead(ids[k].dev(), ids[k].dev() == home ? seq : eng->Issue(ids[k].dev()), ids[k].var());
     eng->MarkWrite(targets[k].dev(), targets[k].dev() == home ? seq : eng->Issue(targets[k].dev()),
                    targets[k].var());
@@ -447,7 +482,7 @@ void CastStorageCopy(const NDArray& from_in, const NDArray& to) {
   } else {
     target.CheckAndAllocRows(nnr);
     // gather = retain with a source that holds every row
-    RetainItem it;
+    RetainItem it{};
     it.ids = ids.data();
     it.ids_dtype = kInt64;
     it.n = nnr;
@@ -478,6 +513,187 @@ void CastStorageCopy(const NDArray& from_in, const NDArray& to) {
     eng->MarkWrite(dev, sq, rws.var());
   }
   if (!target.SameStorage(to)) CopyFromTo(target, to);
+}
+
+// =================================================================================================
+// row-range sharding of a row_sparse table over the GPUs that push to it
+// =================================================================================================
+void KVStore::ShardRsp(KeyEntry& e, const std::vector<int>& devs) {
+  Engine* eng = Engine::Get();
+  const int64_t rows = e.shape[0];
+  const int64_t row_len = static_cast<int64_t>(e.rsp.RowLength());
+  const int n = static_cast<int>(devs.size());
+  e.rsp_rows_per = (rows + n - 1) / n;
+  e.rsp_devs = devs;
+  e.rsp_shards.assign(n, NDArray());
+  e.rsp_shard_state.assign(n, DevState());
+  e.rsp_vbase.clear();
+  DevState& hs = e.dev[e.home];
+  const size_t rb = static_cast<size_t>(row_len) * sizeof(float);
+  for (int j = 0; j < n; ++j) {
+    const int64_t lo = j * e.rsp_rows_per, hi = std::min<int64_t>(rows, lo + e.rsp_rows_per);
+    const int64_t cnt = std::max<int64_t>(hi - lo, 1);
+    auto take = [&](const NDArray& whole, NDArray* shard) {
+      *shard = NDArray({cnt, row_len}, Context::GPU(devs[j]), kFloat32);
+      if (hi > lo) {
+        RawCopy(shard->data(), shard->ctx(), shard->var(), static_cast<const char*>(whole.data()) + lo * rb,
+                whole.ctx(), whole.var(), static_cast<size_t>(hi - lo) * rb);
+      }
+    };
+    take(e.rsp, &e.rsp_shards[j]);
+    if (!hs.s1.is_none()) take(hs.s1, &e.rsp_shard_state[j].s1);
+    if (!hs.s2.is_none()) take(hs.s2, &e.rsp_shard_state[j].s2);
+  }
+  // the whole-table copies are stale from here on: release them (2 GB for a 1 M x 512 table)
+  eng->WaitToWrite(*e.rsp.var());
+  e.rsp = NDArray::RowSparse(e.shape, Context::GPU(e.home), e.dtype);
+  hs.s1 = NDArray();
+  hs.s2 = NDArray();
+}
+
+void KVStore::UnshardRsp(KeyEntry& e) {
+  if (e.rsp_devs.empty()) return;
+  const int64_t rows = e.shape[0];
+  const int home = e.home;
+  NDArray whole = NDArray::RowSparse(e.shape, Context::GPU(home), e.dtype);
+  whole.CheckAndAllocRows(rows);
+  const int64_t row_len = static_cast<int64_t>(whole.RowLength());
+  const size_t rb = static_cast<size_t>(row_len) * sizeof(float);
+  DevState& hs = e.dev[home];
+  const bool has1 = !e.rsp_shard_state[0].s1.is_none(), has2 = !e.rsp_shard_state[0].s2.is_none();
+  if (has1) hs.s1 = NDArray(e.shape, Context::GPU(home), kFloat32);
+  if (has2) hs.s2 = NDArray(e.shape, Context::GPU(home), kFloat32);
+  for (size_t j = 0; j < e.rsp_devs.size(); ++j) {
+    const int64_t lo = static_cast<int64_t>(j) * e.rsp_rows_per, hi = std::min<int64_t>(rows, lo + e.rsp_rows_per);
+    if (hi <= lo) continue;
+    auto put = [&](const NDArray& shard, void* base, Var* var) {
+      RawCopy(static_cast<char*>(base) + lo * rb, Context::GPU(home), var, shard.data(), shard.ctx(),
+              shard.var(), static_cast<size_t>(hi - lo) * rb);
+    };
+    put(e.rsp_shards[j], whole.data(), whole.var());
+    if (has1) put(e.rsp_shard_state[j].s1, hs.s1.data(), hs.s1.var());
+    if (has2) put(e.rsp_shard_state[j].s2, hs.s2.data(), hs.s2.var());
+  }
+  // row ids 0..rows-1
+  std::vector<int64_t> ids(rows);
+  for (int64_t i = 0; i < rows; ++i) ids[i] = i;
+  RawCopy(whole.row_ids(), whole.ctx(), whole.var(), ids.data(), Context::CPU(), nullptr,
+          ids.size() * sizeof(int64_t));
+  Engine::Get()->WaitToRead(*whole.var());  // `ids` goes out of scope
+  e.rsp = whole;
+  e.rsp_devs.clear();
+  e.rsp_shards.clear();
+  e.rsp_shard_state.clear();
+  e.rsp_vbase.clear();
+  e.rsp_rows_per = 0;
+}
+
+const float* const* KVStore::RspShardTable(KeyEntry& e, int dev) {
+  auto it = e.rsp_vbase.find(dev);
+  if (it == e.rsp_vbase.end()) {
+    const int n = static_cast<int>(e.rsp_devs.size());
+    const int64_t row_len = static_cast<int64_t>(e.rsp_shards[0].RowLength());
+    std::vector<const float*> vb(n);
+    for (int j = 0; j < n; ++j) {
+      vb[j] = static_cast<const float*>(e.rsp_shards[j].data()) - static_cast<int64_t>(j) * e.rsp_rows_per * row_len;
+    }
+    NDArray tbl({n}, Context::GPU(dev), kInt64);
+    RawCopy(tbl.data(), tbl.ctx(), tbl.var(), vb.data(), Context::CPU(), nullptr, n * sizeof(void*));
+    Engine::Get()->WaitToRead(*tbl.var());
+    it = e.rsp_vbase.emplace(dev, tbl).first;
+  }
+  return static_cast<const float* const*>(it->second.data());
+}
+
+bool KVStore::PushRowSparseSharded(KeyEntry& e, const std::vector<NDArray>& srcs,
+                                   const std::vector<int>& parts, RspUpdateLaunch U) {
+  Engine* eng = Engine::Get();
+  const int64_t rows = e.shape[0];
+  if (e.rsp_devs.empty()) {
+    if (e.rsp.nnr() != rows) return false;   // only tables that hold every row are sharded
+    std::vector<int> devs = parts;
+    std::sort(devs.begin(), devs.end());
+    ShardRsp(e, devs);
+  } else {
+    for (int d : parts) {
+      if (std::find(e.rsp_devs.begin(), e.rsp_devs.end(), d) == e.rsp_devs.end()) {
+        UnshardRsp(e);       // pushed from a different GPU set: fold back and shard again
+        return PushRowSparseSharded(e, srcs, parts, U);
+      }
+    }
+  }
+  const std::vector<int>& devs = e.rsp_devs;
+  const int n = static_cast<int>(devs.size());
+  const int64_t row_len = static_cast<int64_t>(e.rsp_shards[0].RowLength());
+  RspSources S;
+  int64_t total = 0;
+  for (auto& s : srcs) {
+    if (!s.storage_initialized()) continue;
+    S.idx[S.nsrc] = s.row_ids();
+    S.val[S.nsrc] = static_cast<const float*>(s.data());
+    S.start[S.nsrc] = total;
+    total += s.nnr();
+    ++S.nsrc;
+  }
+  S.start[S.nsrc] = total;
+  std::vector<int> lanes = devs;
+  for (auto& s : srcs) {
+    if (std::find(lanes.begin(), lanes.end(), s.dev()) == lanes.end()) lanes.push_back(s.dev());
+  }
+  {
+    int en = eng->EnablePeerAccess(lanes);
+    KV_CHECK_EQ(en, static_cast<int>(lanes.size() * (lanes.size() - 1)))
+        << "GPU peer access is not available between all participating devices";
+  }
+  // optimizer state of a shard is created on first use (zeros), like Optimizer.create_state
+  const bool need1 = U.opt == kOptSGD || U.opt == kOptAdam, need2 = U.opt == kOptAdam;
+  for (int j = 0; j < n; ++j) {
+    for (int which = 0; which < 2; ++which) {
+      NDArray& a = which == 0 ? e.rsp_shard_state[j].s1 : e.rsp_shard_state[j].s2;
+      if (!(which == 0 ? need1 : need2) || !a.is_none()) continue;
+      a = NDArray(e.rsp_shards[j].shape(), Context::GPU(devs[j]), kFloat32);
+      DeviceGuard g(devs[j]);
+      KV_CUDA(cudaMemsetAsync(a.data(), 0, a.ByteSize(), eng->Stream(devs[j])));
+      eng->MarkWrite(devs[j], eng->Issue(devs[j]), a.var());
+    }
+  }
+  for (auto& s : srcs) eng->BeginRead(s.dev(), *s.var());
+  for (int j = 0; j < n; ++j) {
+    eng->BeginWrite(devs[j], *e.rsp_shards[j].var());
+    if (need1) eng->BeginWrite(devs[j], *e.rsp_shard_state[j].s1.var());
+    if (need2) eng->BeginWrite(devs[j], *e.rsp_shard_state[j].s2.var());
+  }
+  eng->JoinStreams(lanes);
+  const int id_bits = BitsFor(rows);
+  std::vector<NDArray> keep;   // per-device scratch: lives until the kernels retire
+  for (int j = 0; j < n; ++j) {
+    const int64_t lo = static_cast<int64_t>(j) * e.rsp_rows_per, hi = std::min<int64_t>(rows, lo + e.rsp_rows_per);
+    if (hi <= lo) continue;
+    const int dev = devs[j];
+    DeviceGuard g(dev);
+    NDArray d_nnr({1}, Context::GPU(dev), kInt64);
+    NDArray ws({static_cast<int64_t>(RspMergeWorkspaceBytes(total))}, Context::GPU(dev), kUint8);
+    RspUpdateLaunch Uj = U;
+    // virtual bases: row `id` of the table is at base + id*row_len
+    Uj.w = static_cast<float*>(e.rsp_shards[j].data()) - lo * row_len;
+    Uj.s1 = need1 ? static_cast<float*>(e.rsp_shard_state[j].s1.data()) - lo * row_len : nullptr;
+    Uj.s2 = need2 ? static_cast<float*>(e.rsp_shard_state[j].s2.data()) - lo * row_len : nullptr;
+    LaunchRspMerge(S, id_bits, row_len, nullptr, nullptr, static_cast<int64_t*>(d_nnr.data()), ws.data(),
+                   ws.ByteSize(), eng->Stream(dev), &Uj, lo, hi);
+    eng->CountLaunch("rsp_merge(shard)", total * 24);
+    eng->CountLaunch("rsp_sum+update(shard)", 0);
+    const uint64_t seq = eng->Issue(dev);
+    eng->MarkWrite(dev, seq, e.rsp_shards[j].var());
+    if (need1) eng->MarkWrite(dev, seq, e.rsp_shard_state[j].s1.var());
+    if (need2) eng->MarkWrite(dev, seq, e.rsp_shard_state[j].s2.var());
+    eng->MarkWrite(dev, seq, d_nnr.var());
+    eng->MarkWrite(dev, seq, ws.var());
+    keep.push_back(d_nnr);
+    keep.push_back(ws);
+  }
+  eng->JoinStreams(lanes);
+  for (auto& s : srcs) eng->MarkRead(s.dev(), eng->Issue(s.dev()), s.var());
+  return true;
 }
 
 }  // namespace b200kv

@@ -108,12 +108,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_update_kernel(RspUpda
 // ---------------------------------------------------------------------------------------------
 // push: union + ordered sum
 
-__global__ void rsp_tag_kernel(RspSources s, int64_t* keys, uint32_t* vals) {
+// ids outside [lo, hi) (a row-range shard merges only its own rows) become `sentinel`, which sorts
+// behind every real id and forms one trailing segment that the sum kernel skips
+__global__ void rsp_tag_kernel(RspSources s, int64_t lo, int64_t hi, int64_t sentinel, int64_t* keys,
+                               uint32_t* vals) {
   const int64_t total = s.start[s.nsrc];
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int k = find_segment(s.start, s.nsrc, i);
-    keys[i] = s.idx[k][i - s.start[k]];
+    const int64_t id = s.idx[k][i - s.start[k]];
+    keys[i] = (id >= lo && id < hi) ? id : sentinel;
     vals[i] = static_cast<uint32_t>(i);
   }
 }
@@ -134,6 +138,7 @@ struct MergeSum {
   int64_t* out_idx; float* out_val;  // the merged gradient (OPT < 0)
   int64_t row_len;
   RspUpdateLaunch u;                 // OPT >= 0: the lazy optimizer step consumes the sum in registers
+  int64_t sentinel;                  // ids >= sentinel are out-of-shard fillers (0: none)
 };
 
 // OPT < 0: write the merged row_sparse gradient. OPT = kOptSGDSingle / kOptSGD / kOptAdam: the row
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
   const uint32_t b = p.seg[r];
   const uint32_t e = r + 1 < nnr ? p.seg[r + 1] : static_cast<uint32_t>(total);
   const int64_t id = p.keys[b];
+  if (p.sentinel != 0 && id >= p.sentinel) return;  // the out-of-shard filler segment
   if (OPT < 0 && lane == 0) p.out_idx[r] = id;
   // this row's sources, in source order; a row_sparse array holds an id at most once, so there
   // are at most nsrc <= kMaxSrc of them (anything beyond is a malformed input and is ignored)
@@ -445,16 +451,21 @@ retain_kernel(const RetainItem* items, int nitems, int64_t total, int id_bits, c
   const int64_t id = uniq[off[k] + j] & ((int64_t{1} << id_bits) - 1);
   if (lane == 0) it.out_idx[j] = id;
   int64_t srow = -1;
-  if (it.src_dense_rows) {
+  const float* src_base = it.src_val;
+  if (it.shard_vbase != nullptr) {
+    // the table is cut into row ranges over several GPUs: vbase[d] + id*row_len is row `id`
+    src_base = it.shard_vbase[id / it.rows_per_shard];
+    srow = id;
+  } else if (it.src_dense_rows) {
     srow = id;
   } else if (it.src_nnr > 0) {
     const int64_t lb = warp_lower_bound(it.src_idx, it.src_nnr, id, lane);
     if (lb < it.src_nnr && it.src_idx[lb] == id) srow = lb;
   }
   float* out = it.out_val + j * it.row_len;
-  const float* src = srow >= 0 ? it.src_val + srow * it.row_len : nullptr;
+  const float* src = srow >= 0 ? src_base + srow * it.row_len : nullptr;
   const bool vec = (it.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(it.out_val) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(it.src_val) & 15) == 0);
+                   ((reinterpret_cast<uintptr_t>(src_base) & 15) == 0);
   if (vec) {
     const int64_t nv = it.row_len / 4;
     for (int64_t v = lane; v < nv; v += 32) {
@@ -514,7 +525,7 @@ size_t RspMergeWorkspaceBytes(int64_t total_ids) { return LayoutMerge(std::max<i
 
 void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_t* out_idx,
                     float* out_val, int64_t* d_nnr, void* workspace, size_t workspace_bytes,
-                    cudaStream_t stream, const RspUpdateLaunch* fused_update) {
+                    cudaStream_t stream, const RspUpdateLaunch* fused_update, int64_t lo, int64_t hi) {
   const int64_t total = srcs.start[srcs.nsrc];
   KV_CHECK(srcs.nsrc >= 1 && srcs.nsrc <= kMaxSrc);
   KV_CHECK(total > 0 && total < (1LL << 31)) << "row_sparse push: " << total << " row ids";
@@ -527,16 +538,19 @@ void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_
   uint32_t* vals = reinterpret_cast<uint32_t*>(ws + l.vals);
   uint32_t* vals_sorted = reinterpret_cast<uint32_t*>(ws + l.vals_sorted);
   uint32_t* seg = reinterpret_cast<uint32_t*>(ws + l.seg);
-  rsp_tag_kernel<<<GridFor(total, 256), 256, 0, stream>>>(srcs, keys, vals);
+  const bool ranged = lo > 0 || hi < (int64_t{1} << id_bits);
+  KV_CHECK(!ranged || fused_update != nullptr) << "row-range merges feed a fused update";
+  const int64_t sentinel = ranged ? (int64_t{1} << id_bits) : 0;
+  rsp_tag_kernel<<<GridFor(total, 256), 256, 0, stream>>>(srcs, lo, hi, sentinel, keys, vals);
   KV_CUDA(cudaGetLastError());
   size_t tb = l.temp_bytes;
   KV_CUDA(cub::DeviceRadixSort::SortPairs(ws + l.temp, tb, keys, keys_sorted, vals, vals_sorted,
-                                          static_cast<int>(total), 0, id_bits, stream));
+                                          static_cast<int>(total), 0, id_bits + (ranged ? 1 : 0), stream));
   tb = l.temp_bytes;
   KV_CUDA(cub::DeviceSelect::If(ws + l.temp, tb, cub::CountingInputIterator<uint32_t>(0), seg, d_nnr,
                                 static_cast<int>(total), HeadPred{keys_sorted}, stream));
   if (row_len <= 0) return;
-  MergeSum m{srcs, keys_sorted, vals_sorted, seg, d_nnr, out_idx, out_val, row_len, RspUpdateLaunch()};
+  MergeSum m{srcs, keys_sorted, vals_sorted, seg, d_nnr, out_idx, out_val, row_len, RspUpdateLaunch(), sentinel};
   const int blocks = static_cast<int>((total + kWarpsPerBlock - 1) / kWarpsPerBlock);
   const int threads = kWarpsPerBlock * 32;
   if (fused_update == nullptr) {

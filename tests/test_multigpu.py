@@ -153,3 +153,64 @@ def test_row_sparse_multi_device(mx, oracle):
         ri, rv = oracle.sparse_retain(wi, wv, oracle.unique(i))
         assert np.array_equal(o.indices.asnumpy(), ri)
         assert eq(o.data.asnumpy(), rv)
+
+
+@pytest.mark.parametrize("optname", ['sgd_mom', 'adam'])
+def test_row_sparse_table_sharded_by_row_range(optname):
+    """gradients pushed from two GPUs -> every GPU merges and updates its own row range
+    of the table (weight + optimizer state sharded); pulls gather rows from the owning shards.
+    Bit-exact against the oracle, before and after folding the shards back."""
+    import kvoracle as K
+    import anand_mxnet_b200 as mx
+    oracle = K.get_oracle()
+    rng = np.random.default_rng(31)
+    shape = (1001, 24)                      # odd height: unequal shards
+    w = rng.uniform(-1, 1, shape).astype(np.float32)
+    ctxs = [mx.gpu(0), mx.gpu(1)]
+    kv = mx.kv.create('device')
+    kv.init('emb', mx.nd.array(w, ctxs[0]).tostype('row_sparse'))
+    if optname == 'sgd_mom':
+        kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9, wd=1e-3, rescale_grad=0.5))
+    else:
+        kv.set_optimizer(mx.optimizer.Adam(learning_rate=1e-3, wd=0.01, rescale_grad=0.5))
+    sp = K.scalar_param
+    m, v = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+
+    def make(ctx, n):
+        idx = np.sort(rng.choice(shape[0], n, replace=False)).astype(np.int64)
+        val = rng.uniform(-1, 1, (n, shape[1])).astype(np.float32)
+        return mx.nd.sparse.row_sparse_array((val, idx), shape=shape, ctx=ctx), idx, val
+
+    def check(t):
+        for c in ctxs:
+            ids = rng.integers(0, shape[0], 300)
+            out = mx.nd.sparse.zeros('row_sparse', shape, c)
+            kv.row_sparse_pull('emb', out=out, row_ids=mx.nd.array(ids, c, np.int64))
+            u = np.unique(ids)
+            assert np.array_equal(out.indices.asnumpy(), u), t
+            assert np.array_equal(out.data.asnumpy().view(np.uint32), w[u].view(np.uint32)), t
+
+    for t in range(1, 5):
+        srcs = [make(ctxs[i % 2], 90) for i in range(4)]      # two values per GPU
+        kv.push('emb', [s[0] for s in srcs])
+        gi, gv = oracle.rsp_reduce([s[1] for s in srcs], [s[2] for s in srcs])
+        if optname == 'sgd_mom':
+            oracle.sgd_mom_rsp_update(w, m, gi, gv, sp(0.1), sp(0.9), sp(1e-3), sp(0.5), None)
+        else:
+            oracle.adam_rsp_update(w, m, v, gi, gv, sp(K.adam_lr(1e-3, 0.9, 0.999, t)), sp(0.9), sp(0.999),
+                                   sp(1e-8), sp(0.01), sp(0.5), None)
+        check(t)
+        if t == 2:
+            # whole-value access folds the shards back onto one GPU; the next push shards again
+            full = mx.nd.sparse.zeros('row_sparse', shape, ctxs[1])
+            kv.pull('emb', out=full, ignore_sparse=False)
+            assert np.array_equal(full.asnumpy().view(np.uint32), w.view(np.uint32))
+    # a push from a single GPU takes the single-owner path on the folded table
+    s0 = make(ctxs[0], 50)
+    kv.push('emb', s0[0])
+    if optname == 'sgd_mom':
+        oracle.sgd_mom_rsp_update(w, m, s0[1], s0[2], sp(0.1), sp(0.9), sp(1e-3), sp(0.5), None)
+    else:
+        oracle.adam_rsp_update(w, m, v, s0[1], s0[2], sp(K.adam_lr(1e-3, 0.9, 0.999, 5)), sp(0.9), sp(0.999),
+                               sp(1e-8), sp(0.01), sp(0.5), None)
+    check(5)
