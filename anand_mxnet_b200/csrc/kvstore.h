@@ -230,8 +230,10 @@ class KVStore {
   void ShardRsp(KeyEntry& e, const std::vector<int>& devs);
   void UnshardRsp(KeyEntry& e);
   const float* const* RspShardTable(KeyEntry& e, int dev);
-  void PullRowSparseGroup(int home, const std::vector<size_t>& which, const std::vector<int>& keys,
-                          const std::vector<NDArray>& outs, const std::vector<NDArray>& row_ids);
+  // launches one owner's batch; the returned closure waits for the counts and finishes the outputs
+  std::function<void()> PullRowSparseGroup(int home, const std::vector<size_t>& which,
+                                           const std::vector<int>& keys, const std::vector<NDArray>& outs,
+                                           const std::vector<NDArray>& row_ids);
 
   std::string type_;
   bool dist_ = false;         // created inside a one-rank-per-GPU peer group

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <iostream>
 #include <map>
 
@@ -275,12 +276,15 @@ void KVStore::PullRowSparse(const std::vector<int>& keys, const std::vector<NDAr
     // a sharded table has no single owner: the gather runs where the output lives
     by_home[sharded && out.on_gpu() ? out.dev() : e.home].push_back(i);
   }
-  for (auto& kv : by_home) PullRowSparseGroup(kv.first, kv.second, keys, outs, row_ids);
+  std::vector<std::function<void()>> finish;
+  for (auto& kv : by_home) finish.push_back(PullRowSparseGroup(kv.first, kv.second, keys, outs, row_ids));
+  for (auto& f : finish) f();
 }
 
-void KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
-                                 const std::vector<int>& keys, const std::vector<NDArray>& outs,
-                                 const std::vector<NDArray>& row_ids) {
+std::function<void()> KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
+                                                  const std::vector<int>& keys,
+                                                  const std::vector<NDArray>& outs,
+                                                  const std::vector<NDArray>& row_ids) {
   Engine* eng = Engine::Get();
   const int nitems = static_cast<int>(which.size());
   std::vector<RetainItem> items(nitems);
@@ -335,18 +339,20 @@ void KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
     KV_CHECK_EQ(en, static_cast<int>(parts.size() * (parts.size() - 1)))
         << "GPU peer access is not available between all participating devices";
   }
+  // every dependency is taken on the lane that runs the kernels (`home`): arrays on other GPUs are
+  // reached through peer access, their writers / readers are waited for by events -- no stream
+  // join, so groups that run on different GPUs do not serialise each other
   for (int k = 0; k < nitems; ++k) {
-    eng->BeginRead(ids[k].dev(), *ids[k].var());
+    eng->BeginRead(home, *ids[k].var());
     KeyEntry& ek = Entry(keys[which[k]]);
     if (ek.rsp_devs.empty()) {
       eng->BeginRead(home, *ek.rsp.var());
     } else {
       for (auto& sh : ek.rsp_shards) eng->BeginRead(home, *sh.var());
     }
-    eng->BeginWrite(targets[k].dev(), *targets[k].var());
+    eng->BeginWrite(home, *targets[k].var());
   }
-  if (parts.size() > 1) eng->JoinStreams(parts);
-  CountFence fence(home, nitems + 1);
+  auto fence = std::make_shared<CountFence>(home, nitems + 1);
   NDArray d_off({nitems + 1}, Context::GPU(home), kInt64);
   NDArray ws({static_cast<int64_t>(RetainBatchWorkspaceBytes(nitems, total))}, Context::GPU(home), kUint8);
   {
@@ -355,13 +361,12 @@ void KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
     LaunchUniqueBatch(items.data(), nitems, total, id_bits, static_cast<int64_t*>(d_off.data()),
                       ws.data(), ws.ByteSize(), st);
     eng->CountLaunch("unique_batch(gather, sort, unique, bounds)", total * 32);
-    fence.Post(static_cast<const int64_t*>(d_off.data()), st);
+    fence->Post(static_cast<const int64_t*>(d_off.data()), st);
     LaunchRetainBatch(nitems, total, id_bits, static_cast<const int64_t*>(d_off.data()), ws.data(), st);
     uint64_t bytes = 0;
     for (auto& it : items) bytes += static_cast<uint64_t>(it.n) * (it.row_len * 8 + 16);
     eng->CountLaunch("sparse_retain", bytes);
   }
-  if (parts.size() > 1) eng->JoinStreams(parts);
   uint64_t seq = eng->Issue(home);
   eng->MarkWrite(home, seq, d_off.var());
   eng->MarkWrite(home, seq, ws.var());
@@ -372,16 +377,19 @@ void KVStore::PullRowSparseGroup(int home, const std::vector<size_t>& which,
     } else {
       for (auto& sh : ek.rsp_shards) eng->MarkRead(home, seq, sh.var());
     }
-    eng->MarkRead(ids[k].dev(), ids[k].dev() == home ? seq : eng->Issue(ids[k].dev()), ids[k].var());
-    eng->MarkWrite(targets[k].dev(), targets[k].dev() == home ? seq : eng->Issue(targets[k].dev()),
-                   targets[k].var());
+    eng->MarkRead(home, seq, ids[k].var());
+    eng->MarkWrite(home, seq, targets[k].var());
   }
-  const int64_t* off = fence.Wait();
-  for (int k = 0; k < nitems; ++k) {
-    targets[k].SetNnr(off[k + 1] - off[k]);
-    const NDArray& out = outs[which[k]];
-    if (!out.on_gpu()) CopyFromTo(targets[k], out);
-  }
+  // the counts are awaited by the caller AFTER every group of the call has been launched
+  std::vector<NDArray> outs_k(nitems);
+  for (int k = 0; k < nitems; ++k) outs_k[k] = outs[which[k]];
+  return [fence, targets, outs_k, d_off, ws, nitems]() {
+    const int64_t* off = fence->Wait();
+    for (int k = 0; k < nitems; ++k) {
+      targets[k].SetNnr(off[k + 1] - off[k]);
+      if (!outs_k[k].on_gpu()) CopyFromTo(targets[k], outs_k[k]);
+    }
+  };
 }
 
 // =================================================================================================
@@ -657,13 +665,14 @@ bool KVStore::PushRowSparseSharded(KeyEntry& e, const std::vector<NDArray>& srcs
       eng->MarkWrite(devs[j], eng->Issue(devs[j]), a.var());
     }
   }
-  for (auto& s : srcs) eng->BeginRead(s.dev(), *s.var());
+  // each shard's kernels depend on the sources through events on ITS lane (no global join: the
+  // GPUs merge their row ranges concurrently and independently)
   for (int j = 0; j < n; ++j) {
+    for (auto& s : srcs) eng->BeginRead(devs[j], *s.var());
     eng->BeginWrite(devs[j], *e.rsp_shards[j].var());
     if (need1) eng->BeginWrite(devs[j], *e.rsp_shard_state[j].s1.var());
     if (need2) eng->BeginWrite(devs[j], *e.rsp_shard_state[j].s2.var());
   }
-  eng->JoinStreams(lanes);
   const int id_bits = BitsFor(rows);
   std::vector<NDArray> keep;   // per-device scratch: lives until the kernels retire
   for (int j = 0; j < n; ++j) {
@@ -688,11 +697,10 @@ bool KVStore::PushRowSparseSharded(KeyEntry& e, const std::vector<NDArray>& srcs
     if (need2) eng->MarkWrite(dev, seq, e.rsp_shard_state[j].s2.var());
     eng->MarkWrite(dev, seq, d_nnr.var());
     eng->MarkWrite(dev, seq, ws.var());
+    for (auto& s : srcs) eng->MarkRead(dev, seq, s.var());
     keep.push_back(d_nnr);
     keep.push_back(ws);
   }
-  eng->JoinStreams(lanes);
-  for (auto& s : srcs) eng->MarkRead(s.dev(), eng->Issue(s.dev()), s.var());
   return true;
 }
 
