@@ -71,6 +71,8 @@ struct KeyEntry {
   std::vector<DevState> rsp_shard_state;    // s1 / s2 per shard
   int64_t rsp_rows_per = 0;
   std::map<int, NDArray> rsp_vbase;         // per launching GPU: device table of shard virtual bases
+  bool rsp_group = false;                   // one rank per GPU: rsp_shards holds THIS rank's shard only
+  std::vector<int64_t> rsp_peer_off;        // arena offset of every rank's shard (group mode)
   std::vector<NDArray> stage_src, stage_out;  // device staging of host-resident values / outs
   // 2-bit gradient compression: per source slot residual (fp32) and compressed words, both on the
   // source's GPU; decoded sum on `home`
@@ -227,6 +229,9 @@ class KVStore {
   void PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs);
   bool PushRowSparseSharded(KeyEntry& e, const std::vector<NDArray>& srcs, const std::vector<int>& parts,
                             RspUpdateLaunch U);
+  // one rank per GPU: every rank owns a row range; gradients of the peers are read through IPC
+  void PushRowSparseGroup(KeyEntry& e, const NDArray& src, RspUpdateLaunch U);
+  void GroupBarrier();   // cross-rank barrier on this rank's compute lane (signal pads)
   void ShardRsp(KeyEntry& e, const std::vector<int>& devs);
   void UnshardRsp(KeyEntry& e);
   const float* const* RspShardTable(KeyEntry& e, int dev);

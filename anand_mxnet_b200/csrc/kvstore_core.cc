@@ -472,8 +472,7 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
     }
     if (srcs[0].stype() == kRowSparseStorage) {
       for (auto& s : srcs) KV_CHECK_EQ(s.stype(), kRowSparseStorage) << "mixed storage types in push";
-      KV_CHECK(!dist_) << "row_sparse keys are not supported by the one-rank-per-GPU store yet";
-      PushRowSparse(e, srcs);
+      PushRowSparse(e, srcs);   // one rank per GPU: PushRowSparseGroup (row-range shards per rank)
       continue;
     }
     KV_CHECK_EQ(e.stype, kDefaultStorage)
@@ -547,6 +546,8 @@ void KVStore::PullImpl(const std::vector<int>& keys, const std::vector<NDArray>&
       cacheable_call = false;
       NDArray local;
       if (e.stype == kRowSparseStorage) {
+        KV_CHECK(!e.rsp_group) << "key " << e.key << ": a whole-value pull of a row_sparse table that is "
+                               << "sharded over the ranks is not supported; use row_sparse_pull";
         UnshardRsp(e);
         local = e.rsp;
       } else {

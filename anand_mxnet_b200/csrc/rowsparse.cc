@@ -12,6 +12,7 @@
 #include <iostream>
 #include <map>
 
+#include "group.h"
 #include "kvstore.h"
 #include "rowsparse.h"
 #include "scalar_parse.h"
@@ -70,6 +71,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
   KV_CHECK_EQ(e.dtype, kFloat32) << "row_sparse keys are float32 on this path";
   KV_CHECK(srcs_in.size() <= static_cast<size_t>(kMaxSrc));
   Engine* eng = Engine::Get();
+  if (dist_ && e.home < 0) e.home = PeerGroup::Get()->dev();
   if (e.home < 0) {
     int pick = 0;
     for (auto& s : srcs_in) {
@@ -116,7 +118,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
   const bool fused = on_store && opt_.lazy_update;
   RspUpdateLaunch U;
   if (on_store) {
-    KV_CHECK(!e.rsp_devs.empty() || e.rsp.nnr() == e.shape[0])
+    KV_CHECK(!e.rsp_devs.empty() || e.rsp_group || e.rsp.nnr() == e.shape[0])
         << "key " << e.key << ": the stored row_sparse weight must hold every row for sparse "
         << "optimizer updates (initialise it from a dense weight, as gluon does)";
     // Optimizer._update_count, then SGD._update_impl's non-aggregated branch / Adam.update
@@ -124,14 +126,14 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     int c = (it == opt_.count.end() ? opt_.begin_num_update : it->second) + 1;
     opt_.count[e.key] = c;
     opt_.num_update = std::max(opt_.num_update, c);
-    if (total == 0 && fused) return;   // a lazy update with an all-zero gradient touches nothing
+    if (total == 0 && fused && !dist_) return;   // a lazy update with an all-zero gradient touches nothing
     auto lm = opt_.lr_mult.find(e.key);
     auto wm = opt_.wd_mult.find(e.key);
     double lrd = opt_.lr * (lm == opt_.lr_mult.end() ? 1.0 : lm->second);
     double wdd = opt_.wd * (wm == opt_.wd_mult.end() ? 1.0 : wm->second);
     DevState& s = e.dev[home];
     const std::vector<int64_t> dshape = e.shape;
-    const bool sharded_now = !e.rsp_devs.empty();   // state then lives with the shards
+    const bool sharded_now = !e.rsp_devs.empty() || e.rsp_group || dist_;   // state lives with the shards
     auto zero_state = [&](NDArray* a) {
       if (!a->is_none() || sharded_now) return;
       *a = NDArray(dshape, Context::GPU(home), kFloat32);
@@ -161,6 +163,14 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     U.s1 = s.s1.is_none() ? nullptr : static_cast<float*>(s.s1.data());
     U.s2 = s.s2.is_none() ? nullptr : static_cast<float*>(s.s2.data());
     U.row_len = row_len;
+  }
+  if (dist_) {
+    KV_CHECK(fused) << "one-rank-per-GPU store: row_sparse keys need a fused lazy optimizer on the "
+                    << "store (set_optimizer(SGD / Adam)); updater callbacks and plain assignment are "
+                    << "single-process features";
+    KV_CHECK_EQ(srcs.size(), 1u) << "one-rank-per-GPU store: push one row_sparse value per key and rank";
+    PushRowSparseGroup(e, srcs[0], U);
+    return;
   }
   if (fused && total > 0 && parts.size() >= 2 && std::getenv("B200KV_RSP_SHARD_OFF") == nullptr) {
     // sources on several GPUs: every GPU merges and updates its own row range of the table
@@ -259,7 +269,7 @@ void KVStore::PullRowSparse(const std::vector<int>& keys, const std::vector<NDAr
     KV_CHECK_EQ(e.stype, kRowSparseStorage) << "PullRowSparse expects row_sparse src NDArray";
     const NDArray& out = outs[i];
     if (e.home < 0) e.home = out.on_gpu() ? out.dev() : (row_ids[i].on_gpu() ? row_ids[i].dev() : 0);
-    const bool sharded = !e.rsp_devs.empty();
+    const bool sharded = !e.rsp_devs.empty() || e.rsp_group;
     if (!sharded && !e.rsp.on_gpu()) e.rsp = e.rsp.Copy(Context::GPU(e.home));
     KV_CHECK(out.shape() == e.shape) << "row_sparse_pull: out shape mismatch for key " << e.key;
     KV_CHECK_EQ(out.dtype(), e.dtype) << "row_sparse_pull: out dtype mismatch for key " << e.key;
@@ -313,7 +323,7 @@ std::function<void()> KVStore::PullRowSparseGroup(int home, const std::vector<si
     it.ids_dtype = ids[k].dtype();
     it.n = n;
     it.start = total;
-    if (!e.rsp_devs.empty()) {
+    if (!e.rsp_devs.empty() || e.rsp_group) {
       it.src_idx = nullptr;
       it.src_val = nullptr;
       it.src_nnr = e.shape[0];
@@ -345,7 +355,7 @@ std::function<void()> KVStore::PullRowSparseGroup(int home, const std::vector<si
   for (int k = 0; k < nitems; ++k) {
     eng->BeginRead(home, *ids[k].var());
     KeyEntry& ek = Entry(keys[which[k]]);
-    if (ek.rsp_devs.empty()) {
+    if (ek.rsp_devs.empty() && !ek.rsp_group) {
       eng->BeginRead(home, *ek.rsp.var());
     } else {
       for (auto& sh : ek.rsp_shards) eng->BeginRead(home, *sh.var());
@@ -372,7 +382,7 @@ std::function<void()> KVStore::PullRowSparseGroup(int home, const std::vector<si
   eng->MarkWrite(home, seq, ws.var());
   for (int k = 0; k < nitems; ++k) {
     KeyEntry& ek = Entry(keys[which[k]]);
-    if (ek.rsp_devs.empty()) {
+    if (ek.rsp_devs.empty() && !ek.rsp_group) {
       eng->MarkRead(home, seq, ek.rsp.var());
     } else {
       for (auto& sh : ek.rsp_shards) eng->MarkRead(home, seq, sh.var());
@@ -599,11 +609,14 @@ void KVStore::UnshardRsp(KeyEntry& e) {
 const float* const* KVStore::RspShardTable(KeyEntry& e, int dev) {
   auto it = e.rsp_vbase.find(dev);
   if (it == e.rsp_vbase.end()) {
-    const int n = static_cast<int>(e.rsp_devs.size());
+    const int n = e.rsp_group ? static_cast<int>(e.rsp_peer_off.size()) : static_cast<int>(e.rsp_devs.size());
     const int64_t row_len = static_cast<int64_t>(e.rsp_shards[0].RowLength());
     std::vector<const float*> vb(n);
     for (int j = 0; j < n; ++j) {
-      vb[j] = static_cast<const float*>(e.rsp_shards[j].data()) - static_cast<int64_t>(j) * e.rsp_rows_per * row_len;
+      const float* base = e.rsp_group
+          ? static_cast<const float*>(PeerGroup::Get()->PeerPtr(j, e.rsp_peer_off[j]))
+          : static_cast<const float*>(e.rsp_shards[j].data());
+      vb[j] = base - static_cast<int64_t>(j) * e.rsp_rows_per * row_len;
     }
     NDArray tbl({n}, Context::GPU(dev), kInt64);
     RawCopy(tbl.data(), tbl.ctx(), tbl.var(), vb.data(), Context::CPU(), nullptr, n * sizeof(void*));
@@ -702,6 +715,141 @@ bool KVStore::PushRowSparseSharded(KeyEntry& e, const std::vector<NDArray>& srcs
     keep.push_back(ws);
   }
   return true;
+}
+
+// =================================================================================================
+// one rank per GPU (torchrun): row_sparse keys
+// =================================================================================================
+void KVStore::GroupBarrier() {
+  PeerGroup* g = PeerGroup::Get();
+  Engine* eng = Engine::Get();
+  DenseLaunch L;
+  L.signal_pads = g->d_pads();
+  L.counter = g->d_counter();
+  L.rank = g->rank();
+  L.world = g->world();
+  L.epoch = g->NextEpoch();
+  L.n_chunks = 0;               // no work: the fused kernel's start + end barriers only
+  L.dtype = kFloat32;
+  L.opt = kOptAssign;
+  DeviceGuard guard(g->dev());
+  LaunchDenseFused(L, eng->Stream(g->dev()));
+  eng->CountLaunch("group_barrier", 0);
+}
+
+void KVStore::PushRowSparseGroup(KeyEntry& e, const NDArray& src_in, RspUpdateLaunch U) {
+  PeerGroup* g = PeerGroup::Get();
+  KV_CHECK(g != nullptr);
+  Engine* eng = Engine::Get();
+  const int dev = g->dev(), W = g->world(), R = g->rank();
+  const int64_t rows = e.shape[0];
+  KV_CHECK_EQ(e.home, dev) << "key " << e.key << " lives on another GPU than this rank's";
+  // ---- this rank's shard (rows [R*per, (R+1)*per)) and every rank's shard address, once
+  if (!e.rsp_group) {
+    KV_CHECK_EQ(e.rsp.nnr(), rows)
+        << "key " << e.key << ": the stored row_sparse weight must hold every row (initialise it from "
+        << "a dense weight, as gluon does)";
+    e.rsp_rows_per = (rows + W - 1) / W;
+    const int64_t lo = R * e.rsp_rows_per, hi = std::min<int64_t>(rows, lo + e.rsp_rows_per);
+    const int64_t row_len = static_cast<int64_t>(e.rsp.RowLength());
+    NDArray shard({std::max<int64_t>(hi - lo, 1), row_len}, Context::GPU(dev), kFloat32);
+    KV_CHECK(g->InArena(shard.data())) << "IPC arena exhausted; raise B200KV_IPC_ARENA_MB";
+    if (hi > lo) {
+      RawCopy(shard.data(), shard.ctx(), shard.var(),
+              static_cast<const char*>(e.rsp.data()) + lo * row_len * sizeof(float), e.rsp.ctx(), e.rsp.var(),
+              static_cast<size_t>(hi - lo) * row_len * sizeof(float));
+    }
+    eng->WaitToWrite(*e.rsp.var());
+    e.rsp = NDArray::RowSparse(e.shape, Context::GPU(dev), e.dtype);  // the full copy is released
+    e.rsp_shards.assign(1, shard);
+    e.rsp_shard_state.assign(1, DevState());
+    const std::vector<int64_t> all = g->AllGatherI64({g->OffsetOf(shard.data()), rows, row_len});
+    e.rsp_peer_off.resize(W);
+    for (int r = 0; r < W; ++r) {
+      KV_CHECK(all[3 * r + 1] == rows && all[3 * r + 2] == row_len)
+          << "key " << e.key << " has a different shape on rank " << r;
+      e.rsp_peer_off[r] = all[3 * r];
+    }
+    e.rsp_group = true;
+    e.rsp_vbase.clear();
+  }
+  const int64_t row_len = static_cast<int64_t>(e.rsp_shards[0].RowLength());
+  const int64_t lo = R * e.rsp_rows_per, hi = std::min<int64_t>(rows, lo + e.rsp_rows_per);
+  // ---- the gradient must be addressable by the peers: inside this rank's arena
+  NDArray src = src_in;
+  if (!src.on_gpu() || src.dev() != dev ||
+      (src.storage_initialized() && !(g->InArena(src.data()) && g->InArena(src.row_ids())))) {
+    src = src_in.Copy(Context::GPU(dev));
+  }
+  const int64_t my_nnr = src.storage_initialized() ? src.nnr() : 0;
+  if (my_nnr > 0) {
+    KV_CHECK(g->InArena(src.data()) && g->InArena(src.row_ids()))
+        << "IPC arena exhausted; raise B200KV_IPC_ARENA_MB";
+  }
+  // per push: where every rank's gradient lives and how many rows it has (host all-gather: the
+  // arrays and row counts change every step)
+  const std::vector<int64_t> all = g->AllGatherI64(
+      {my_nnr > 0 ? g->OffsetOf(src.row_ids()) : 0, my_nnr > 0 ? g->OffsetOf(src.data()) : 0, my_nnr,
+       static_cast<int64_t>(e.key)});
+  RspSources S;
+  int64_t total = 0;
+  for (int r = 0; r < W; ++r) {            // rank order == the reference's value-list order
+    KV_CHECK_EQ(all[4 * r + 3], static_cast<int64_t>(e.key))
+        << "one-rank-per-GPU store: rank " << r << " pushed a different row_sparse key";
+    const int64_t n = all[4 * r + 2];
+    if (n == 0) continue;
+    S.idx[S.nsrc] = static_cast<const int64_t*>(g->PeerPtr(r, all[4 * r]));
+    S.val[S.nsrc] = static_cast<const float*>(g->PeerPtr(r, all[4 * r + 1]));
+    S.start[S.nsrc] = total;
+    total += n;
+    ++S.nsrc;
+  }
+  S.start[S.nsrc] = total;
+  // optimizer state of the shard
+  const bool need1 = U.opt == kOptSGD || U.opt == kOptAdam, need2 = U.opt == kOptAdam;
+  DevState& st8 = e.rsp_shard_state[0];
+  for (int which = 0; which < 2; ++which) {
+    NDArray& a = which == 0 ? st8.s1 : st8.s2;
+    if (!(which == 0 ? need1 : need2) || !a.is_none()) continue;
+    a = NDArray(e.rsp_shards[0].shape(), Context::GPU(dev), kFloat32);
+    DeviceGuard gd(dev);
+    KV_CUDA(cudaMemsetAsync(a.data(), 0, a.ByteSize(), eng->Stream(dev)));
+    eng->MarkWrite(dev, eng->Issue(dev), a.var());
+  }
+  eng->BeginRead(dev, *src.var());
+  eng->BeginWrite(dev, *e.rsp_shards[0].var());
+  if (need1) eng->BeginWrite(dev, *st8.s1.var());
+  if (need2) eng->BeginWrite(dev, *st8.s2.var());
+  // barrier 1: every rank's gradient is complete (its barrier kernel is stream-ordered behind the
+  // producer) before anybody reads it through IPC
+  GroupBarrier();
+  NDArray d_nnr, ws;
+  if (total > 0 && hi > lo) {
+    DeviceGuard gd(dev);
+    d_nnr = NDArray({1}, Context::GPU(dev), kInt64);
+    ws = NDArray({static_cast<int64_t>(RspMergeWorkspaceBytes(total))}, Context::GPU(dev), kUint8);
+    RspUpdateLaunch Uj = U;
+    Uj.row_len = row_len;
+    Uj.w = static_cast<float*>(e.rsp_shards[0].data()) - lo * row_len;
+    Uj.s1 = need1 ? static_cast<float*>(st8.s1.data()) - lo * row_len : nullptr;
+    Uj.s2 = need2 ? static_cast<float*>(st8.s2.data()) - lo * row_len : nullptr;
+    LaunchRspMerge(S, BitsFor(rows), row_len, nullptr, nullptr, static_cast<int64_t*>(d_nnr.data()),
+                   ws.data(), ws.ByteSize(), eng->Stream(dev), &Uj, lo, hi);
+    eng->CountLaunch("rsp_merge(rank shard)", total * 24);
+    eng->CountLaunch("rsp_sum+update(rank shard)", 0);
+  }
+  // barrier 2: every rank has finished reading the peers' gradients (they may now be reused) and
+  // updating its shard (a pull that follows sees the new rows on every rank)
+  GroupBarrier();
+  const uint64_t seq = eng->Issue(dev);
+  eng->MarkRead(dev, seq, src.var());
+  eng->MarkWrite(dev, seq, e.rsp_shards[0].var());
+  if (need1) eng->MarkWrite(dev, seq, st8.s1.var());
+  if (need2) eng->MarkWrite(dev, seq, st8.s2.var());
+  if (!d_nnr.is_none()) {
+    eng->MarkWrite(dev, seq, d_nnr.var());
+    eng->MarkWrite(dev, seq, ws.var());
+  }
 }
 
 }  // namespace b200kv

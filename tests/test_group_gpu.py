@@ -99,6 +99,49 @@ def _worker(rank, world, port, q, nvls=False):
             for k in keys:
                 if not eq(fresh[k].asnumpy(), model.pull(k)):
                     errors.append("pull %s key %d" % (kvtype, k))
+        # ---- row_sparse key: every rank owns a row range of the table (weight + state), reads the
+        # peers' gradients through IPC, pulls gather rows from the owning ranks (bit-exact)
+        for optname in ('sgd_mom', 'adam'):
+            shape = (997, 16)
+            w = np.random.default_rng(71).uniform(-1, 1, shape).astype(np.float32)
+            kv = mx.kv.create('device')
+            kv.init('emb', mx.nd.array(w, ctx).tostype('row_sparse'))
+            if optname == 'sgd_mom':
+                kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9, wd=1e-3, rescale_grad=0.5))
+            else:
+                kv.set_optimizer(mx.optimizer.Adam(learning_rate=1e-3, wd=0.01, rescale_grad=0.5))
+            sp = K.scalar_param
+            m, v = np.zeros(shape, np.float32), np.zeros(shape, np.float32)
+            o = K.get_oracle()
+
+            def rsp_of(r, t):
+                rg = np.random.default_rng(500 + 31 * r + t)
+                n = 0 if (r == 1 and t == 2) else 60          # one rank pushes an all-zero gradient once
+                idx = np.sort(rg.choice(shape[0], n, replace=False)).astype(np.int64)
+                return idx, rg.uniform(-1, 1, (n, shape[1])).astype(np.float32)
+            for t in range(1, 4):
+                idx, val = rsp_of(rank, t)
+                if len(idx):
+                    g = mx.nd.sparse.row_sparse_array((val, idx), shape=shape, ctx=ctx)
+                else:
+                    g = mx.nd.sparse.zeros('row_sparse', shape, ctx)
+                kv.push('emb', g)
+                parts = [rsp_of(r, t) for r in range(world)]
+                parts = [p for p in parts if len(p[0])]
+                gi, gv = o.rsp_reduce([p[0] for p in parts], [p[1] for p in parts])
+                if optname == 'sgd_mom':
+                    o.sgd_mom_rsp_update(w, m, gi, gv, sp(0.1), sp(0.9), sp(1e-3), sp(0.5), None)
+                else:
+                    o.adam_rsp_update(w, m, v, gi, gv, sp(K.adam_lr(1e-3, 0.9, 0.999, t)), sp(0.9),
+                                      sp(0.999), sp(1e-8), sp(0.01), sp(0.5), None)
+                ids = np.random.default_rng(900 + rank + 7 * t).integers(0, shape[0], 250)
+                out = mx.nd.sparse.zeros('row_sparse', shape, ctx)
+                kv.row_sparse_pull('emb', out=out, row_ids=mx.nd.array(ids, ctx, np.int64))
+                u = np.unique(ids)
+                if not np.array_equal(out.indices.asnumpy(), u):
+                    errors.append("rsp %s step %d ids" % (optname, t))
+                elif not np.array_equal(out.data.asnumpy().view(np.uint32), w[u].view(np.uint32)):
+                    errors.append("rsp %s step %d rows" % (optname, t))
         # kv.init: "only the value supplied by worker with rank 0 is used" (kvstore.py:136-141)
         kv = mx.kv.create('device')
         vals0 = [np.random.default_rng(5 + k).uniform(-1, 1, s).astype(np.float32)
