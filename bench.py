@@ -9,14 +9,16 @@ momentum ON THE STORE, and pull the new weights back -- one grouped MXKVStorePus
 the library turns into ONE fused kernel launch per GPU.
 
 Printed JSON (one line, rank 0):
-  value      GB/s of ALGORITHMIC bytes (24 B/element for SGD-momentum at N=1; the
-             all-reduce bus-bandwidth formula of tools/bandwidth/measure.py:137-138 at N>=2), inputs
-             and outputs resident in HBM, timed with CUDA events on the launching stream
+  value      push+pull payload GB/s of the whole job: n_gpus x (bytes pushed + bytes pulled per GPU)
+             / step time -- the same definition at every N, so the per-N lines are comparable --
+             inputs and outputs resident in HBM, timed with CUDA events on the launching stream
   e2e        same metric through the same C-ABI call with HOST buffers (pinned CPU-context
              NDArrays): the H2D copy of the gradients and the D2H copy of the weights are inside
              the timed region
-  roofline   dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events)
-             against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline   dominant kernel: ALGORITHMIC bytes per launch (24 B/element for
+             SGD-momentum at N=1; all-reduce bus bandwidth per GPU, tools/bandwidth/measure.py:137-138,
+             at N>=2) / mean launch duration (CUDA events) against the measured HBM copy bandwidth
+             (MEASURED_PEAKS.json) or 900 GB/s/dir NVLink
   cpu_baseline   the reference's CPU kvstore('local') arithmetic (oracle/_ref, else the oracle
              port) on this box's host cores, bounded sample
 `--impl reference` times that CPU path as the whole job (the driver's reference arm).
@@ -37,6 +39,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "kvstore_push_pull_GBps"
 UNIT = "GB/s"
+VALUE_FORMULA = ("n_gpus * (bytes pushed + bytes pulled per GPU) / time = n_gpus * 2 * gradient-set "
+                 "bytes / time, identical at every N; roofline.achieved uses the kernel's algorithmic "
+                 "bytes (HBM, N=1) or the all-reduce bus bandwidth per GPU (NVLink, N>=2)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -83,6 +88,14 @@ WORKLOADS = {
 
 SGD_KW = dict(learning_rate=0.1, momentum=0.9, wd=1e-4)
 ADAM_KW = dict(learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, wd=0.01)
+
+
+def payload_bytes(workload, n_gpus):
+    """`value`: bytes PUSHED plus bytes PULLED per step over the whole job -- the same definition at
+    every N (each GPU pushes its gradient set and pulls the weights), so the per-N values are
+    comparable (weak scaling). The roofline uses the kernel's ALGORITHMIC bytes instead."""
+    n_elem = sum(int(np.prod(s)) for s in WORKLOADS[workload]["shapes"]())
+    return n_gpus * n_elem * 4 * 2
 
 
 def algorithmic_bytes(workload, n_gpus):
@@ -240,8 +253,7 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    nbytes = algorithmic_bytes(args.workload, n_src) * (n_src if n_src > 1 else 1)
-    value = nbytes / dt / 1e9
+    value = payload_bytes(args.workload, n_src) / dt / 1e9
     sample = "%d full steps of %s with %d host gradient buffers per key" % (
         args.steps, args.workload, n_src)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
@@ -249,7 +261,7 @@ def run_reference(args):
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload]["desc"], "store": "kvstore('local') on CPU",
-                       "values_per_key": n_src},
+                       "values_per_key": n_src, "value_formula": VALUE_FORMULA},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": sample, "host_cores_visible": host_cores()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -346,7 +358,8 @@ def run_single_gpu(args):
     # its average launch duration (incl. launch gaps) is the region's duration / K
     ms_kernel = ms_step
     alg = algorithmic_bytes(args.workload, 1)
-    value = alg / (ms_step * 1e-3) / 1e9
+    pay = payload_bytes(args.workload, 1)
+    value = pay / (ms_step * 1e-3) / 1e9
     peaks, peak_src = measured_peaks()
     achieved = alg / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -371,7 +384,7 @@ def run_single_gpu(args):
         step()
     host_c_us = (time.perf_counter() - th) / args.steps * 1e6
     torch.cuda.synchronize()
-    frontends = {"python_api_GBps": alg / (py_ms * 1e-3) / 1e9, "python_api_ms_per_step": py_ms,
+    frontends = {"python_api_GBps": pay / (py_ms * 1e-3) / 1e9, "python_api_ms_per_step": py_ms,
                  "python_api_host_us_per_call": host_py_us, "c_abi_host_us_per_call": host_c_us}
 
     # ---- end-to-end arm: same C-ABI call, HOST (pinned) gradient and weight buffers
@@ -394,7 +407,7 @@ def run_single_gpu(args):
     e1.record(stream)
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
-    e2e = {"value": alg / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_elem * 4,
+    e2e = {"value": pay / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_elem * 4,
            "d2h_bytes_per_step": n_elem * 4, "ms_per_step": e2e_ms, "steps": e2e_steps}
 
     # ---- cpu baseline (bounded sample, rank 0, N=1)
@@ -408,7 +421,7 @@ def run_single_gpu(args):
             cstep()
             n += 1
         cdt = (time.perf_counter() - t0) / n
-        cpu = {"value": alg / cdt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+        cpu = {"value": pay / cdt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": "%d full steps of %s (reduce of 1 value + optimizer + copy-out per key), "
                          "%.1f ms/step" % (n, args.workload, cdt * 1e3)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
@@ -418,6 +431,7 @@ def run_single_gpu(args):
                        "call": "one grouped MXKVStorePushPull (C ABI, prebuilt argument arrays) over "
                                "all keys per step; python front-end timing under 'frontends'",
                        "l2": "working set %.0f MB per step > 126 MB L2, no flush needed" % (alg / 1e6),
+                       "value_formula": VALUE_FORMULA,
                        "optimizer": SGD_KW if WORKLOADS[args.workload]["opt"] == "sgd" else ADAM_KW},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "frontends": frontends}

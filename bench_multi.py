@@ -4,8 +4,8 @@ weights; per step each rank launches ONE fused kernel that reduces the stripes i
 IPC-mapped NVLink peer memory, applies SGD-momentum, and writes the new weights into every rank's
 weight arrays (reduce-scatter + update + all-gather in one kernel, no NCCL on the data path).
 
-value  = whole-job aggregate of the reference's own bandwidth metric
-         (tools/bandwidth/measure.py:137-138): N x size x 2(N-1)/N / time
+value  = whole-job push+pull payload rate: N x 2 x gradient-set bytes / time (same definition as
+         the N=1 arm, so the per-N values are comparable)
 roofline.achieved = that bus bandwidth PER GPU against 900 GB/s/dir NVLink 5 (measured peer copy
          770 GB/s/dir, B200_PROFILING.md)
 """
@@ -21,7 +21,7 @@ def run_multi_gpu(args):
     import torch.distributed as dist
     import anand_mxnet_b200 as mx
     from bench import (WORKLOADS, METRIC, UNIT, SGD_KW, ADAM_KW, ClockSampler, make_optimizer,
-                       algorithmic_bytes)
+                       algorithmic_bytes, payload_bytes, VALUE_FORMULA)
     from anand_mxnet_b200.kvstore.base import _ctype_key_value
 
     rank = int(os.environ.get("RANK", "0"))
@@ -121,15 +121,18 @@ def run_multi_gpu(args):
     bus_per_gpu = algorithmic_bytes(args.workload, world)      # bytes per GPU per step
     if rank == 0:
         busbw = bus_per_gpu / (ms_step * 1e-3) / 1e9
+        pay = payload_bytes(args.workload, world)
         line = {
-            "metric": METRIC, "value": busbw * world, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": pay / (ms_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload]["desc"], "store": "kvstore('device')",
                        "parallelism": "one rank per GPU, stripes of the key space owned round-robin, "
                                       "fused reduce-scatter+update+all-gather kernel over IPC peer memory",
-                       "value_formula": "n_gpus * size * 2(n-1)/n / time (tools/bandwidth/measure.py:137)",
+                       "value_formula": VALUE_FORMULA,
+                       "bus_bandwidth_GBps_per_gpu": busbw,
+                       "bus_bandwidth_formula": "size * 2(n-1)/n / time (tools/bandwidth/measure.py:137)",
                        "l2": "per-GPU working set > 126 MB L2, no flush needed",
                        "nvls_in_switch_reduce": bool(mx.dist.nvls_wanted(world) and mx.dist.has_multicast()),
                        "parity_mode": ("1e-6 relative (in-switch summation order)"
@@ -141,7 +144,7 @@ def run_multi_gpu(args):
                          "traffic": None, "kernel": "dense_fused_kernel<float,%d,SGD>" % world,
                          "note": "bus bandwidth per GPU = size*2(n-1)/n/time vs 900 GB/s/dir nominal"},
             "cpu_baseline": None,
-            "e2e": {"value": bus_per_gpu * world / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+            "e2e": {"value": pay / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": n_elem * 4, "d2h_bytes_per_step": n_elem * 4,
                     "ms_per_step": e2e_ms, "steps": e2e_steps, "note": "bytes per rank"},
             "gpu_launches": int(launches), "clocks": clocks,
