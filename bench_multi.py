@@ -134,6 +134,7 @@ def run_multi_gpu(args):
                        "bus_bandwidth_GBps_per_gpu": busbw,
                        "bus_bandwidth_formula": "size * 2(n-1)/n / time (tools/bandwidth/measure.py:137)",
                        "l2": "per-GPU working set > 126 MB L2, no flush needed",
+                       "numa_bound": mx.dist._state.get('numa_node') is not None,
                        "nvls_in_switch_reduce": bool(mx.dist.nvls_wanted(world) and mx.dist.has_multicast()),
                        "parity_mode": ("1e-6 relative (in-switch summation order)"
                                        if mx.dist.nvls_wanted(world) and mx.dist.has_multicast()
