@@ -63,3 +63,66 @@ def test_lars_and_lamb_bookkeeping():
     lamb = mx.optimizer.create('lamb', learning_rate=0.01)
     assert lamb.aggregate_num == 45 and lamb.epsilon == 1e-6 and lamb.bias_correction
     assert isinstance(mx.optimizer.get_updater(lamb), mx.optimizer.Updater)
+
+
+def test_every_multi_tensor_operator_is_registered_and_has_golden_cases():
+    """the operator names of SURVEY 8f-f1 resolve through NNGetOpHandle (no GPU needed for the
+    lookup) and each of them is exercised by a seeded case whose golden output is committed"""
+    import ctypes
+    import inspect
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import golden_ops as G
+    import anand_mxnet_b200 as mx
+    ops = ['multi_sum_sq', 'multi_lars', 'preloaded_multi_sgd_update', 'preloaded_multi_sgd_mom_update',
+           'preloaded_multi_mp_sgd_update', 'preloaded_multi_mp_sgd_mom_update', '_adamw_update',
+           '_mp_adamw_update', '_multi_adamw_update', '_multi_mp_adamw_update', 'lamb_update_phase1',
+           'lamb_update_phase2', 'mp_lamb_update_phase1', 'mp_lamb_update_phase2', '_multi_lamb_update',
+           '_multi_mp_lamb_update']
+    src = inspect.getsource(G)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "multi_tensor_ops.npz"))
+    assert {k.split('/')[0] for k in gold.files} == set(G.CASES)
+    for name in ops:
+        h = ctypes.c_void_p()
+        assert mx.base._LIB.NNGetOpHandle(name.encode(), ctypes.byref(h)) == 0 and h.value, name
+        assert hasattr(G.OracleOps, '_op_' + name.lstrip('_')), name
+        base = name.replace('_mom_', '_%s').replace('_mp_', '_%s') if False else name
+        assert ("'%s'" % name in src) or (name.startswith('preloaded_') and "'preloaded_multi_%ssgd_%supdate'" in src), name
+    h = ctypes.c_void_p()
+    assert mx.base._LIB.NNGetOpHandle(b'no_such_operator', ctypes.byref(h)) != 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_ops_match_live_reference_on_random_cases(seed):
+    """beyond the fixed golden cases: random shapes / hyper-parameters, restatement vs the reference's
+    own FCompute<cpu> (only where oracle/_ref was built, i.e. in the build container)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import golden_ops as G
+    import kvoracle as K
+    ref = K.ref()
+    if ref is None or not ref.has_ops():
+        pytest.skip("oracle/_ref/libmxref.so not built here")
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 7))
+    shapes = [tuple(int(x) for x in rng.integers(1, 40, int(rng.integers(1, 4)))) for _ in range(n)]
+    kw = dict(lrs=[float(x) for x in rng.uniform(1e-4, 1e-1, n)], wds=[float(x) for x in rng.uniform(0, 1e-2, n)],
+              etas=[float(x) for x in rng.uniform(0.5, 1.0, n)], beta1=float(rng.uniform(0.8, 0.95)),
+              beta2=float(rng.uniform(0.9, 0.9999)), epsilon=float(10 ** rng.uniform(-9, -5)), num_weights=n)
+    if seed % 2:
+        kw['clip_gradient'] = float(rng.uniform(0.1, 2.0))
+    lamb = dict(learning_rates=kw['lrs'], wds=kw['wds'], beta1=kw['beta1'], beta2=kw['beta2'],
+                epsilon=kw['epsilon'], rescale_grad=float(rng.uniform(0.1, 2.0)), bias_correction=bool(seed % 3),
+                num_tensors=n, step_count=[int(x) for x in rng.integers(1, 2000, n)])
+    results = []
+    for backend in (G._RefBackend(ref), G.OracleOps()):
+        r2 = np.random.default_rng(77 + seed)
+        ws = [r2.uniform(-1, 1, s).astype(np.float32) for s in shapes]
+        gs = [r2.uniform(-3, 3, s).astype(np.float32) for s in shapes]
+        ms = [r2.uniform(-0.1, 0.1, s).astype(np.float32) for s in shapes]
+        vs = [r2.uniform(0, 0.1, s).astype(np.float32) for s in shapes]
+        rs = np.array([0.37], np.float32)
+        ins = [x for t in zip(ws, gs, ms, vs) for x in t]
+        backend.invoke('_multi_adamw_update', ins + [rs], ws, **kw)
+        backend.invoke('_multi_lamb_update', ins, ws, **lamb)
+        results.append([a.copy() for a in ws + ms + vs])
+    for a, b in zip(*results):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
