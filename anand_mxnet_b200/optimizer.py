@@ -34,64 +34,59 @@ def _flatten_list(nested_list):
 
 
 class Optimizer(object):
-    """The base class inherited by all optimizers (optimizer.py:53-524)."""
+    """The base class inherited by all optimizers (optimizer.py:53-524): hyper-parameters, per-index
+    learning-rate / weight-decay multipliers, per-device update counters."""
     opt_registry = {}
 
     def __init__(self, rescale_grad=1., param_idx2name=None, wd=0., clip_gradient=None,
                  learning_rate=None, lr_scheduler=None, sym=None, begin_num_update=0,
                  multi_precision=False, param_dict=None):
-        self.rescale_grad = rescale_grad
-        self.lr_scheduler = lr_scheduler
-        if self.lr_scheduler is None and learning_rate is None:
-            learning_rate = 0.01
-        self.lr = learning_rate
-        if self.lr_scheduler is not None and learning_rate is not None:
-            if self.lr_scheduler.base_lr != learning_rate:
-                print(UserWarning("learning rate from ``lr_scheduler`` has been overwritten by "
-                                  "``learning_rate`` in optimizer."))
-                self.lr_scheduler.base_lr = learning_rate
-        self.wd = wd
-        self.lr_mult = {}
-        self.wd_mult = {}
-        self.begin_num_update = begin_num_update
-        self.num_update = begin_num_update
-        self._all_index_update_counts = {0: {}}
-        self._index_update_count = self._all_index_update_counts[0]
-        self.clip_gradient = clip_gradient
+        if lr_scheduler is None:
+            learning_rate = 0.01 if learning_rate is None else learning_rate
+        elif learning_rate is not None and lr_scheduler.base_lr != learning_rate:
+            # an explicit learning rate wins over the scheduler's base (optimizer.py:117-123)
+            print(UserWarning("learning rate from ``lr_scheduler`` has been overwritten by "
+                              "``learning_rate`` in optimizer."))
+            lr_scheduler.base_lr = learning_rate
+        assert param_idx2name is None or isinstance(param_idx2name, dict), \
+            'param_idx2name should be a dict of param indexes to names.'
+        self.lr, self.lr_scheduler, self.wd = learning_rate, lr_scheduler, wd
+        self.rescale_grad, self.clip_gradient = rescale_grad, clip_gradient
         self.multi_precision = multi_precision
         self.aggregate_num = 0
-        if param_idx2name is None:
-            param_idx2name = {}
-        assert isinstance(param_idx2name, dict), \
-            'param_idx2name should be a dict of param indexes to names.'
-        self.idx2name = param_idx2name.copy()
+        # update counters: one table per device (Trainer shares one optimizer between the updaters
+        # of all its devices), `num_update` is the largest count seen anywhere
+        self.begin_num_update = self.num_update = begin_num_update
+        self._all_index_update_counts = {0: {}}
+        self._index_update_count = self._all_index_update_counts[0]
+        self.idx2name = dict(param_idx2name or {})
+        self.param_dict = param_dict or {}
         self.sym_info = ()
-        self.param_dict = param_dict if param_dict else {}
+        self.lr_mult, self.wd_mult = {}, {}
         self.set_lr_mult({})
         self.set_wd_mult({})
 
     @staticmethod
     def register(klass):
         assert isinstance(klass, type)
-        name = klass.__name__.lower()
-        if name in Optimizer.opt_registry:
+        key = klass.__name__.lower()
+        old = Optimizer.opt_registry.get(key)
+        if old is not None:
             warnings.warn('WARNING: New optimizer %s.%s is overriding existing optimizer %s.%s' % (
-                klass.__module__, klass.__name__, Optimizer.opt_registry[name].__module__,
-                Optimizer.opt_registry[name].__name__))
-        Optimizer.opt_registry[name] = klass
+                klass.__module__, klass.__name__, old.__module__, old.__name__))
+        Optimizer.opt_registry[key] = klass
         return klass
 
     @staticmethod
     def create_optimizer(name, **kwargs):
-        if name.lower() in Optimizer.opt_registry:
-            return Optimizer.opt_registry[name.lower()](**kwargs)
-        raise ValueError('Cannot find optimizer %s' % name)
+        klass = Optimizer.opt_registry.get(name.lower())
+        if klass is None:
+            raise ValueError('Cannot find optimizer %s' % name)
+        return klass(**kwargs)
 
     @property
     def learning_rate(self):
-        if self.lr_scheduler is not None:
-            return self.lr_scheduler(self.num_update)
-        return self.lr
+        return self.lr if self.lr_scheduler is None else self.lr_scheduler(self.num_update)
 
     def create_state(self, index, weight):
         """Creates auxiliary state for a given weight."""
@@ -125,55 +120,49 @@ class Optimizer(object):
         self.lr = lr
 
     def set_lr_mult(self, args_lr_mult):
-        self.lr_mult = {}
-        self.lr_mult.update(args_lr_mult)
+        self.lr_mult = dict(args_lr_mult)
 
     def set_wd_mult(self, args_wd_mult):
-        self.wd_mult = {}
-        for n in self.idx2name.values():
-            if not (n.endswith('_weight') or n.endswith('_gamma')):
-                self.wd_mult[n] = 0.0
+        # parameters that are neither *_weight nor *_gamma do not decay unless told otherwise
+        self.wd_mult = {n: 0.0 for n in self.idx2name.values()
+                        if not n.endswith(('_weight', '_gamma'))}
         self.wd_mult.update(args_wd_mult)
 
     def _set_current_context(self, device_id):
-        if device_id not in self._all_index_update_counts:
-            self._all_index_update_counts[device_id] = {}
-        self._index_update_count = self._all_index_update_counts[device_id]
+        self._index_update_count = self._all_index_update_counts.setdefault(device_id, {})
 
     def _update_count(self, index):
-        if not isinstance(index, (list, tuple)):
-            index = [index]
-        for idx in index:
-            if idx not in self._index_update_count:
-                self._index_update_count[idx] = self.begin_num_update
-            self._index_update_count[idx] += 1
-            self.num_update = max(self._index_update_count[idx], self.num_update)
+        counts = self._index_update_count
+        for idx in (index if isinstance(index, (list, tuple)) else [index]):
+            counts[idx] = counts.get(idx, self.begin_num_update) + 1
+            if counts[idx] > self.num_update:
+                self.num_update = counts[idx]
+
+    def _multiplier(self, table, attr, index):
+        """precedence: the Parameter object of the index, then the index, then its name"""
+        if index in self.param_dict:
+            return getattr(self.param_dict[index], attr)
+        if index in table:
+            return table[index]
+        if index in self.idx2name:
+            return table.get(self.idx2name[index], 1.0)
+        return None
+
+    def _scaled(self, base, table, attr, indices):
+        out = []
+        for index in indices:
+            m = self._multiplier(table, attr, index)
+            out.append(base if m is None else base * m)
+        return out
 
     def _get_lrs(self, indices):
-        lr = self.lr_scheduler(self.num_update) if self.lr_scheduler is not None else self.lr
-        lrs = [lr for _ in indices]
-        for i, index in enumerate(indices):
-            if index in self.param_dict:
-                lrs[i] *= self.param_dict[index].lr_mult
-            elif index in self.lr_mult:
-                lrs[i] *= self.lr_mult[index]
-            elif index in self.idx2name:
-                lrs[i] *= self.lr_mult.get(self.idx2name[index], 1.0)
-        return lrs
+        return self._scaled(self.learning_rate, self.lr_mult, 'lr_mult', indices)
 
     def _get_lr(self, index):
         return self._get_lrs([index])[0]
 
     def _get_wds(self, indices):
-        wds = [self.wd for _ in indices]
-        for i, index in enumerate(indices):
-            if index in self.param_dict:
-                wds[i] *= self.param_dict[index].wd_mult
-            elif index in self.wd_mult:
-                wds[i] *= self.wd_mult[index]
-            elif index in self.idx2name:
-                wds[i] *= self.wd_mult.get(self.idx2name[index], 1.0)
-        return wds
+        return self._scaled(self.wd, self.wd_mult, 'wd_mult', indices)
 
     def _get_wd(self, index):
         return self._get_wds([index])[0]
@@ -307,33 +296,18 @@ class LARS(Optimizer):
 
     def _get_lrs(self, indices):
         # also remembers the previous global lr for the momentum correction (optimizer.py:842-871)
-        if self.cur_lr is not None:
-            self.last_lr = self.cur_lr
-        lr = self.lr_scheduler(self.num_update) if self.lr_scheduler is not None else self.lr
-        if self.cur_lr is None:
-            self.last_lr = lr
+        lr = self.learning_rate
+        self.last_lr = lr if self.cur_lr is None else self.cur_lr
         self.cur_lr = lr
-        lrs = [lr for _ in indices]
-        for i, index in enumerate(indices):
-            if index in self.param_dict:
-                lrs[i] *= self.param_dict[index].lr_mult
-            elif index in self.lr_mult:
-                lrs[i] *= self.lr_mult[index]
-            elif index in self.idx2name:
-                lrs[i] *= self.lr_mult.get(self.idx2name[index], 1.0)
-        return lrs
+        return self._scaled(lr, self.lr_mult, 'lr_mult', indices)
 
     def set_wd_mult(self, args_wd_mult):
         # only *_weight parameters decay (optimizer.py:873-886)
-        self.wd_mult = {}
-        for n in self.idx2name.values():
-            if not n.endswith('_weight'):
-                self.wd_mult[n] = 0.0
+        self.wd_mult = {n: 0.0 for n in self.idx2name.values() if not n.endswith('_weight')}
         if self.sym_info:
             attr, arg_names = self.sym_info
-            for name in arg_names:
-                if name in attr and '__wd_mult__' in attr[name]:
-                    self.wd_mult[name] = float(attr[name]['__wd_mult__'])
+            self.wd_mult.update({name: float(attr[name]['__wd_mult__']) for name in arg_names
+                                 if name in attr and '__wd_mult__' in attr[name]})
         self.wd_mult.update(args_wd_mult)
 
     create_state_multi_precision = SGD.create_state_multi_precision
@@ -574,7 +548,9 @@ class Test(Optimizer):
 
 
 class Updater(object):
-    """Updater for kvstore (optimizer.py:2071-2161)."""
+    """Updater for kvstore (optimizer.py:2071-2161): owns the per-key optimizer states, creates
+    them on first sight of a key, and hands keys to the optimizer one at a time or -- when the
+    optimizer aggregates -- grouped by dtype in chunks of `aggregate_num`."""
 
     def __init__(self, optimizer):
         self.optimizer = optimizer
@@ -582,59 +558,54 @@ class Updater(object):
         self.states_synced = {}
         self.aggregate_updates = optimizer.aggregate_num > 0
 
+    def _state_for(self, idx, weight):
+        if idx not in self.states:
+            self.states[idx] = self.optimizer.create_state_multi_precision(idx, weight)
+        elif not self.states_synced[idx]:
+            # states restored from a checkpoint live wherever they were saved
+            self.states[idx] = self.sync_state_context(self.states[idx], weight.context)
+        self.states_synced[idx] = True
+        return self.states[idx]
+
     def __call__(self, index, grad, weight):
-        if not isinstance(index, (list, tuple)):
-            indices, grads, weights = [index], [grad], [weight]
-        else:
-            indices, grads, weights = index, grad, weight
+        single = not isinstance(index, (list, tuple))
+        indices = [index] if single else list(index)
+        grads = [grad] if single else grad
+        weights = [weight] if single else weight
         if weights:
             self.optimizer._set_current_context(weights[0].context.device_id)
-        for i, idx in enumerate(indices):
-            if isinstance(idx, bytes):
-                indices[i] = idx.decode('utf-8')
-                idx = indices[i]
-            if idx not in self.states:
-                self.states[idx] = self.optimizer.create_state_multi_precision(idx, weights[i])
-                self.states_synced[idx] = True
-            elif not self.states_synced[idx]:
-                self.states[idx] = self.sync_state_context(self.states[idx], weights[i].context)
-                self.states_synced[idx] = True
-        if self.aggregate_updates:
-            type_map = {}
-            for i, w, g in zip(indices, weights, grads):
-                type_map.setdefault(str(w.dtype), []).append((i, w, g))
-            for idx in type_map:
-                current_index = 0
-                indices, weights, grads = zip(*type_map[idx])
-                while current_index < len(indices):
-                    states = []
-                    step = min(self.optimizer.aggregate_num, len(indices) - current_index)
-                    for j in range(step):
-                        states.append(self.states[indices[current_index + j]])
-                    n = self.optimizer.aggregate_num
-                    self.optimizer.update_multi_precision(
-                        list(indices[current_index:current_index + n]),
-                        list(weights[current_index:current_index + n]),
-                        list(grads[current_index:current_index + n]), states)
-                    current_index += n
-        else:
-            for i, w, g in zip(indices, weights, grads):
-                self.optimizer.update_multi_precision(i, w, g, self.states[i])
+        if any(isinstance(i, bytes) for i in indices):
+            indices = [i.decode('utf-8') if isinstance(i, bytes) else i for i in indices]
+            if isinstance(index, list):
+                index[:] = indices           # the reference decodes byte keys in the caller's list
+        for idx, w in zip(indices, weights):
+            self._state_for(idx, w)
+        if not self.aggregate_updates:
+            for idx, w, g in zip(indices, weights, grads):
+                self.optimizer.update_multi_precision(idx, w, g, self.states[idx])
+            return
+        by_dtype = {}
+        for triple in zip(indices, weights, grads):
+            by_dtype.setdefault(str(triple[1].dtype), []).append(triple)
+        step = self.optimizer.aggregate_num
+        for members in by_dtype.values():
+            for at in range(0, len(members), step):
+                idxs, ws, gs = (list(x) for x in zip(*members[at:at + step]))
+                self.optimizer.update_multi_precision(idxs, ws, gs, [self.states[i] for i in idxs])
 
     def sync_state_context(self, state, context):
         if isinstance(state, NDArray):
             return state.as_in_context(context)
         if isinstance(state, (tuple, list)):
-            synced = (self.sync_state_context(i, context) for i in state)
-            return tuple(synced) if isinstance(state, tuple) else list(synced)
+            return type(state)(self.sync_state_context(i, context) for i in state)
         return state
 
     def set_states(self, states):
-        states = pickle.loads(states)
-        if isinstance(states, tuple) and len(states) == 2:
-            self.states, self.optimizer = states
+        loaded = pickle.loads(states)
+        if isinstance(loaded, tuple) and len(loaded) == 2:
+            self.states, self.optimizer = loaded
         else:
-            self.states = states
+            self.states = loaded
         self.states_synced = dict.fromkeys(self.states.keys(), False)
 
     def get_states(self, dump_optimizer=False):
