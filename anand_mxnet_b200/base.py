@@ -108,5 +108,10 @@ def get_stream(dev_id):
     return s.value or 0
 
 
+def flush_all():
+    """Issue every queued (bucketed) KVStore call now, without waiting for the device."""
+    check_call(_LIB.B200KVFlushAll())
+
+
 def waitall():
     check_call(_LIB.MXNDArrayWaitAll())

@@ -254,6 +254,7 @@ int MXNDArrayGetShapeEx(NDArrayHandle handle, int* out_dim, const int** out_pdat
 
 int MXNDArrayGetData(NDArrayHandle handle, void** out_pdata) {
   API_BEGIN();
+  KVStore::FlushAll();  // the caller is about to look at the memory
   NDArray& a = ND(handle);
   *out_pdata = a.is_none() ? nullptr : a.data();
   API_END();
@@ -743,6 +744,34 @@ int B200KVStoreFlush(KVStoreHandle handle) {
   API_BEGIN();
   KV(handle).Flush();
   API_END();
+}
+
+int B200KVFlushAll(void) {
+  API_BEGIN();
+  KVStore::FlushAll();
+  API_END();
+}
+
+// One call PER KEY, issued from compiled code the way the reference's C++ callers do
+// (cpp-package KVStore::Push/Pull loops; gluon Trainer._allreduce_grads is the python analogue):
+// pattern 0 = pushpull(key i, priority -i) for every i; pattern 1 = push(key i, priority i) for
+// every i, then pull(key i, priority i) for every i (tools/bandwidth/measure.py:112-122).
+int B200KVIssuePerKey(KVStoreHandle handle, mx_uint num, const int* keys, NDArrayHandle* vals,
+                      NDArrayHandle* outs, int pattern) {
+  for (mx_uint i = 0; i < num; ++i) {
+    const int pr = pattern == 0 ? -static_cast<int>(i) : static_cast<int>(i);
+    const int rc = pattern == 0
+        ? MXKVStorePushPull(handle, 1, keys + i, 1, keys + i, vals + i, outs + i, pr)
+        : MXKVStorePush(handle, 1, keys + i, vals + i, pr);
+    if (rc != 0) return rc;
+  }
+  if (pattern != 0) {
+    for (mx_uint i = 0; i < num; ++i) {
+      const int rc = MXKVStorePullWithSparse(handle, 1, keys + i, outs + i, static_cast<int>(i), true);
+      if (rc != 0) return rc;
+    }
+  }
+  return 0;
 }
 
 int B200KVEngineSetStream(int dev_id, void* cuda_stream) {

@@ -178,7 +178,7 @@ class KVStore {
   // ---- fused optimizer (B200 extension)
   void SetOptimizer(const std::string& name,
                     const std::vector<std::pair<std::string, std::string>>& kw);
-  OptConfig& opt() { return opt_; }
+  OptConfig& opt() { Flush(); return opt_; }  // queued calls ran with the old hyper-parameters
   void TouchOpt() { ++opt_version_; }  // call after changing opt() scalars / multipliers
   NDArray GetOptimizerState(int key, int state_id);
   void SetOptimizerState(int key, int state_id, const NDArray& v);
@@ -268,6 +268,8 @@ class KVStore {
   std::vector<PendingOp> pending_;
   std::unordered_set<int> pending_pushed_, pending_pulled_;
   size_t pending_bytes_ = 0, bucket_bytes_ = 0;
+  bool bucket_auto_ = true;                      // queue single-key calls (see the constructor)
+  size_t auto_bucket_bytes_ = static_cast<size_t>(256) << 20;
   uint64_t opt_version_ = 1;   // bumped whenever a hyper-parameter / multiplier changes
   uint64_t layout_epoch_ = 1;  // bumped whenever placement / optimizer kind / updater changes
   std::string gc_type_ = "none";

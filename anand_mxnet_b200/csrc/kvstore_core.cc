@@ -75,7 +75,17 @@ KVStore::KVStore(const std::string& type) : type_(type) {
     rank_ = g->rank();
     group_size_ = g->world();
   }
-  if (const char* b = std::getenv("B200KV_BUCKET_MB")) bucket_bytes_ = static_cast<size_t>(std::atoi(b)) << 20;
+  // Deferred bucket execution. Default ("auto"): calls that name ONE key -- the way Trainer and
+  // tools/bandwidth/measure.py drive the store, one call per parameter -- are queued and fused into
+  // one launch; calls that already carry a key list run at once. B200KV_BUCKET_MB=n queues every
+  // call up to n MB, 0 switches queuing off.
+  if (const char* b = std::getenv("B200KV_BUCKET_MB")) {
+    bucket_bytes_ = static_cast<size_t>(std::max(0, std::atoi(b))) << 20;
+    bucket_auto_ = false;
+  }
+  if (const char* b = std::getenv("B200KV_AUTO_BUCKET_MB")) {
+    auto_bucket_bytes_ = static_cast<size_t>(std::max(1, std::atoi(b))) << 20;
+  }
   LiveStores().insert(this);
 }
 
@@ -134,6 +144,7 @@ void KVStore::InitStr(const std::vector<std::string>& str_keys, const std::vecto
 }
 
 void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>& values) {
+  Flush();
   KV_CHECK_EQ(keys.size(), values.size());
   for (size_t i = 0; i < keys.size(); ++i) {
     KV_CHECK(local_.find(keys[i]) == local_.end())
@@ -167,6 +178,7 @@ void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>&
 }
 
 void KVStore::SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle) {
+  Flush();  // queued calls were issued under the previous updater / optimizer
   updater_ = fn;
   str_updater_ = sfn;
   updater_handle_ = handle;
@@ -178,6 +190,7 @@ void KVStore::SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle) {
 void KVStore::SetGradientCompression(const std::vector<std::pair<std::string, std::string>>& kw) {
   // GradientCompression::SetParams (src/kvstore/gradient_compression.cc:44-60): type in
   // {none, 2bit}, threshold > 0 (default 0.5)
+  Flush();
   std::string type = gc_type_;
   float threshold = gc_threshold_;
   for (auto& kv : kw) {
@@ -208,6 +221,7 @@ static double ParseD(const std::string& s) {
 
 void KVStore::SetOptimizer(const std::string& name,
                            const std::vector<std::pair<std::string, std::string>>& kw) {
+  Flush();
   OptConfig o;
   const std::string n = Lower(name);
   if (n == "sgd") {
@@ -331,7 +345,17 @@ void KVStore::FlushAll() {
 
 bool KVStore::TryDefer(int kind, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
                        const std::vector<int>& okeys, const std::vector<NDArray>& outs, int priority) {
-  if (bucket_bytes_ == 0 || (updater_ != nullptr && !opt_.enabled) || gc_type_ != "none") return false;
+  if ((updater_ != nullptr && !opt_.enabled) || gc_type_ != "none") return false;
+  size_t cap = bucket_bytes_;
+  if (cap == 0) {
+    if (!bucket_auto_) return false;
+    // auto mode: only single-key calls (n values of one key count as one key)
+    const int k0 = !vkeys.empty() ? vkeys[0] : (!okeys.empty() ? okeys[0] : 0);
+    for (int k : vkeys) if (k != k0) return false;
+    for (int k : okeys) if (k != k0) return false;
+    if (vkeys.empty() && okeys.empty()) return false;
+    cap = auto_bucket_bytes_;
+  }
   size_t bytes = 0;
   for (size_t i = 0; i < vkeys.size(); ++i) {
     KeyEntry& e = Entry(vkeys[i]);  // un-initialised keys still fail synchronously
@@ -369,7 +393,7 @@ bool KVStore::TryDefer(int kind, const std::vector<int>& vkeys, const std::vecto
   for (int k : vkeys) pending_pushed_.insert(k);
   for (int k : okeys) pending_pulled_.insert(k);
   pending_bytes_ += bytes;
-  if (pending_bytes_ >= bucket_bytes_) Flush();
+  if (pending_bytes_ >= cap) Flush();
   return true;
 }
 
@@ -401,6 +425,7 @@ void KVStore::Flush() {
 void KVStore::SetBucketBytes(size_t n) {
   Flush();
   bucket_bytes_ = n;
+  bucket_auto_ = false;  // an explicit size (0 = off) replaces the automatic policy
 }
 
 void KVStore::Push(const std::vector<int>& keys, const std::vector<NDArray>& values, int priority) {
@@ -903,6 +928,7 @@ NDArray KVStore::GetOptimizerState(int key, int state_id) {
 }
 
 void KVStore::SetOptimizerState(int key, int state_id, const NDArray& v) {
+  Flush();
   KeyEntry& e = Entry(key);
   if (!e.rsp_devs.empty()) UnshardRsp(e);
   int dev = e.striped ? devset_[0] : e.home;

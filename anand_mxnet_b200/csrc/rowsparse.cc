@@ -248,6 +248,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
 // a CountFence while the retain kernel is already running.
 void KVStore::PullRowSparse(const std::vector<int>& keys, const std::vector<NDArray>& outs,
                             const std::vector<NDArray>& row_ids, int) {
+  Flush();
   KV_CHECK_EQ(keys.size(), outs.size());
   KV_CHECK_EQ(keys.size(), row_ids.size());
   // GroupKVPairsPullRsp (kvstore_local.h:352-371): stable by key, storage types validated

@@ -14,11 +14,20 @@ Printed JSON (one line, rank 0):
              inputs and outputs resident in HBM, timed with CUDA events on the launching stream
   e2e        same metric through the same C-ABI call with HOST buffers (pinned CPU-context
              NDArrays): the H2D copy of the gradients and the D2H copy of the weights are inside
-             the timed region
+             the timed region; e2e.roofline = bytes per PCIe direction / time against the pinned
+             copy rate measured in the same run with both directions busy
   roofline   dominant kernel: ALGORITHMIC bytes per launch (24 B/element for
              SGD-momentum at N=1; all-reduce bus bandwidth per GPU, tools/bandwidth/measure.py:137-138,
              at N>=2) / mean launch duration (CUDA events) against the measured HBM copy bandwidth
              (MEASURED_PEAKS.json) or 900 GB/s/dir NVLink
+  parity     the weights pulled after the first two steps of THIS run compared with the CPU oracle
+             (kvstore('local') model fed the same seeded gradients): bit-exact, or <= 1e-6 relative
+             L1 when the NVSwitch sums (NVLS mode); a failed check makes the run exit non-zero
+  configs    short legs over the other BASELINE.json configs (BERT-base + Adam, row_sparse table
+             1M x 512) with their own roofline / parity blocks
+  frontends  the same step issued the way the reference's callers do: one call PER KEY with
+             priority=-i (gluon/trainer.py:385-396) and push-all-then-pull-all (tools/bandwidth/
+             measure.py:112-122), plus the python front-end's grouped call
   cpu_baseline   the reference's CPU kvstore('local') arithmetic (oracle/_ref, else the oracle
              port) on this box's host cores, bounded sample
 `--impl reference` times that CPU path as the whole job (the driver's reference arm).
@@ -42,6 +51,7 @@ UNIT = "GB/s"
 VALUE_FORMULA = ("n_gpus * (bytes pushed + bytes pulled per GPU) / time = n_gpus * 2 * gradient-set "
                  "bytes / time, identical at every N; roofline.achieved uses the kernel's algorithmic "
                  "bytes (HBM, N=1) or the all-reduce bus bandwidth per GPU (NVLink, N>=2)")
+L2_NOTE = "per-GPU working set of a step > 126 MB L2 (inputs larger than L2), no flush between steps"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -85,9 +95,29 @@ WORKLOADS = {
                       desc="BERT-base gradient set, 199 fp32 tensors / 109482240 elements, Adam "
                            "fused on the store"),
 }
+RSP_DESC = ("row_sparse push + row_sparse_pull, embedding table (1000000, 512) fp32, 10000 distinct hot "
+            "rows per value (1 %), lazy SGD on the store, pull ids unsorted with 5 % duplicates")
 
 SGD_KW = dict(learning_rate=0.1, momentum=0.9, wd=1e-4)
 ADAM_KW = dict(learning_rate=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-8, wd=0.01)
+
+
+def opt_kwargs(workload, n_gpus):
+    if WORKLOADS[workload]["opt"] == "sgd":
+        return "SGD", dict(rescale_grad=1.0 / (256 * n_gpus), **SGD_KW)
+    return "Adam", dict(rescale_grad=1.0 / n_gpus, **ADAM_KW)
+
+
+def kernel_label(workload, n_src, nvls=False):
+    opt = "SGD" if WORKLOADS[workload]["opt"] == "sgd" else "Adam"
+    return "dense_fused_kernel<float,%d,%s>%s" % (1 if nvls else n_src, opt, " [NVLS multimem]" if nvls else "")
+
+
+def config_block(workload, n_values):
+    """`config` is a pure function of (workload, N): both arms of the driver's comparison print the
+    same dict; arm-specific descriptors live under `impl_detail`."""
+    desc = RSP_DESC if workload == "rsp" else WORKLOADS[workload]["desc"]
+    return {"workload": desc, "values_per_key": n_values, "value_formula": VALUE_FORMULA, "l2": L2_NOTE}
 
 
 def payload_bytes(workload, n_gpus):
@@ -104,6 +134,69 @@ def algorithmic_bytes(workload, n_gpus):
         return n_elem * WORKLOADS[workload]["bytes_per_elem"]
     # all-reduce bus bandwidth, per GPU (tools/bandwidth/measure.py:137-138)
     return int(n_elem * 4 * 2 * (n_gpus - 1) / n_gpus)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data (uniform [-1, 1), seeded per role and per GPU) and the oracle check
+# ------------------------------------------------------------------------------------------------
+def flat_set(seed, sizes):
+    """values of every tensor of a set from ONE seeded stream; views of one flat fp32 buffer"""
+    rng = np.random.default_rng(seed)
+    flat = rng.random(int(sum(sizes)), dtype=np.float32)
+    flat *= 2.0
+    flat -= 1.0
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return [flat[offs[i]:offs[i + 1]] for i in range(len(sizes))]
+
+
+def weight_seed():
+    return 0xB200 + 777
+
+
+def grad_seed(rank):
+    return 0xB200 + 1000 * rank
+
+
+def oracle_expected(workload, n_ranks, steps, order="device"):
+    """Weights after `steps` pushes of every rank's (constant) seeded gradient set, computed by the
+    CPU oracle's kvstore('local') model (oracle/kvoracle.py: LocalKVStoreModel; reduce order of the
+    store type, optimizer bookkeeping of python/mxnet/optimizer/optimizer.py). Checker only."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kvoracle as K
+    shapes = WORKLOADS[workload]["shapes"]()
+    sizes = [int(np.prod(s)) for s in shapes]
+    model = K.LocalKVStoreModel(order)
+    w0 = flat_set(weight_seed(), sizes)
+    for k in range(len(sizes)):
+        model.init(k, w0[k])
+    name, kw = opt_kwargs(workload, n_ranks)
+    kw = dict(kw)
+    kw["lr"] = kw.pop("learning_rate")
+    model.set_optimizer(name.lower(), **kw)
+    grads = [flat_set(grad_seed(r), sizes) for r in range(n_ranks)]
+    for _ in range(steps):
+        for k in range(len(sizes)):
+            model.push(k, [grads[r][k] for r in range(n_ranks)])
+    return [model.pull(k) for k in range(len(sizes))]
+
+
+def compare_sets(got, want, exact):
+    """parity block: bit equality, or the reference's own relative L1 bound
+    (tests/nightly/test_kvstore.py:95-98: sum|got - want| / sum|want| < 1e-6)"""
+    num = den = 0.0
+    bad = 0
+    for g, w in zip(got, want):
+        g = np.ascontiguousarray(g, dtype=np.float32).reshape(-1)
+        w = np.ascontiguousarray(w, dtype=np.float32).reshape(-1)
+        if not np.array_equal(g.view(np.uint32), w.view(np.uint32)):
+            bad += 1
+        num += float(np.sum(np.abs(g.astype(np.float64) - w)))
+        den += float(np.sum(np.abs(w.astype(np.float64))))
+    rel = num / den if den > 0 else (0.0 if num == 0 else float("inf"))
+    ok = (bad == 0) if exact else (rel < 1e-6)
+    return {"mode": "bit-exact" if exact else "1e-6 relative L1 (in-switch summation order)",
+            "ok": bool(ok), "max_rel": rel, "tensors": len(want), "tensors_differing": bad,
+            "checker": "oracle/kvoracle.py LocalKVStoreModel (CPU restatement pinned to oracle/_ref)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -173,19 +266,21 @@ def host_cores():
 def best_cpu_threads(workload, n_src):
     """The reference sizes its CPU kernels' OpenMP team from the visible cores
     (engine::OpenMP::GetRecommendedOMPThreadCount); on a big shared host that is far from the
-    fastest choice for 157 mostly-small tensors, so the baseline gets the BEST team size from a
-    short probe (one step each, ascending, stop once clearly past the optimum)."""
+    fastest choice for 157 mostly-small tensors, so the baseline gets the BEST team size of a probe
+    (every power of two up to the visible cores, best of three steps each)."""
     best, best_t = 1, float("inf")
-    cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, host_cores()) if c <= host_cores()})
+    cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, 128, host_cores()) if c <= host_cores()})
     for c in cands:
         step, _, _ = cpu_kvstore_step_fn(workload, n_src, c)
         step()
-        t0 = time.perf_counter()
-        step()
-        dt = time.perf_counter() - t0
+        dt = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            step()
+            dt = min(dt, time.perf_counter() - t0)
         if dt < best_t:
             best, best_t = c, dt
-        elif dt > 2.0 * best_t:
+        elif dt > 3.0 * best_t:
             break
     return best
 
@@ -245,6 +340,9 @@ def cpu_kvstore_step_fn(workload, n_src, threads=None):
 
 def run_reference(args):
     """The reference arm: the reference's own CPU implementation of the path on this box's cores."""
+    if args.workload == "rsp":
+        import bench_rsp
+        return bench_rsp.run_reference(args)
     n_src = max(1, args.gpus)
     step, kind, cores = cpu_kvstore_step_fn(args.workload, n_src, best_cpu_threads(args.workload, n_src))
     for _ in range(args.warmup):
@@ -260,8 +358,11 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload]["desc"], "store": "kvstore('local') on CPU",
-                       "values_per_key": n_src, "value_formula": VALUE_FORMULA},
+            "config": config_block(args.workload, n_src),
+            "impl_detail": {"store": "kvstore('local') on CPU: the reference's own CommCPU reduce and "
+                                     "optimizer kernels (oracle/_ref, compiled in place from "
+                                     "/root/reference) over host buffers",
+                            "omp_team": cores, "omp_team_choice": "best of a probe over powers of two"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": sample, "host_cores_visible": host_cores()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -281,9 +382,244 @@ def measured_peaks():
 
 
 def make_optimizer(mx, workload, n_gpus):
-    if WORKLOADS[workload]["opt"] == "sgd":
-        return mx.optimizer.SGD(rescale_grad=1.0 / (256 * n_gpus), **SGD_KW)
-    return mx.optimizer.Adam(rescale_grad=1.0, **ADAM_KW)
+    name, kw = opt_kwargs(workload, n_gpus)
+    return getattr(mx.optimizer, name)(**kw)
+
+
+def pcie_pinned_copy_peak(torch, dev, nbytes):
+    """Pinned-memory copy rate of this box in GB/s per direction: one direction alone, and with
+    H2D and D2H running at the same time on two streams (the denominator of e2e.roofline: a step
+    moves the gradient set in and the weight set out, both directions busy)."""
+    n = nbytes // 4
+    h_in = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_out = torch.empty(n, dtype=torch.float32).pin_memory()
+    d_in = torch.empty(n, dtype=torch.float32, device=dev)
+    d_out = torch.ones(n, dtype=torch.float32, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    reps = 5
+
+    def timed(both):
+        best = float("inf")
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c, d = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(s1):
+                a.record()
+                d_in.copy_(h_in, non_blocking=True)
+                b.record()
+            if both:
+                with torch.cuda.stream(s2):
+                    c.record()
+                    h_out.copy_(d_out, non_blocking=True)
+                    d.record()
+            torch.cuda.synchronize()
+            t = a.elapsed_time(b)
+            if both:
+                t = max(t, c.elapsed_time(d))
+            best = min(best, t)
+        return nbytes / (best * 1e-3) / 1e9
+    uni = timed(False)
+    bidir = timed(True)
+    return {"h2d_alone_GBps": uni, "per_direction_both_busy_GBps": bidir}
+
+
+def c_step_fn(mx, kv, keys, vals, outs):
+    """the C-ABI entry point itself with prebuilt argument arrays, as a compiled host issues it"""
+    from anand_mxnet_b200.kvstore.base import _ctype_key_value
+    ckeys, cvals, _ = _ctype_key_value(keys, vals)
+    _, couts, _ = _ctype_key_value(keys, outs)
+    lib, handle, nkeys, zero = mx.base._LIB, kv.handle, ctypes.c_uint(len(keys)), ctypes.c_int(0)
+
+    def step(_keep=(ckeys, cvals, couts)):
+        rc = lib.MXKVStorePushPull(handle, nkeys, ckeys, nkeys, ckeys, cvals, couts, zero)
+        if rc != 0:
+            raise RuntimeError(lib.MXGetLastError().decode())
+    return step
+
+
+def per_key_step_fns(mx, kv, keys, vals, outs):
+    """The reference's callers issue one call per key: Trainer._allreduce_grads
+    (python/mxnet/gluon/trainer.py:385-396: pushpull / push+pull of parameter i with priority=-i)
+    and tools/bandwidth/measure.py:112-122 (push every key, then pull every key, priority=i).
+    Issued from compiled code (B200KVIssuePerKey loops over the MXKVStore* entry points), as a C++
+    host would; `python_loop` is the trainer pattern issued call by call through ctypes."""
+    lib, handle = mx.base._LIB, kv.handle
+    n = ctypes.c_uint(len(keys))
+    ck = (ctypes.c_int * len(keys))(*keys)
+    cv = (ctypes.c_void_p * len(keys))(*[v._hv for v in vals])
+    co = (ctypes.c_void_p * len(keys))(*[o._hv for o in outs])
+
+    def issue(pattern):
+        def fn(_keep=(ck, cv, co)):
+            if lib.B200KVIssuePerKey(handle, n, ck, cv, co, ctypes.c_int(pattern)) != 0:
+                raise RuntimeError(lib.MXGetLastError().decode())
+        return fn
+    one = ctypes.c_uint(1)
+    k1 = [(ctypes.c_int * 1)(k) for k in keys]
+    v1 = [(ctypes.c_void_p * 1)(v._hv) for v in vals]
+    o1 = [(ctypes.c_void_p * 1)(o._hv) for o in outs]
+    pr = [ctypes.c_int(-i) for i in range(len(keys))]
+
+    def python_loop():
+        for i in range(len(keys)):
+            if lib.MXKVStorePushPull(handle, one, k1[i], one, k1[i], v1[i], o1[i], pr[i]) != 0:
+                raise RuntimeError(lib.MXGetLastError().decode())
+    return issue(0), issue(1), python_loop
+
+
+def time_region(torch, stream, fn, steps, after=None):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    if after is not None:
+        after()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def device_sets(mx, torch, dev, shapes, host_sets):
+    """one flat device buffer per role, one 512-byte aligned view per tensor -- the arrays stay
+    separate NDArrays, exactly what a framework hands the store"""
+    sizes = [int(np.prod(s)) for s in shapes]
+    offs = np.concatenate([[0], np.cumsum([(n + 127) // 128 * 128 for n in sizes])]).astype(np.int64)
+    res = []
+    for hs in host_sets:
+        if hs is None:
+            flat = torch.empty(int(offs[-1]), device=dev)
+        else:
+            buf = np.zeros(int(offs[-1]), np.float32)
+            for i, n in enumerate(sizes):
+                buf[offs[i]:offs[i] + n] = hs[i]
+            flat = torch.from_numpy(buf).to(dev)
+        views = [flat[int(offs[i]):int(offs[i]) + sizes[i]].view(shapes[i]) for i in range(len(shapes))]
+        res.append((flat, views, [mx.nd.from_torch(t) for t in views]))
+    return res
+
+
+def run_dense_single(mx, torch, stream, args, workload, steps, warmup, full):
+    """One dense workload on one GPU: parity, device-resident timing, and (full) the front-end
+    variants and the host-buffer arm."""
+    dev = torch.device("cuda", 0)
+    shapes = WORKLOADS[workload]["shapes"]()
+    sizes = [int(np.prod(s)) for s in shapes]
+    keys = list(range(len(shapes)))
+    n_elem = sum(sizes)
+    w0 = flat_set(weight_seed(), sizes)
+    g0 = flat_set(grad_seed(0), sizes)
+    (_wf, _wv, w_nd), (_gf, _gv, grads), (_of, outs_t, outs) = device_sets(
+        mx, torch, dev, shapes, [w0, g0, None])
+    kv = mx.kv.create("device")
+    kv.init(keys, w_nd)
+    kv.set_optimizer(make_optimizer(mx, workload, 1))
+    torch.cuda.synchronize()
+    # ---- parity: the first two steps of this very store against the CPU oracle
+    for _ in range(2):
+        kv.pushpull(keys, grads, out=outs)      # python front-end: hands lr / multipliers over
+    mx.nd.waitall()
+    torch.cuda.synchronize()
+    got = [t.cpu().numpy() for t in outs_t]
+    want = oracle_expected(workload, 1, 2)
+    parity = compare_sets(got, want, exact=True)
+    parity["after_steps"] = 2
+
+    step = c_step_fn(mx, kv, keys, grads, outs)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    mx.base.reset_kernel_launch_count()
+    ms_step = time_region(torch, stream, step, steps)
+    launches = mx.base.kernel_launch_count()
+    clocks = sampler.stop()
+    # the timed region is exactly K launches of the dominant kernel back to back on this stream:
+    # its average launch duration (incl. launch gaps) is the region's duration / K
+    alg = algorithmic_bytes(workload, 1)
+    pay = payload_bytes(workload, 1)
+    peaks, peak_src = measured_peaks()
+    achieved = alg / (ms_step * 1e-3) / 1e9
+    res = {"workload": WORKLOADS[workload]["desc"], "ms_per_step": ms_step, "steps": steps,
+           "value": pay / (ms_step * 1e-3) / 1e9, "unit": UNIT, "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                        "traffic_note": "dram bytes per launch are in the committed ncu capture of this "
+                                        "command (profiles/), not re-read at run time",
+                        "kernel": kernel_label(workload, 1), "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_step},
+           "parity": parity, "clocks": clocks}
+    if not full:
+        return res
+
+    # ---- front-ends: python grouped call, and the per-key call patterns of the reference's callers
+    th = time.perf_counter()
+    py_ms = time_region(torch, stream, lambda: kv.pushpull(keys, grads, out=outs), steps)
+    host_py_us = (time.perf_counter() - th) / steps * 1e6
+    th = time.perf_counter()
+    for _ in range(steps):
+        step()
+    host_c_us = (time.perf_counter() - th) / steps * 1e6
+    torch.cuda.synchronize()
+    trainer_pattern, measure_pattern, python_loop = per_key_step_fns(mx, kv, keys, grads, outs)
+    flush = mx.base.flush_all
+    fe = {"python_api_GBps": pay / (py_ms * 1e-3) / 1e9, "python_api_ms_per_step": py_ms,
+          "python_api_host_us_per_call": host_py_us, "c_abi_host_us_per_call": host_c_us}
+    def flushed(fn):
+        # the caller's next read of a weight is what runs a queued bucket; one flush per step
+        # stands in for it (a framework reads the weights in its next forward pass)
+        def g():
+            fn()
+            flush()
+        return g
+    for name, fn, calls in (("per_key_pushpull_priority_minus_i", trainer_pattern, len(keys)),
+                            ("per_key_push_all_then_pull_all", measure_pattern, 2 * len(keys)),
+                            ("per_key_pushpull_python_ctypes_loop", python_loop, len(keys))):
+        try:
+            for _ in range(3):
+                flushed(fn)()
+            torch.cuda.synchronize()
+            mx.base.reset_kernel_launch_count()
+            th = time.perf_counter()
+            ms = time_region(torch, stream, flushed(fn), steps)
+            fe[name] = {"ms_per_step": ms, "GBps": pay / (ms * 1e-3) / 1e9,
+                        "vs_grouped_call": ms / ms_step,
+                        "host_us_per_step": (time.perf_counter() - th) / steps * 1e6,
+                        "calls_per_step": calls,
+                        "kernel_launches_per_step": mx.base.kernel_launch_count() / steps}
+        except Exception as e:  # a front-end variant must not sink the headline
+            fe[name] = {"error": str(e)[:200]}
+    res["frontends"] = fe
+
+    # ---- end-to-end arm: same C-ABI call, HOST (pinned) gradient and weight buffers
+    kv2 = mx.kv.create("device")
+    kv2.init(keys, [mx.nd.array(w0[k].reshape(shapes[k]), mx.cpu()) for k in keys])
+    kv2.set_optimizer(make_optimizer(mx, workload, 1))
+    hgrads = [mx.nd.array(g0[k].reshape(shapes[k]), mx.cpu()) for k in keys]
+    houts = [mx.nd.empty(s, mx.cpu()) for s in shapes]
+    e2e_steps = max(3, min(steps, 10))
+    for _ in range(2):
+        kv2.pushpull(keys, hgrads, out=houts)
+    mx.nd.waitall()
+    e2e_parity = compare_sets([h.asnumpy() for h in houts], want, exact=True)
+    hstep = c_step_fn(mx, kv2, keys, hgrads, houts)
+    hstep()
+    mx.nd.waitall()
+    # the last D2H copies run on the copy-out lane: wait for them before stamping the end event
+    e2e_ms = time_region(torch, stream, hstep, e2e_steps, after=mx.nd.waitall)
+    pcie = pcie_pinned_copy_peak(torch, dev, n_elem * 4)
+    per_dir = n_elem * 4 / (e2e_ms * 1e-3) / 1e9
+    res["e2e"] = {"value": pay / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_elem * 4,
+                  "d2h_bytes_per_step": n_elem * 4, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                  "parity": e2e_parity,
+                  "roofline": {"bound": "pcie", "achieved": per_dir,
+                               "peak": pcie["per_direction_both_busy_GBps"], "unit": "GB/s per direction",
+                               "frac": per_dir / pcie["per_direction_both_busy_GBps"],
+                               "peak_source": "cudaMemcpyAsync pinned<->device, H2D and D2H concurrently, "
+                                              "measured in this run", "h2d_alone_GBps": pcie["h2d_alone_GBps"]}}
+    return res
 
 
 def run_single_gpu(args):
@@ -297,122 +633,34 @@ def run_single_gpu(args):
     torch.cuda.set_stream(stream)
     mx.base.set_stream(0, stream.cuda_stream)
     assert mx.base.get_stream(0) == stream.cuda_stream
-    shapes = WORKLOADS[args.workload]["shapes"]()
-    keys = list(range(len(shapes)))
-    n_elem = sum(int(np.prod(s)) for s in shapes)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(0xB200)
-    sizes = [int(np.prod(s)) for s in shapes]
-    offs = np.concatenate([[0], np.cumsum([(n + 127) // 128 * 128 for n in sizes])]).astype(np.int64)
 
-    def flat_views(fill):
-        """one flat buffer per role (three torch kernels in total), one 512-byte aligned view per
-        tensor -- the arrays stay separate NDArrays, exactly what a framework hands the store"""
-        flat = torch.empty(int(offs[-1]), device=dev)
-        if fill:
-            flat.uniform_(-1, 1, generator=gen)
-        return flat, [flat[int(offs[i]):int(offs[i]) + sizes[i]].view(shapes[i]) for i in range(len(shapes))]
+    if args.workload == "rsp":
+        import bench_rsp
+        line = bench_rsp.run_single_gpu_line(mx, torch, stream, args)
+        print(json.dumps(line))
+        if not line["parity"]["ok"]:
+            sys.exit(3)
+        return
 
-    # ---- device-resident arm
-    kv = mx.kv.create("device")
-    _w_flat, w_views = flat_views(True)
-    kv.init(keys, [mx.nd.from_torch(t) for t in w_views])
-    kv.set_optimizer(make_optimizer(mx, args.workload, 1))
-    _g_flat, grads_t = flat_views(True)
-    _o_flat, outs_t = flat_views(False)
-    grads = [mx.nd.from_torch(t) for t in grads_t]
-    outs = [mx.nd.from_torch(t) for t in outs_t]
-    torch.cuda.synchronize()
-    kv.pushpull(keys, grads, out=outs)      # python front-end once: hands lr / multipliers over
-    # the timed call is the C-ABI entry point itself with prebuilt argument arrays, as a compiled
-    # host would issue it; the python front-end's per-call marshalling is reported separately
-    from anand_mxnet_b200.kvstore.base import _ctype_key_value
-    ckeys, cvals, _ = _ctype_key_value(keys, grads)
-    _, couts, _ = _ctype_key_value(keys, outs)
-    lib, handle, nkeys = mx.base._LIB, kv.handle, ctypes.c_uint(len(keys))
-    zero = ctypes.c_int(0)
-
-    def step():
-        rc = lib.MXKVStorePushPull(handle, nkeys, ckeys, nkeys, ckeys, cvals, couts, zero)
-        if rc != 0:
-            raise RuntimeError(lib.MXGetLastError().decode())
-
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
-    mx.base.reset_kernel_launch_count()
-    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    t_all0.record(stream)
-    for i in range(args.steps):
-        step()
-    t_all1.record(stream)
-    torch.cuda.synchronize()
-    launches = mx.base.kernel_launch_count()
-    clocks = sampler.stop()
-    ms_total = t_all0.elapsed_time(t_all1)
-    ms_step = ms_total / args.steps
-    # the timed region is exactly K launches of the dominant kernel back to back on this stream:
-    # its average launch duration (incl. launch gaps) is the region's duration / K
-    ms_kernel = ms_step
-    alg = algorithmic_bytes(args.workload, 1)
-    pay = payload_bytes(args.workload, 1)
-    value = pay / (ms_step * 1e-3) / 1e9
-    peaks, peak_src = measured_peaks()
-    achieved = alg / (ms_kernel * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": _ncu_traffic(args.workload), "kernel":
-                "dense_fused_kernel<float,1,SGD>" if WORKLOADS[args.workload]["opt"] == "sgd"
-                else "dense_fused_kernel<float,1,Adam>", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_kernel}
-
-    # ---- the same loop through the python front-end (kv.pushpull): includes ctypes marshalling
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    th = time.perf_counter()
-    p0.record(stream)
-    for _ in range(args.steps):
-        kv.pushpull(keys, grads, out=outs)
-    p1.record(stream)
-    host_py_us = (time.perf_counter() - th) / args.steps * 1e6
-    torch.cuda.synchronize()
-    py_ms = p0.elapsed_time(p1) / args.steps
-    th = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    host_c_us = (time.perf_counter() - th) / args.steps * 1e6
-    torch.cuda.synchronize()
-    frontends = {"python_api_GBps": pay / (py_ms * 1e-3) / 1e9, "python_api_ms_per_step": py_ms,
-                 "python_api_host_us_per_call": host_py_us, "c_abi_host_us_per_call": host_c_us}
-
-    # ---- end-to-end arm: same C-ABI call, HOST (pinned) gradient and weight buffers
-    kv2 = mx.kv.create("device")
-    kv2.init(keys, [mx.nd.array(np.zeros(s, np.float32), mx.cpu()) for s in shapes])
-    kv2.set_optimizer(make_optimizer(mx, args.workload, 1))
-    rng = np.random.default_rng(0xB200)
-    hgrads = [mx.nd.array(rng.uniform(-1, 1, s).astype(np.float32), mx.cpu()) for s in shapes]
-    houts = [mx.nd.empty(s, mx.cpu()) for s in shapes]
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        kv2.pushpull(keys, hgrads, out=houts)
-    mx.nd.waitall()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        kv2.pushpull(keys, hgrads, out=houts)
-    mx.nd.waitall()        # the last D2H copies run on the copy-out lane: wait before stamping
-    e1.record(stream)
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
-    e2e = {"value": pay / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_elem * 4,
-           "d2h_bytes_per_step": n_elem * 4, "ms_per_step": e2e_ms, "steps": e2e_steps}
+    main = run_dense_single(mx, torch, stream, args, args.workload, args.steps, args.warmup, full=True)
+    configs = {}
+    if not args.no_config_legs:
+        other = "bert_adam" if args.workload == "resnet50_sgd" else "resnet50_sgd"
+        try:
+            leg = run_dense_single(mx, torch, stream, args, other, max(3, min(args.steps, 10)), 3, full=False)
+            configs[other] = leg
+        except Exception as e:
+            configs[other] = {"error": str(e)[:300]}
+        try:
+            import bench_rsp
+            configs["rsp"] = bench_rsp.run_single_gpu_leg(mx, torch, stream, max(5, min(args.steps, 20)))
+        except Exception as e:
+            configs["rsp"] = {"error": str(e)[:300]}
 
     # ---- cpu baseline (bounded sample, rank 0, N=1)
     cpu = None
     if not args.no_cpu_baseline:
+        pay = payload_bytes(args.workload, 1)
         cstep, kind, cores = cpu_kvstore_step_fn(args.workload, 1, best_cpu_threads(args.workload, 1))
         cstep()
         t0 = time.perf_counter()
@@ -424,33 +672,24 @@ def run_single_gpu(args):
         cpu = {"value": pay / cdt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": "%d full steps of %s (reduce of 1 value + optimizer + copy-out per key), "
                          "%.1f ms/step" % (n, args.workload, cdt * 1e3)}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+    line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload]["desc"], "store": "kvstore('device')",
-                       "call": "one grouped MXKVStorePushPull (C ABI, prebuilt argument arrays) over "
-                               "all keys per step; python front-end timing under 'frontends'",
-                       "l2": "working set %.0f MB per step > 126 MB L2, no flush needed" % (alg / 1e6),
-                       "value_formula": VALUE_FORMULA,
-                       "optimizer": SGD_KW if WORKLOADS[args.workload]["opt"] == "sgd" else ADAM_KW},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "frontends": frontends}
+            "config": config_block(args.workload, 1),
+            "impl_detail": {"store": "kvstore('device')",
+                            "call": "one grouped MXKVStorePushPull (C ABI, prebuilt argument arrays) over "
+                                    "all keys per step; per-key call patterns and the python front-end "
+                                    "under 'frontends'",
+                            "optimizer": opt_kwargs(args.workload, 1)[1]},
+            "roofline": main["roofline"], "parity": main["parity"], "cpu_baseline": cpu, "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"], "clocks": main["clocks"], "frontends": main["frontends"],
+            "configs": configs}
     print(json.dumps(line))
-
-
-def _ncu_traffic(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture of THIS workload
-    (profiles/r01_dense_fused_traffic.json holds the ResNet-50 SGD-momentum launch), else None."""
-    if workload != "resnet50_sgd":
-        return None
-    p = os.path.join(ROOT, "profiles", "r01_dense_fused_traffic.json")
-    if os.path.exists(p):
-        try:
-            with open(p) as f:
-                return json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+    ok = main["parity"]["ok"] and main["e2e"]["parity"]["ok"] and all(
+        c.get("parity", {}).get("ok", True) for c in configs.values())
+    if not ok:
+        sys.stderr.write("bench.py: PARITY FAILURE against the oracle\n")
+        sys.exit(3)
 
 
 def main():
@@ -459,11 +698,16 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="resnet50_sgd", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="resnet50_sgd", choices=sorted(WORKLOADS) + ["rsp"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config-legs", action="store_true",
+                    help="skip the short legs over the other BASELINE configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is entitled to all host
+        # threads (it sizes its OpenMP teams itself), so drop the cap before libgomp loads
+        os.environ.pop("OMP_NUM_THREADS", None)
         if rank == 0:
             run_reference(args)
         return

@@ -205,11 +205,21 @@ B200KV_DLL int B200KVStoreSetOptimizerState(KVStoreHandle handle, int key, int s
 B200KV_DLL int B200KVStoreGetUpdateCount(KVStoreHandle handle, int key, int* out);
 B200KV_DLL int B200KVStoreSetUpdateCount(KVStoreHandle handle, int key, int count);
 
-/* Deferred bucket execution: with max_bytes > 0, push/pull/pushpull calls are queued and fused
- * into one launch per device when the queued bytes reach max_bytes, when a queued array is waited
- * on / read, or on B200KVStoreFlush. 0 (default) executes each C call as one fused launch. */
+/* Deferred bucket execution: push/pull/pushpull calls are queued and fused into one launch per
+ * device when the queued bytes reach the bucket size, when any array is waited on / read / exported,
+ * when the store's configuration changes, or on B200KVStoreFlush. Default policy ("auto"): calls
+ * that name ONE key are queued (bucket 256 MB, B200KV_AUTO_BUCKET_MB), calls carrying a key list run
+ * at once as one fused launch. max_bytes > 0 queues every call up to max_bytes; 0 switches queuing
+ * off. Env B200KV_BUCKET_MB=n sets the same at store creation. Results are identical either way:
+ * queued calls of one key keep their order, higher priority keys are issued first. */
 B200KV_DLL int B200KVStoreSetBucketBytes(KVStoreHandle handle, size_t max_bytes);
 B200KV_DLL int B200KVStoreFlush(KVStoreHandle handle);
+B200KV_DLL int B200KVFlushAll(void);   /* every store of the process; does not wait for the device */
+/* Issues one call PER KEY from compiled code, as the reference's callers do: pattern 0 =
+ * pushpull(key i, priority -i) (python/mxnet/gluon/trainer.py:385-396), pattern 1 = push of every
+ * key then pull of every key with priority i (tools/bandwidth/measure.py:112-122). */
+B200KV_DLL int B200KVIssuePerKey(KVStoreHandle handle, mx_uint num, const int* keys,
+                                 NDArrayHandle* vals, NDArrayHandle* outs, int pattern);
 
 /* Stream interop: make the engine issue all work for GPU `dev_id` on a caller-owned cudaStream_t
  * (e.g. torch.cuda.current_stream().cuda_stream) so KVStore work is ordered with the framework
