@@ -16,6 +16,11 @@
 #include <cstdio>
 #include <cstring>
 
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+
 #include "kvstore.h"
 #include "ndarray.h"
 #include "ops.h"
@@ -491,6 +496,138 @@ int MXImperativeInvokeEx(AtomicSymbolCreator creator, int num_inputs, NDArrayHan
 // ------------------------------------------------------------------------------------------ KVStore
 int MXInitPSEnv(mx_uint, const char**, const char**) { return 0; }
 
+// ------------------------------------------------------------------------------------------ engine ABI
+// MXEnginePushAsyncND / MXEnginePushSyncND (include/mxnet/c_api.h:3323-3351, src/c_api/c_api.cc:
+// 2396-2513): how an external scheduler (a Horovod-style plugin) joins the dependency graph. On
+// the lane engine an external operation is ordered like the library's own: its reads wait for the
+// arrays' writers, its writes for writers and readers; on a GPU context those waits are stream
+// waits on the device's compute lane and the function receives that lane's stream in rctx->stream
+// (work it enqueues there is ordered by the stream; on_complete may be called at once). On a CPU
+// context the dependencies are awaited on the host before the function runs. The push returns once
+// the function has signalled completion; a failure it reports (or throws) is parked on the arrays
+// it was to write and surfaces at the next wait on them (threaded_engine.h:380-387).
+namespace {
+struct RunCtxABI {       // layout of mxnet::RunContext (include/mxnet/base.h:350-365)
+  int32_t dev_type, dev_id;
+  void* stream;          // the compute lane's cudaStream_t on a GPU context, else NULL
+  void* aux_stream;
+  bool is_bulk;
+};
+struct PendingExt {
+  std::mutex m;
+  std::condition_variable cv;
+  bool done = false, failed = false;
+  std::string msg;
+};
+struct OnCompleteABI {   // layout of mxnet::engine::CallbackOnComplete (include/mxnet/engine.h:73-90)
+  void (*callback)(void* engine, void* param, const void* error);
+  void* engine;
+  void* param;
+};
+void ExtOnComplete(void*, void* param, const void* error) {
+  PendingExt* p = static_cast<PendingExt*>(param);
+  std::lock_guard<std::mutex> lk(p->m);
+  if (error != nullptr) {  // const dmlc::Error* : a std::runtime_error
+    p->failed = true;
+    p->msg = static_cast<const std::exception*>(error)->what();
+  }
+  p->done = true;
+  p->cv.notify_all();
+}
+
+int PushExternal(void (*async_fn)(void*, void*, void*), void (*sync_fn)(void*, void*), void* func_param,
+                 EngineFuncParamDeleter deleter, ContextHandle ctx_handle, NDArrayHandle* const_nds,
+                 int num_const, NDArrayHandle* mutable_nds, int num_mutable, const char* opr_name) {
+  std::shared_ptr<void> keep(func_param, deleter ? deleter : [](void*) {});
+  KVStore::FlushAll();
+  KV_CHECK(ctx_handle != nullptr) << "MXEnginePush*: null context";
+  const int32_t* c = static_cast<const int32_t*>(ctx_handle);
+  const Context ctx = MakeCtx(c[0], c[1]);
+  Engine* eng = Engine::Get();
+  std::vector<Var*> rd, wr;
+  for (int i = 0; i < num_const; ++i) if (!ND(const_nds[i]).is_none()) rd.push_back(ND(const_nds[i]).var());
+  for (int i = 0; i < num_mutable; ++i) if (!ND(mutable_nds[i]).is_none()) wr.push_back(ND(mutable_nds[i]).var());
+  // an operation whose inputs carry a parked failure is not run; the failure moves to its outputs
+  // (ThreadedEngine::OnStart / OnComplete exception propagation)
+  for (Var* v : rd) {
+    if (v->err && !v->err->empty()) {
+      for (Var* w : wr) eng->SetError(w, *v->err);
+      return 0;
+    }
+  }
+  const bool gpu = ctx.dev_type == kGPU;
+  const int lane = gpu ? ctx.dev_id : -1;
+  RunCtxABI rctx{ctx.dev_type, ctx.dev_id, nullptr, nullptr, false};
+  if (gpu) {
+    for (Var* v : rd) eng->BeginRead(lane, *v);
+    for (Var* v : wr) eng->BeginWrite(lane, *v);
+    rctx.stream = eng->Stream(lane);
+  } else {
+    for (Var* v : rd) eng->WaitToRead(*v);
+    for (Var* v : wr) eng->WaitToWrite(*v);
+  }
+  PendingExt pend;
+  OnCompleteABI oc{ExtOnComplete, eng, &pend};
+  try {
+    if (async_fn != nullptr) {
+      async_fn(&rctx, &oc, func_param);
+      std::unique_lock<std::mutex> lk(pend.m);
+      pend.cv.wait(lk, [&] { return pend.done; });
+    } else {
+      sync_fn(&rctx, func_param);
+    }
+  } catch (const std::exception& e) {
+    pend.failed = true;
+    pend.msg = e.what();
+  }
+  if (gpu) {
+    const uint64_t seq = eng->Issue(lane);
+    for (Var* v : rd) eng->MarkRead(lane, seq, v);
+    for (Var* v : wr) eng->MarkWrite(lane, seq, v);
+  }
+  if (pend.failed) {
+    const std::string msg = std::string("operator ") + (opr_name ? opr_name : "<external>") + ": " + pend.msg;
+    for (Var* w : wr) eng->SetError(w, msg);
+  }
+  return 0;
+}
+}  // namespace
+
+int MXEnginePushAsyncND(EngineAsyncFunc async_func, void* func_param, EngineFuncParamDeleter deleter,
+                        ContextHandle ctx_handle, NDArrayHandle* const_nds_handle, int num_const_nds,
+                        NDArrayHandle* mutable_nds_handle, int num_mutable_nds,
+                        EngineFnPropertyHandle, int, const char* opr_name, bool) {
+  API_BEGIN();
+  KV_CHECK(async_func != nullptr);
+  PushExternal(async_func, nullptr, func_param, deleter, ctx_handle, const_nds_handle, num_const_nds,
+               mutable_nds_handle, num_mutable_nds, opr_name);
+  API_END();
+}
+
+int MXEnginePushSyncND(EngineSyncFunc sync_func, void* func_param, EngineFuncParamDeleter deleter,
+                       ContextHandle ctx_handle, NDArrayHandle* const_nds_handle, int num_const_nds,
+                       NDArrayHandle* mutable_nds_handle, int num_mutable_nds, EngineFnPropertyHandle, int,
+                       const char* opr_name) {
+  API_BEGIN();
+  KV_CHECK(sync_func != nullptr);
+  PushExternal(nullptr, sync_func, func_param, deleter, ctx_handle, const_nds_handle, num_const_nds,
+               mutable_nds_handle, num_mutable_nds, opr_name);
+  API_END();
+}
+
+int B200KVEngineOnComplete(void* on_complete, const char* error) {
+  API_BEGIN();
+  KV_CHECK(on_complete != nullptr);
+  const OnCompleteABI* oc = static_cast<const OnCompleteABI*>(on_complete);
+  if (error != nullptr) {
+    const std::runtime_error e(error);
+    oc->callback(oc->engine, oc->param, &e);
+  } else {
+    oc->callback(oc->engine, oc->param, nullptr);
+  }
+  API_END();
+}
+
 int MXKVStoreCreate(const char* type, KVStoreHandle* out) {
   API_BEGIN();
   *out = new KVStore(type);
@@ -674,27 +811,43 @@ int B200KVStoreSetOptimizer(KVStoreHandle handle, const char* name, mx_uint num_
 
 int B200KVStoreSetLearningRate(KVStoreHandle handle, double lr) {
   API_BEGIN();
-  KV(handle).opt().lr = lr;
-  KV(handle).TouchOpt();
+  if (KV(handle).opt_view().lr != lr) {   // re-sent every step by front-ends: only a change matters
+    KV(handle).opt().lr = lr;
+    KV(handle).TouchOpt();
+  }
   API_END();
 }
 
 int B200KVStoreSetRescaleGrad(KVStoreHandle handle, double rescale_grad) {
   API_BEGIN();
-  KV(handle).opt().rescale = rescale_grad;
-  KV(handle).TouchOpt();
+  if (KV(handle).opt_view().rescale != rescale_grad) {
+    KV(handle).opt().rescale = rescale_grad;
+    KV(handle).TouchOpt();
+  }
   API_END();
 }
 
 int B200KVStoreSetKeyMultipliers(KVStoreHandle handle, mx_uint num, const int* keys,
                                  const double* lr_mult, const double* wd_mult) {
   API_BEGIN();
-  OptConfig& o = KV(handle).opt();
-  for (mx_uint i = 0; i < num; ++i) {
-    if (lr_mult) o.lr_mult[keys[i]] = lr_mult[i];
-    if (wd_mult) o.wd_mult[keys[i]] = wd_mult[i];
+  const OptConfig& cur = KV(handle).opt_view();
+  bool changed = false;
+  for (mx_uint i = 0; i < num && !changed; ++i) {
+    auto differs = [&](const std::unordered_map<int, double>& m, const double* v) {
+      if (v == nullptr) return false;
+      auto it = m.find(keys[i]);
+      return (it == m.end() ? 1.0 : it->second) != v[i];   // an absent multiplier is 1
+    };
+    changed = differs(cur.lr_mult, lr_mult) || differs(cur.wd_mult, wd_mult);
   }
-  KV(handle).TouchOpt();
+  if (changed) {
+    OptConfig& o = KV(handle).opt();
+    for (mx_uint i = 0; i < num; ++i) {
+      if (lr_mult) o.lr_mult[keys[i]] = lr_mult[i];
+      if (wd_mult) o.wd_mult[keys[i]] = wd_mult[i];
+    }
+    KV(handle).TouchOpt();
+  }
   API_END();
 }
 
@@ -719,9 +872,13 @@ int B200KVStoreSetOptimizerState(KVStoreHandle handle, int key, int state_id, ND
 
 int B200KVStoreGetUpdateCount(KVStoreHandle handle, int key, int* out) {
   API_BEGIN();
-  OptConfig& o = KV(handle).opt();
-  auto it = o.count.find(key);
-  *out = it == o.count.end() ? o.begin_num_update : it->second;
+  *out = KV(handle).UpdateCount(key);
+  API_END();
+}
+
+int B200KVStoreGetNumUpdate(KVStoreHandle handle, int* out) {
+  API_BEGIN();
+  *out = KV(handle).NumUpdate();
   API_END();
 }
 

@@ -39,6 +39,7 @@ NDArray KVStore::CompressedReduce(KeyEntry& e, const std::vector<NDArray>& srcs_
       // buf.residual[i] = 0 on the source's device (comm.h:569-571)
       res = NDArray(e.shape, Context::GPU(d), kFloat32);
       DeviceGuard g(d);
+      eng->BeginWrite(d, *res.var());   // first writer of a possibly recycled block
       KV_CUDA(cudaMemsetAsync(res.data(), 0, res.ByteSize(), eng->Stream(d)));
       eng->MarkWrite(d, eng->Issue(d), res.var());
       e.gc_compressed[i] = NDArray({words}, Context::GPU(d), kInt32);

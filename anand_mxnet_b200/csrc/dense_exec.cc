@@ -101,7 +101,7 @@ bool KVStore::CallSignature(int tag, const std::vector<int>& vkeys, const std::v
                             const std::vector<int>* okeys, const std::vector<NDArray>* outs,
                             std::vector<uint64_t>* sig) {
   sig->clear();
-  sig->reserve(4 + 2 * vkeys.size() + (okeys ? 2 * okeys->size() : 0));
+  sig->reserve(4 + 3 * vkeys.size() + (okeys ? 3 * okeys->size() : 0));
   sig->push_back(static_cast<uint64_t>(tag));
   sig->push_back(vkeys.size());
   for (size_t i = 0; i < vkeys.size(); ++i) {
@@ -109,6 +109,7 @@ bool KVStore::CallSignature(int tag, const std::vector<int>& vkeys, const std::v
     if (a.is_none() || a.stype() != kDefaultStorage) return false;  // row_sparse: slow path
     sig->push_back(static_cast<uint64_t>(static_cast<int64_t>(vkeys[i])));
     sig->push_back(reinterpret_cast<uint64_t>(a.storage()) ^ (reinterpret_cast<uint64_t>(a.data()) << 1));
+    sig->push_back(static_cast<uint64_t>(a.Size()) * 16 + static_cast<uint64_t>(a.dtype()));  // a view of another length must not hit
   }
   sig->push_back(0xfeedULL);
   if (okeys != nullptr) {
@@ -117,6 +118,7 @@ bool KVStore::CallSignature(int tag, const std::vector<int>& vkeys, const std::v
       if (a.is_none() || a.stype() != kDefaultStorage) return false;
       sig->push_back(static_cast<uint64_t>(static_cast<int64_t>((*okeys)[i])));
       sig->push_back(reinterpret_cast<uint64_t>(a.storage()) ^ (reinterpret_cast<uint64_t>(a.data()) << 1));
+      sig->push_back(static_cast<uint64_t>(a.Size()) * 16 + static_cast<uint64_t>(a.dtype()));
     }
   }
   return true;
@@ -141,7 +143,22 @@ bool KVStore::RunCachedCall(const std::vector<uint64_t>& sig) {
 }
 
 void KVStore::StoreCachedCall(const std::vector<uint64_t>& sig, std::vector<Prepared>&& launches) {
-  if (call_cache_.size() > 64) call_cache_.clear();
+  // A cached call keeps its operand arrays alive. Training loops repeat a handful of signatures;
+  // imperative use with fresh gradient arrays every step would otherwise pin one gradient set per
+  // entry: first drop the entries nobody but the cache still holds operands of, then cap the size.
+  if (call_cache_.size() >= 8) {
+    for (auto it = call_cache_.begin(); it != call_cache_.end();) {
+      bool orphan = false;
+      for (auto& p : it->second->launches) {
+        for (auto& op : p.ops) {
+          for (auto& a : op.srcs) orphan = orphan || a.use_count() <= 1;
+          for (auto& a : op.outs) orphan = orphan || a.use_count() <= 1;
+        }
+      }
+      it = orphan ? call_cache_.erase(it) : std::next(it);
+    }
+  }
+  if (call_cache_.size() > 32) call_cache_.clear();
   auto c = std::make_shared<CachedCall>();
   c->sig = sig;
   c->launches = std::move(launches);
@@ -362,11 +379,7 @@ void KVStore::RunPrepared(Prepared& P) {
       // one rank per GPU: in-kernel start/end barriers on the IPC signal pads order the ranks
       PeerGroup* g = PeerGroup::Get();
       KV_CHECK(g != nullptr) << "the peer group was destroyed while a store still uses it";
-      L.signal_pads = g->d_pads();
-      L.counter = g->d_counter();
-      L.rank = g->rank();
-      L.world = g->world();
-      L.epoch = g->NextEpoch();
+      g->FillLaunch(&L);
     }
     L.keys = static_cast<const KeyDesc*>(pd.d_keys);
     L.chunks = static_cast<const ChunkDesc*>(pd.d_chunks);

@@ -121,13 +121,28 @@ void Engine::MarkRead(int sid, uint64_t seq, Var* v) {
 
 void Engine::MarkWrite(int sid, uint64_t seq, Var* v) {
   v->writer = Tag{sid, seq};
+  if (v->err) v->err.reset();  // a new writer supersedes the failed one
   if (v->has_readers) {
     for (int e = 0; e < kMaxStreams; ++e) v->reader_seq[e] = 0;
     v->has_readers = false;
   }
 }
 
-void Engine::WaitToRead(const Var& v) { HostWait(v.writer); }
+// Re-throw (once) the failure parked on `v`; mirrors ThreadedEngine::WaitForVar, which rethrows the
+// var's exception and clears it (src/engine/threaded_engine.cc:375-420).
+static void ThrowParked(const Var& v, std::shared_ptr<std::string>* global) {
+  if (!v.err || v.err->empty()) return;
+  const std::string msg = *v.err;
+  v.err->clear();  // shared with every copy of the record: reported once
+  if (*global && (*global)->empty()) global->reset();
+  KV_FATAL << msg;
+}
+
+void Engine::WaitToRead(const Var& v) {
+  HostWait(v.writer);
+  CheckDeviceError();
+  ThrowParked(v, &global_err_);
+}
 
 void Engine::WaitToWrite(const Var& v) {
   HostWait(v.writer);
@@ -136,6 +151,37 @@ void Engine::WaitToWrite(const Var& v) {
       if (v.reader_seq[e]) HostWait(Tag{e, v.reader_seq[e]});
     }
   }
+  CheckDeviceError();
+  ThrowParked(v, &global_err_);
+}
+
+void Engine::SetError(Var* v, const std::string& msg) {
+  v->err = std::make_shared<std::string>(msg);
+  if (!global_err_ || global_err_->empty()) global_err_ = v->err;
+}
+
+uint32_t* Engine::DeviceErrorWord() {
+  if (dev_err_ == nullptr) {
+    void* p = nullptr;
+    KV_CUDA(cudaHostAlloc(&p, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    dev_err_ = static_cast<volatile uint32_t*>(p);
+    dev_err_[0] = 0;
+    dev_err_[1] = 0;
+  }
+  void* d = nullptr;
+  KV_CUDA(cudaHostGetDevicePointer(&d, const_cast<uint32_t*>(dev_err_), 0));
+  return static_cast<uint32_t*>(d);
+}
+
+void Engine::CheckDeviceError() {
+  if (dev_err_ == nullptr || dev_err_[0] == 0) return;
+  const uint32_t code = dev_err_[0], info = dev_err_[1];
+  dev_err_[0] = 0;
+  dev_err_[1] = 0;
+  KV_FATAL << "one-rank-per-GPU store: this rank waited longer than B200KV_PEER_TIMEOUT_S for rank "
+           << (code - 1) << " inside a fused kernel (barrier phase " << (info >> 31) << ", epoch "
+           << (info & 0x7fffffffu) << "): the peer never launched the matching call, or died. "
+           << "Results of the affected call are undefined; the process itself stays usable";
 }
 
 void Engine::WaitAll() {
@@ -147,6 +193,13 @@ void Engine::WaitAll() {
     uint64_t upto = d.issued;
     KV_CUDA(cudaStreamSynchronize(d.cur));
     d.completed = std::max(d.completed, upto);
+  }
+  CheckDeviceError();
+  if (global_err_ && !global_err_->empty()) {   // WaitForAll rethrows any pending failure
+    const std::string msg = *global_err_;
+    global_err_->clear();
+    global_err_.reset();
+    KV_FATAL << msg;
   }
 }
 
@@ -224,6 +277,7 @@ void Engine::Free(int dev, void* p, size_t bytes, const Var* last_use) {
   b.p = p;
   if (last_use != nullptr) {
     b.pending = *last_use;
+    b.pending.err.reset();
   } else {
     b.pending.writer = Tag{dev, lanes_[dev].issued};
   }

@@ -19,7 +19,9 @@
 // cudaEventSynchronize.
 #pragma once
 #include <map>
+#include <memory>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.h"
@@ -38,6 +40,9 @@ struct Var {
   Tag writer;
   uint64_t reader_seq[kMaxStreams] = {0};  // last read issued on each lane
   bool has_readers = false;
+  // deferred failure of the asynchronous operation that last wrote the array: re-thrown by the
+  // next wait on it (src/engine/threaded_engine.h:380-387, ThrowException / var_exception)
+  std::shared_ptr<std::string> err;
 };
 
 class Engine {
@@ -65,6 +70,14 @@ class Engine {
   void WaitToRead(const Var& v);
   void WaitToWrite(const Var& v);
   void WaitAll();
+  // ---- deferred errors. An asynchronous operation that fails cannot report to the call that
+  // enqueued it; the failure is parked on the arrays it was to write and re-thrown (once) by the
+  // next WaitToRead / WaitToWrite of such an array, or by WaitAll.
+  void SetError(Var* v, const std::string& msg);
+  // device-side failures (a peer-barrier time-out inside a kernel) land in a pinned host word the
+  // kernels can write; every host wait checks it. Returns the device-visible pointer.
+  uint32_t* DeviceErrorWord();
+  void CheckDeviceError();
   // Full barrier among lanes: everything issued so far on any of them completes before anything
   // issued afterwards on any of them starts (2N event operations, not N^2).
   void JoinStreams(const std::vector<int>& sids);
@@ -121,6 +134,8 @@ class Engine {
   std::vector<DevMem> mem_;
   int ndev_ = 0;
   std::multimap<size_t, void*> pinned_pool_;
+  std::shared_ptr<std::string> global_err_;   // first unreported deferred failure (for WaitAll)
+  volatile uint32_t* dev_err_ = nullptr;      // pinned + mapped
   bool peer_[kMaxDevices][kMaxDevices] = {{false}};
   bool inited_ = false;
   std::recursive_mutex mu_;

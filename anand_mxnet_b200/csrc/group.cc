@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "engine.h"
+#include "kernels.h"
 
 namespace b200kv {
 
@@ -131,6 +132,24 @@ void PeerGroup::Destroy() {
   // the arena itself is left to process teardown: pooled blocks carved from it may still be cached
   g_group = nullptr;
   delete g;
+}
+
+void PeerGroup::FillLaunch(DenseLaunch* L) {
+  // B200KV_PEER_TIMEOUT_S: how long a rank waits inside a kernel for a peer that has not launched
+  // the matching call before it reports an error (0 = wait for ever, like NCCL). Default 10 min.
+  static const unsigned long long timeout_ns = []() {
+    const char* z = std::getenv("B200KV_PEER_TIMEOUT_S");
+    const double s = z ? std::atof(z) : 600.0;
+    return s <= 0 ? 0ULL : static_cast<unsigned long long>(s * 1e9);
+  }();
+  L->signal_pads = d_pads_;
+  L->counter = d_counter_;
+  L->rank = rank_;
+  L->world = world_;
+  L->epoch = NextEpoch();
+  L->timeout_ns = timeout_ns;
+  DeviceGuard guard(dev_);
+  L->err_word = Engine::Get()->DeviceErrorWord();
 }
 
 void* PeerGroup::ArenaAlloc(size_t bytes) {

@@ -65,6 +65,8 @@ class PeerGroup {
   uint32_t* const* d_pads() const { return d_pads_; }  // device array [world] of pad pointers
   uint32_t* d_counter() const { return d_counter_; }   // "CTAs finished" counter of this rank
   uint32_t NextEpoch() { return ++epoch_; }
+  // barrier part of a fused launch: pads, counter, rank / world, a fresh epoch, the time-out policy
+  void FillLaunch(struct DenseLaunch* L);
 
  private:
   PeerGroup() {}

@@ -76,6 +76,11 @@ struct DenseLaunch {
   uint32_t* counter = nullptr;             // this rank's finished-CTA counter
   int rank = 0, world = 1;
   uint32_t epoch = 0;
+  // a rank that waits longer than timeout_ns for a peer writes (peer + 1, phase/epoch) into the
+  // host-visible err_word, stops waiting and lets the kernel finish: the host raises a recoverable
+  // error at its next wait instead of the context dying in a __trap
+  uint32_t* err_word = nullptr;
+  unsigned long long timeout_ns = 0;
 };
 
 // Fused reduce (+scale/clip +optimizer step) (+broadcast) over a list of chunks, one CTA per chunk.
@@ -127,7 +132,9 @@ struct RspSources {
   int64_t start[kMaxSrc + 1];  // prefix of the row counts; start[nsrc] = total
   int nsrc = 0;
 };
-size_t RspMergeWorkspaceBytes(int64_t total_ids);
+// id_bits / nsrc / [lo, hi) as passed to LaunchRspMerge: they decide between the bitmap union
+// (tables of up to 8 M rows per range) and the radix-sort union
+size_t RspMergeWorkspaceBytes(int64_t total_ids, int id_bits, int nsrc, int64_t lo = 0, int64_t hi = INT64_MAX);
 void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_t* out_idx,
                     float* out_val, int64_t* d_nnr, void* workspace, size_t workspace_bytes,
                     cudaStream_t stream, const RspUpdateLaunch* fused_update = nullptr,
@@ -148,7 +155,7 @@ struct RetainItem {
   // (shard base - first_row*row_len, so that vbase[id / rows_per_shard] + id*row_len is row id)
   const float* const* shard_vbase; int64_t rows_per_shard;
 };
-size_t RetainBatchWorkspaceBytes(int nitems, int64_t total_ids);
+size_t RetainBatchWorkspaceBytes(int nitems, int64_t total_ids, int id_bits);
 // d_items: device copy of `nitems` RetainItem (inside the workspace, filled by the callee from
 // h_items); d_off: device int64[nitems + 1]
 void LaunchUniqueBatch(const RetainItem* h_items, int nitems, int64_t total_ids, int id_bits,

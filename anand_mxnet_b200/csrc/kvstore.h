@@ -178,7 +178,12 @@ class KVStore {
   // ---- fused optimizer (B200 extension)
   void SetOptimizer(const std::string& name,
                     const std::vector<std::pair<std::string, std::string>>& kw);
-  OptConfig& opt() { Flush(); return opt_; }  // queued calls ran with the old hyper-parameters
+  OptConfig& opt() { Flush(); return opt_; }  // queued calls run with the old hyper-parameters first
+  const OptConfig& opt_view() const { return opt_; }
+  // Optimizer._index_update_count[key] / Optimizer.num_update as they stand once the queued calls
+  // have run (a queued push counts), without running them
+  int UpdateCount(int key) const;
+  int NumUpdate() const;
   void TouchOpt() { ++opt_version_; }  // call after changing opt() scalars / multipliers
   NDArray GetOptimizerState(int key, int state_id);
   void SetOptimizerState(int key, int state_id, const NDArray& v);

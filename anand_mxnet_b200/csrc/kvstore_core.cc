@@ -354,6 +354,10 @@ bool KVStore::TryDefer(int kind, const std::vector<int>& vkeys, const std::vecto
     for (int k : vkeys) if (k != k0) return false;
     for (int k : okeys) if (k != k0) return false;
     if (vkeys.empty() && okeys.empty()) return false;
+    // memory another framework owns (DLPack imports) can be read by its owner without any call
+    // into this library, so nothing would ever flush the queue for it: run such calls at once
+    for (auto& v : values) if (v.external()) return false;
+    for (auto& o : outs) if (o.external()) return false;
     cap = auto_bucket_bytes_;
   }
   size_t bytes = 0;
@@ -420,6 +424,18 @@ void KVStore::Flush() {
   } else {
     PullImpl(okeys, outs, true);
   }
+}
+
+int KVStore::UpdateCount(int key) const {
+  auto it = opt_.count.find(key);
+  const int c = it == opt_.count.end() ? opt_.begin_num_update : it->second;
+  return c + (pending_pushed_.count(key) ? 1 : 0);
+}
+
+int KVStore::NumUpdate() const {
+  int n = opt_.num_update;
+  for (int k : pending_pushed_) n = std::max(n, UpdateCount(k));
+  return n;
 }
 
 void KVStore::SetBucketBytes(size_t n) {
@@ -699,6 +715,9 @@ static NDArray ZeroState(const KeyEntry& e, int dev) {
   if (a.Size() == 0) return a;
   Engine* eng = Engine::Get();
   DeviceGuard g(dev);
+  // a recycled block carries the pending work of its previous owner (possibly on a copy lane or
+  // a peer GPU): the memset is the first writer and must wait for it
+  eng->BeginWrite(dev, *a.var());
   KV_CUDA(cudaMemsetAsync(a.data(), 0, a.ByteSize(), eng->Stream(dev)));
   eng->MarkWrite(dev, eng->Issue(dev), a.var());
   return a;

@@ -80,12 +80,14 @@ class NDArray {
   // host array in the library's own pinned+mapped memory: kernels can address it directly (UVA),
   // so the fused kernel reads gradients from / writes weights to it over PCIe without staging
   bool kernel_visible_host() const { return st_ && !st_->ctx.is_gpu() && !st_->external; }
+  bool external() const { return st_ && st_->external; }  // memory owned by another framework (DLPack)
   bool kernel_visible() const { return on_gpu() || kernel_visible_host(); }
   size_t Size() const;        // product of shape
   size_t RowLength() const;   // product of shape[1:]
   size_t ByteSize() const { return Size() * DTypeSize(dtype_); }
   Var* var() const { return &st_->var; }
   Storage* storage() const { return st_.get(); }
+  long use_count() const { return st_.use_count(); }   // holders of the underlying storage
   bool SameStorage(const NDArray& o) const { return st_ == o.st_; }
 
   void Alloc() const;  // dense: allocate if delayed

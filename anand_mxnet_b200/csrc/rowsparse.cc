@@ -138,6 +138,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
       if (!a->is_none() || sharded_now) return;
       *a = NDArray(dshape, Context::GPU(home), kFloat32);
       DeviceGuard g(home);
+      eng->BeginWrite(home, *a->var());   // first writer of a possibly recycled block
       KV_CUDA(cudaMemsetAsync(a->data(), 0, a->ByteSize(), eng->Stream(home)));
       eng->MarkWrite(home, eng->Issue(home), a->var());
     };
@@ -197,7 +198,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     if (parts.size() > 1) eng->JoinStreams(parts);
     DeviceGuard g(home);
     cudaStream_t st = eng->Stream(home);
-    Scratch ws(home, RspMergeWorkspaceBytes(total));
+    Scratch ws(home, RspMergeWorkspaceBytes(total, BitsFor(e.shape[0]), S.nsrc));
     LaunchRspMerge(S, BitsFor(e.shape[0]), row_len, fused ? nullptr : merged.row_ids(),
                    fused ? nullptr : static_cast<float*>(merged.data()),
                    static_cast<int64_t*>(d_nnr.data()), ws.p, ws.bytes, st, fused ? &U : nullptr);
@@ -365,7 +366,7 @@ std::function<void()> KVStore::PullRowSparseGroup(int home, const std::vector<si
   }
   auto fence = std::make_shared<CountFence>(home, nitems + 1);
   NDArray d_off({nitems + 1}, Context::GPU(home), kInt64);
-  NDArray ws({static_cast<int64_t>(RetainBatchWorkspaceBytes(nitems, total))}, Context::GPU(home), kUint8);
+  NDArray ws({static_cast<int64_t>(RetainBatchWorkspaceBytes(nitems, total, id_bits))}, Context::GPU(home), kUint8);
   {
     DeviceGuard g(home);
     cudaStream_t st = eng->Stream(home);
@@ -514,13 +515,13 @@ void CastStorageCopy(const NDArray& from_in, const NDArray& to) {
     it.out_idx = target.row_ids();
     it.out_val = static_cast<float*>(target.data());
     NDArray off({2}, Context::GPU(dev), kInt64);
-    NDArray rws({static_cast<int64_t>(RetainBatchWorkspaceBytes(1, nnr))}, Context::GPU(dev), kUint8);
+    const int id_bits = BitsFor(rows);
+    NDArray rws({static_cast<int64_t>(RetainBatchWorkspaceBytes(1, nnr, id_bits))}, Context::GPU(dev), kUint8);
     eng->BeginRead(dev, *from.var());
     eng->BeginRead(dev, *ids.var());
     eng->BeginWrite(dev, *target.var());
     eng->BeginWrite(dev, *off.var());
     eng->BeginWrite(dev, *rws.var());
-    const int id_bits = BitsFor(rows);
     LaunchUniqueBatch(&it, 1, nnr, id_bits, static_cast<int64_t*>(off.data()), rws.data(), rws.ByteSize(), st);
     LaunchRetainBatch(1, nnr, id_bits, static_cast<const int64_t*>(off.data()), rws.data(), st);
     eng->CountLaunch("cast_storage(dns->rsp gather)", static_cast<uint64_t>(nnr) * row_len * 8);
@@ -675,6 +676,7 @@ bool KVStore::PushRowSparseSharded(KeyEntry& e, const std::vector<NDArray>& srcs
       if (!(which == 0 ? need1 : need2) || !a.is_none()) continue;
       a = NDArray(e.rsp_shards[j].shape(), Context::GPU(devs[j]), kFloat32);
       DeviceGuard g(devs[j]);
+      eng->BeginWrite(devs[j], *a.var());   // first writer of a possibly recycled block
       KV_CUDA(cudaMemsetAsync(a.data(), 0, a.ByteSize(), eng->Stream(devs[j])));
       eng->MarkWrite(devs[j], eng->Issue(devs[j]), a.var());
     }
@@ -695,7 +697,7 @@ bool KVStore::PushRowSparseSharded(KeyEntry& e, const std::vector<NDArray>& srcs
     const int dev = devs[j];
     DeviceGuard g(dev);
     NDArray d_nnr({1}, Context::GPU(dev), kInt64);
-    NDArray ws({static_cast<int64_t>(RspMergeWorkspaceBytes(total))}, Context::GPU(dev), kUint8);
+    NDArray ws({static_cast<int64_t>(RspMergeWorkspaceBytes(total, id_bits, S.nsrc, lo, hi))}, Context::GPU(dev), kUint8);
     RspUpdateLaunch Uj = U;
     // virtual bases: row `id` of the table is at base + id*row_len
     Uj.w = static_cast<float*>(e.rsp_shards[j].data()) - lo * row_len;
@@ -725,11 +727,7 @@ void KVStore::GroupBarrier() {
   PeerGroup* g = PeerGroup::Get();
   Engine* eng = Engine::Get();
   DenseLaunch L;
-  L.signal_pads = g->d_pads();
-  L.counter = g->d_counter();
-  L.rank = g->rank();
-  L.world = g->world();
-  L.epoch = g->NextEpoch();
+  g->FillLaunch(&L);
   L.n_chunks = 0;               // no work: the fused kernel's start + end barriers only
   L.dtype = kFloat32;
   L.opt = kOptAssign;
@@ -814,6 +812,7 @@ void KVStore::PushRowSparseGroup(KeyEntry& e, const NDArray& src_in, RspUpdateLa
     if (!(which == 0 ? need1 : need2) || !a.is_none()) continue;
     a = NDArray(e.rsp_shards[0].shape(), Context::GPU(dev), kFloat32);
     DeviceGuard gd(dev);
+    eng->BeginWrite(dev, *a.var());   // first writer of a possibly recycled block
     KV_CUDA(cudaMemsetAsync(a.data(), 0, a.ByteSize(), eng->Stream(dev)));
     eng->MarkWrite(dev, eng->Issue(dev), a.var());
   }
@@ -828,7 +827,7 @@ void KVStore::PushRowSparseGroup(KeyEntry& e, const NDArray& src_in, RspUpdateLa
   if (total > 0 && hi > lo) {
     DeviceGuard gd(dev);
     d_nnr = NDArray({1}, Context::GPU(dev), kInt64);
-    ws = NDArray({static_cast<int64_t>(RspMergeWorkspaceBytes(total))}, Context::GPU(dev), kUint8);
+    ws = NDArray({static_cast<int64_t>(RspMergeWorkspaceBytes(total, BitsFor(rows), S.nsrc, lo, hi))}, Context::GPU(dev), kUint8);
     RspUpdateLaunch Uj = U;
     Uj.row_len = row_len;
     Uj.w = static_cast<float*>(e.rsp_shards[0].data()) - lo * row_len;

@@ -147,29 +147,11 @@ struct MergeSum {
 // parallel step instead of a per-source pointer chase) and parks it in shared memory; the row is
 // then processed in tiles of 4 x 32 float4 so that every lane keeps 4 source loads (+ the weight /
 // state loads of the tile) in flight.
+// The row work shared by both union front-ends: `rows[0..cnt)` are the source rows of union row r
+// (id `id`) in SOURCE ORDER.
 template <int OPT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p) {
-  __shared__ const float* s_rows[kWarpsPerBlock][kMaxSrc];
-  const int warp = threadIdx.x >> 5;
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + warp;
-  const int64_t nnr = *p.d_nnr;
-  if (r >= nnr) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t total = p.s.start[p.s.nsrc];
-  const uint32_t b = p.seg[r];
-  const uint32_t e = r + 1 < nnr ? p.seg[r + 1] : static_cast<uint32_t>(total);
-  const int64_t id = p.keys[b];
-  if (p.sentinel != 0 && id >= p.sentinel) return;  // the out-of-shard filler segment
-  if (OPT < 0 && lane == 0) p.out_idx[r] = id;
-  // this row's sources, in source order; a row_sparse array holds an id at most once, so there
-  // are at most nsrc <= kMaxSrc of them (anything beyond is a malformed input and is ignored)
-  const int cnt = min(static_cast<int>(e - b), kMaxSrc);
-  if (lane < cnt) {
-    const int64_t pos = p.vals[b + lane];
-    const int k = find_segment(p.s.start, p.s.nsrc, pos);
-    s_rows[warp][lane] = p.s.val[k] + (pos - p.s.start[k]) * p.row_len;
-  }
-  __syncwarp();
+__device__ __forceinline__ void rsp_sum_row(const MergeSum& p, const float* const* rows, int cnt,
+                                            int64_t id, int64_t r, int lane) {
   Hyper h{p.u.lr, p.u.wd, p.u.momentum, p.u.rescale, p.u.clip, p.u.beta1, p.u.beta2, p.u.eps};
   float* out = OPT < 0 ? p.out_val + r * p.row_len : nullptr;
   float* w = OPT < 0 ? nullptr : p.u.w + id * p.row_len;
@@ -205,7 +187,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
         }
       }
       for (int j = 0; j < cnt; ++j) {
-        const float4* row = reinterpret_cast<const float4*>(s_rows[warp][j]);
+        const float4* row = reinterpret_cast<const float4*>(rows[j]);
         float4 x[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -238,7 +220,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
   } else {
     for (int64_t col = lane; col < p.row_len; col += 32) {
       float acc = 0.f;
-      for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, s_rows[warp][j][col]);
+      for (int j = 0; j < cnt; ++j) acc = __fadd_rn(acc, rows[j][col]);
       if (OPT < 0) {
         out[col] = acc;
       } else {
@@ -249,6 +231,221 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p
         if (OPT == kOptSGD || OPT == kOptAdam) s1[col] = a;
         if (OPT == kOptAdam) s2[col] = c;
       }
+    }
+  }
+}
+
+template <int OPT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_kernel(MergeSum p) {
+  __shared__ const float* s_rows[kWarpsPerBlock][kMaxSrc];
+  const int warp = threadIdx.x >> 5;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + warp;
+  const int64_t nnr = *p.d_nnr;
+  if (r >= nnr) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = p.s.start[p.s.nsrc];
+  const uint32_t b = p.seg[r];
+  const uint32_t e = r + 1 < nnr ? p.seg[r + 1] : static_cast<uint32_t>(total);
+  const int64_t id = p.keys[b];
+  if (p.sentinel != 0 && id >= p.sentinel) return;  // the out-of-shard filler segment
+  if (OPT < 0 && lane == 0) p.out_idx[r] = id;
+  // this row's sources, in source order; a row_sparse array holds an id at most once, so there
+  // are at most nsrc <= kMaxSrc of them (anything beyond is a malformed input and is ignored)
+  const int cnt = min(static_cast<int>(e - b), kMaxSrc);
+  if (lane < cnt) {
+    const int64_t pos = p.vals[b + lane];
+    const int k = find_segment(p.s.start, p.s.nsrc, pos);
+    s_rows[warp][lane] = p.s.val[k] + (pos - p.s.start[k]) * p.row_len;
+  }
+  __syncwarp();
+  rsp_sum_row<OPT>(p, s_rows[warp], cnt, id, r, lane);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Bitmap union: the ids of a push (or the requested ids of a pull) are marked in a bitmap over the
+// table's row range, a popcount prefix over the bitmap ranks them, and every id finds its place in
+// the ascending unique union with two loads -- no sort. 1 M rows = 31 250 words: the bitmap and
+// its prefix stay in L2 and the whole bookkeeping of a push is three launches of a few
+// microseconds (mark, scan, scatter) where the radix sort of (id, position) pairs took nine
+// (histogram, 3 x onesweep, select ...: ~60 us for 80 K ids, more than half of the row traffic's
+// time). Tables taller than kBitmapMaxWords*32 rows keep the sort path.
+constexpr int64_t kBitmapMaxWords = int64_t{1} << 18;   // per group: 8 M rows
+constexpr int64_t kBitmapMaxTotalWords = int64_t{1} << 22;
+constexpr int kScanThreads = 1024;
+
+// B200KV_RSP_SORT=1 forces the radix-sort union (read per call so tests can cover both paths)
+bool BitmapDisabled() {
+  const char* z = std::getenv("B200KV_RSP_SORT");
+  return z != nullptr && z[0] != '\0' && z[0] != '0';
+}
+
+__global__ void bm_mark_push_kernel(RspSources s, int64_t lo, int64_t hi, uint32_t* bitmap,
+                                    uint32_t* srcpos, int64_t table_words) {
+  const int64_t total = s.start[s.nsrc];
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = tid; i < total; i += nth) {
+    const int k = find_segment(s.start, s.nsrc, i);
+    const int64_t id = s.idx[k][i - s.start[k]];
+    if (id >= lo && id < hi) {
+      const int64_t r = id - lo;
+      atomicOr(&bitmap[r >> 5], 1u << (r & 31));
+    }
+  }
+  for (int64_t j = tid; j < table_words; j += nth) srcpos[j] = 0u;   // source table of the union rows
+}
+
+// one CTA per group: prefix[w] = number of set bits in the words before w; count[g] = set bits
+__global__ void __launch_bounds__(kScanThreads) bm_scan_kernel(const uint32_t* bitmap, int64_t nwords,
+                                                               uint32_t* prefix, int64_t* d_count) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t s_total;
+  bitmap += static_cast<int64_t>(blockIdx.x) * nwords;
+  prefix += static_cast<int64_t>(blockIdx.x) * nwords;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t per_warp = (((nwords + 31) / 32) + 31) / 32 * 32;   // words per warp, multiple of 32
+  const int64_t wb = warp * per_warp;
+  const int64_t we = min(wb + per_warp, nwords);
+  uint32_t cnt = 0;
+  for (int64_t w = wb + lane; w < we; w += 32) cnt += __popc(bitmap[w]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) wsum[warp] = cnt;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t v = wsum[lane];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    wsum[lane] = incl - v;
+    if (lane == 31) s_total = incl;
+  }
+  __syncthreads();
+  uint32_t base = wsum[warp];
+  for (int64_t w0 = wb; w0 < we; w0 += 32) {
+    const int64_t w = w0 + lane;
+    const uint32_t c = w < we ? __popc(bitmap[w]) : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (w < we) prefix[w] = base + incl - c;
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (threadIdx.x == 0) d_count[blockIdx.x] = s_total;
+}
+
+// every (source, position) pair finds its union row: uid[u] = id, srcpos[u][k] = position + 1
+__global__ void bm_scatter_push_kernel(RspSources s, int64_t lo, int64_t hi, const uint32_t* bitmap,
+                                       const uint32_t* prefix, int64_t* uid, uint32_t* srcpos) {
+  const int64_t total = s.start[s.nsrc];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = find_segment(s.start, s.nsrc, i);
+    const int64_t id = s.idx[k][i - s.start[k]];
+    if (id < lo || id >= hi) continue;
+    const int64_t r = id - lo;
+    const uint32_t word = bitmap[r >> 5];
+    const uint32_t u = prefix[r >> 5] + __popc(word & ((1u << (r & 31)) - 1u));
+    uid[u] = id;
+    srcpos[static_cast<int64_t>(u) * s.nsrc + k] = static_cast<uint32_t>(i - s.start[k]) + 1u;
+  }
+}
+
+struct MergeSumBm {
+  MergeSum m;              // sources, outputs, fused update (keys / vals / seg unused)
+  const int64_t* uid;      // union ids, ascending
+  const uint32_t* srcpos;  // [union row][source] -> position + 1, 0 = the source lacks the row
+};
+
+// Persistent warps over the union rows. The bookkeeping of the NEXT row (its id and source
+// positions: two independent loads) is fetched before the current row's data is touched, so a
+// warp's dependent chain is just row pointer -> row data.
+template <int OPT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) rsp_sum_bm_kernel(MergeSumBm q) {
+  __shared__ const float* s_rows[kWarpsPerBlock][kMaxSrc];
+  const MergeSum& p = q.m;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t nnr = *p.d_nnr;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
+  const int nsrc = p.s.nsrc;
+  int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + warp;
+  int64_t id = 0;
+  uint32_t pos = 0;
+  if (r < nnr) {
+    id = q.uid[r];
+    pos = lane < nsrc ? q.srcpos[r * nsrc + lane] : 0u;
+  }
+  while (r < nnr) {
+    const int64_t rn = r + nwarps;
+    int64_t id_n = 0;
+    uint32_t pos_n = 0;
+    if (rn < nnr) {
+      id_n = q.uid[rn];
+      pos_n = lane < nsrc ? q.srcpos[rn * nsrc + lane] : 0u;
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, pos != 0u);
+    if (pos != 0u) {
+      s_rows[warp][__popc(mask & ((1u << lane) - 1u))] =
+          p.s.val[lane] + static_cast<int64_t>(pos - 1u) * p.row_len;
+    }
+    __syncwarp();
+    if (OPT < 0 && lane == 0) p.out_idx[r] = id;
+    rsp_sum_row<OPT>(p, s_rows[warp], __popc(mask), id, r, lane);
+    __syncwarp();
+    r = rn;
+    id = id_n;
+    pos = pos_n;
+  }
+}
+
+// ---- pull: per item one bitmap; ids of any integer / float dtype
+__device__ __forceinline__ int64_t load_id(const void* ids, int dtype, int64_t i);
+__device__ __forceinline__ int find_item(const RetainItem* items, int nitems, int64_t i);
+
+__global__ void bm_mark_pull_kernel(const RetainItem* items, int nitems, int64_t total, int64_t nwords,
+                                    uint32_t* bitmap) {
+  const int64_t cap = nwords * 32;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = find_item(items, nitems, i);
+    const int64_t id = load_id(items[k].ids, items[k].ids_dtype, i - items[k].start);
+    if (id >= 0 && id < cap) atomicOr(&bitmap[k * nwords + (id >> 5)], 1u << (id & 31));
+  }
+}
+
+constexpr int kBmMaxItems = 1024;
+// uniq[off[k] + j] = j-th smallest requested id of item k; off[] = prefix of the items' counts
+__global__ void bm_emit_pull_kernel(const uint32_t* bitmap, const uint32_t* prefix, const int64_t* count,
+                                    int nitems, int64_t nwords, int64_t* uniq, int64_t* off) {
+  __shared__ int64_t s_off[kBmMaxItems + 1];
+  if (threadIdx.x == 0) {
+    int64_t acc = 0;
+    for (int k = 0; k < nitems; ++k) { s_off[k] = acc; acc += count[k]; }
+    s_off[nitems] = acc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int k = threadIdx.x; k <= nitems; k += blockDim.x) off[k] = s_off[k];
+  }
+  const int64_t all = nwords * nitems;
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < all;
+       j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint32_t word = bitmap[j];
+    if (word == 0u) continue;
+    const int k = static_cast<int>(j / nwords);
+    const int64_t w = j - k * nwords;
+    int64_t* dst = uniq + s_off[k] + prefix[j];
+    while (word) {
+      const int b = __ffs(word) - 1;
+      *dst++ = (w << 5) + b;
+      word &= word - 1u;
     }
   }
 }
@@ -365,6 +562,30 @@ struct MergeLayout {
   size_t keys, keys_sorted, vals, vals_sorted, seg, temp, temp_bytes, total;
 };
 
+// workspace of the bitmap union of a push: bitmap + prefix over the row range, union ids, source table
+struct BmMergeLayout {
+  bool ok = false;
+  int64_t nwords = 0;
+  size_t bitmap = 0, prefix = 0, uid = 0, srcpos = 0, total = 0;
+};
+
+BmMergeLayout LayoutMergeBm(int64_t n, int id_bits, int nsrc, int64_t lo, int64_t hi) {
+  auto up = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+  BmMergeLayout l;
+  if (BitmapDisabled() || id_bits < 1 || id_bits > 40) return l;
+  const int64_t top = std::min(hi, int64_t{1} << id_bits);
+  if (top <= lo) return l;
+  l.nwords = (top - lo + 31) / 32;
+  if (l.nwords > kBitmapMaxWords) return l;
+  l.ok = true;
+  l.bitmap = 0;
+  l.prefix = up(static_cast<size_t>(l.nwords) * 4);
+  l.uid = l.prefix + up(static_cast<size_t>(l.nwords) * 4);
+  l.srcpos = l.uid + up(static_cast<size_t>(n) * 8);
+  l.total = l.srcpos + up(static_cast<size_t>(n) * std::max(nsrc, 1) * 4) + 256;
+  return l;
+}
+
 MergeLayout LayoutMerge(int64_t n) {
   auto up = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
   MergeLayout l;
@@ -480,9 +701,14 @@ retain_kernel(const RetainItem* items, int nitems, int64_t total, int id_bits, c
 
 struct RetainLayout {
   size_t items, comp, sorted, uniq, count, temp, temp_bytes, total;
+  // bitmap unique (id_bits > 0 and the table is short enough): bitmap + prefix per item live in the
+  // region the sort path uses for its keys and temporaries
+  bool bm = false;
+  int64_t nwords = 0;
+  size_t bm_bitmap = 0, bm_prefix = 0;
 };
 
-RetainLayout LayoutRetain(int nitems, int64_t n) {
+RetainLayout LayoutRetain(int nitems, int64_t n, int id_bits = 0) {
   auto up = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
   RetainLayout l;
   const size_t k = up(static_cast<size_t>(n) * sizeof(int64_t));
@@ -497,9 +723,20 @@ RetainLayout LayoutRetain(int nitems, int64_t n) {
   l.sorted = l.comp + k;
   l.uniq = l.sorted + k;
   l.count = l.uniq + k;
-  l.temp = l.count + 256;
+  l.temp = l.count + up(static_cast<size_t>(nitems + 1) * sizeof(int64_t));
   l.temp_bytes = up(std::max(t1, t2));
   l.total = l.temp + l.temp_bytes + 256;
+  if (id_bits >= 1 && id_bits <= 40 && !BitmapDisabled() && nitems <= kBmMaxItems) {
+    const int64_t nwords = ((int64_t{1} << id_bits) + 31) / 32;
+    if (nwords <= kBitmapMaxWords && nwords * nitems <= kBitmapMaxTotalWords) {
+      l.bm = true;
+      l.nwords = nwords;
+      const size_t bytes = up(static_cast<size_t>(nwords) * nitems * 4);
+      l.bm_bitmap = l.temp;
+      l.bm_prefix = l.temp + bytes;
+      l.total = std::max(l.total, l.bm_prefix + bytes + 256);
+    }
+  }
   return l;
 }
 
@@ -521,7 +758,11 @@ void LaunchRspUpdate(const RspUpdateLaunch& p, cudaStream_t stream) {
   KV_CUDA(cudaGetLastError());
 }
 
-size_t RspMergeWorkspaceBytes(int64_t total_ids) { return LayoutMerge(std::max<int64_t>(total_ids, 1)).total; }
+size_t RspMergeWorkspaceBytes(int64_t total_ids, int id_bits, int nsrc, int64_t lo, int64_t hi) {
+  const int64_t n = std::max<int64_t>(total_ids, 1);
+  const BmMergeLayout b = LayoutMergeBm(n, id_bits, nsrc, lo, hi);
+  return b.ok ? b.total : LayoutMerge(n).total;
+}
 
 void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_t* out_idx,
                     float* out_val, int64_t* d_nnr, void* workspace, size_t workspace_bytes,
@@ -530,9 +771,46 @@ void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_
   KV_CHECK(srcs.nsrc >= 1 && srcs.nsrc <= kMaxSrc);
   KV_CHECK(total > 0 && total < (1LL << 31)) << "row_sparse push: " << total << " row ids";
   KV_CHECK(id_bits >= 1 && id_bits <= 63);
+  char* ws = static_cast<char*>(workspace);
+  const BmMergeLayout bl = LayoutMergeBm(total, id_bits, srcs.nsrc, lo, hi);
+  if (bl.ok) {
+    // ---- bitmap union: mark, scan, scatter, then persistent warps over the union rows
+    KV_CHECK(workspace_bytes >= bl.total) << "rsp merge: workspace too small";
+    const int64_t top = std::min(hi, int64_t{1} << id_bits);
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(ws + bl.bitmap);
+    uint32_t* prefix = reinterpret_cast<uint32_t*>(ws + bl.prefix);
+    int64_t* uid = reinterpret_cast<int64_t*>(ws + bl.uid);
+    uint32_t* srcpos = reinterpret_cast<uint32_t*>(ws + bl.srcpos);
+    KV_CUDA(cudaMemsetAsync(bitmap, 0, static_cast<size_t>(bl.nwords) * 4, stream));
+    const int64_t table_words = total * srcs.nsrc;
+    bm_mark_push_kernel<<<GridFor(std::max(total, table_words / 4), 256), 256, 0, stream>>>(
+        srcs, lo, top, bitmap, srcpos, table_words);
+    bm_scan_kernel<<<1, kScanThreads, 0, stream>>>(bitmap, bl.nwords, prefix, d_nnr);
+    bm_scatter_push_kernel<<<GridFor(total, 256), 256, 0, stream>>>(srcs, lo, top, bitmap, prefix, uid, srcpos);
+    KV_CUDA(cudaGetLastError());
+    if (row_len <= 0) return;
+    MergeSumBm q;
+    q.m = MergeSum{srcs, nullptr, nullptr, nullptr, d_nnr, out_idx, out_val, row_len, RspUpdateLaunch(), 0};
+    q.uid = uid;
+    q.srcpos = srcpos;
+    const int threads = kWarpsPerBlock * 32;
+    const int blocks = static_cast<int>(std::min<int64_t>((total + kWarpsPerBlock - 1) / kWarpsPerBlock, 148 * 6));
+    if (fused_update == nullptr) {
+      rsp_sum_bm_kernel<-1><<<blocks, threads, 0, stream>>>(q);
+    } else {
+      q.m.u = *fused_update;
+      switch (q.m.u.opt) {
+        case kOptSGDSingle: rsp_sum_bm_kernel<kOptSGDSingle><<<blocks, threads, 0, stream>>>(q); break;
+        case kOptSGD: rsp_sum_bm_kernel<kOptSGD><<<blocks, threads, 0, stream>>>(q); break;
+        case kOptAdam: rsp_sum_bm_kernel<kOptAdam><<<blocks, threads, 0, stream>>>(q); break;
+        default: KV_FATAL << "row_sparse push: unsupported optimizer kind " << q.m.u.opt;
+      }
+    }
+    KV_CUDA(cudaGetLastError());
+    return;
+  }
   const MergeLayout l = LayoutMerge(total);
   KV_CHECK(workspace_bytes >= l.total) << "rsp merge: workspace too small";
-  char* ws = static_cast<char*>(workspace);
   int64_t* keys = reinterpret_cast<int64_t*>(ws + l.keys);
   int64_t* keys_sorted = reinterpret_cast<int64_t*>(ws + l.keys_sorted);
   uint32_t* vals = reinterpret_cast<uint32_t*>(ws + l.vals);
@@ -567,8 +845,8 @@ void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_
   KV_CUDA(cudaGetLastError());
 }
 
-size_t RetainBatchWorkspaceBytes(int nitems, int64_t total_ids) {
-  return LayoutRetain(std::max(nitems, 1), std::max<int64_t>(total_ids, 1)).total;
+size_t RetainBatchWorkspaceBytes(int nitems, int64_t total_ids, int id_bits) {
+  return LayoutRetain(std::max(nitems, 1), std::max<int64_t>(total_ids, 1), id_bits).total;
 }
 
 void LaunchUniqueBatch(const RetainItem* h_items, int nitems, int64_t total, int id_bits,
@@ -577,7 +855,7 @@ void LaunchUniqueBatch(const RetainItem* h_items, int nitems, int64_t total, int
   int item_bits = 0;
   while ((1 << item_bits) < nitems) ++item_bits;
   KV_CHECK(id_bits >= 1 && id_bits + item_bits <= 62) << "row_sparse_pull: id space too large";
-  const RetainLayout l = LayoutRetain(nitems, total);
+  const RetainLayout l = LayoutRetain(nitems, total, id_bits);
   KV_CHECK(workspace_bytes >= l.total) << "retain batch: workspace too small";
   char* ws = static_cast<char*>(workspace);
   RetainItem* items = reinterpret_cast<RetainItem*>(ws + l.items);
@@ -586,6 +864,18 @@ void LaunchUniqueBatch(const RetainItem* h_items, int nitems, int64_t total, int
   int64_t* uniq = reinterpret_cast<int64_t*>(ws + l.uniq);
   int64_t* count = reinterpret_cast<int64_t*>(ws + l.count);
   KV_CUDA(cudaMemcpyAsync(items, h_items, nitems * sizeof(RetainItem), cudaMemcpyHostToDevice, stream));
+  if (l.bm) {
+    // bitmap unique: mark every item's ids in its own bitmap, rank them, emit them in order
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(ws + l.bm_bitmap);
+    uint32_t* prefix = reinterpret_cast<uint32_t*>(ws + l.bm_prefix);
+    KV_CUDA(cudaMemsetAsync(bitmap, 0, static_cast<size_t>(l.nwords) * nitems * 4, stream));
+    bm_mark_pull_kernel<<<GridFor(total, 256), 256, 0, stream>>>(items, nitems, total, l.nwords, bitmap);
+    bm_scan_kernel<<<nitems, kScanThreads, 0, stream>>>(bitmap, l.nwords, prefix, count);
+    bm_emit_pull_kernel<<<GridFor(l.nwords * nitems, 256), 256, 0, stream>>>(bitmap, prefix, count, nitems,
+                                                                              l.nwords, uniq, d_off);
+    KV_CUDA(cudaGetLastError());
+    return;
+  }
   retain_gather_kernel<<<GridFor(total, 256), 256, 0, stream>>>(items, nitems, total, id_bits, comp);
   KV_CUDA(cudaGetLastError());
   size_t tb = l.temp_bytes;
@@ -600,7 +890,7 @@ void LaunchUniqueBatch(const RetainItem* h_items, int nitems, int64_t total, int
 
 void LaunchRetainBatch(int nitems, int64_t total, int id_bits, const int64_t* d_off, void* workspace,
                        cudaStream_t stream) {
-  const RetainLayout l = LayoutRetain(nitems, total);
+  const RetainLayout l = LayoutRetain(nitems, total, id_bits);
   char* ws = static_cast<char*>(workspace);
   const RetainItem* items = reinterpret_cast<const RetainItem*>(ws + l.items);
   const int64_t* uniq = reinterpret_cast<const int64_t*>(ws + l.uniq);

@@ -206,7 +206,9 @@ class KVStore(KVStoreBase):
                 (ctypes.c_double * len(nk))(*lr_mult), (ctypes.c_double * len(nk))(*wd_mult)))
             self._mult_sent.update(new)
         if o.lr_scheduler is not None:
-            lr = o.lr_scheduler(max(o.num_update, self._native_num_update(keys) + 1))
+            # Optimizer._update_count then _get_lr (optimizer.py:412-441): the scheduler sees
+            # num_update = max over every index's count, this push included
+            lr = o.lr_scheduler(max(o.num_update, self._native_num_update(keys)))
         else:
             lr = o.lr
         if lr != self._fused_sent['lr']:
@@ -217,12 +219,14 @@ class KVStore(KVStoreBase):
             self._fused_sent['rescale'] = o.rescale_grad
 
     def _native_num_update(self, keys):
+        """Optimizer.num_update as it stands after the push of `keys` that is about to be issued"""
         c = ctypes.c_int()
-        m = 0
-        for k in keys[:1]:
+        check_call(_LIB.B200KVStoreGetNumUpdate(self.handle, ctypes.byref(c)))
+        m = c.value
+        for k in keys:
             check_call(_LIB.B200KVStoreGetUpdateCount(self.handle, ctypes.c_int(self._native_key(k)),
                                                       ctypes.byref(c)))
-            m = max(m, c.value)
+            m = max(m, c.value + 1)
         return m
 
     @property

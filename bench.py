@@ -481,25 +481,6 @@ def time_region(torch, stream, fn, steps, after=None):
     return e0.elapsed_time(e1) / steps
 
 
-def device_sets(mx, torch, dev, shapes, host_sets):
-    """one flat device buffer per role, one 512-byte aligned view per tensor -- the arrays stay
-    separate NDArrays, exactly what a framework hands the store"""
-    sizes = [int(np.prod(s)) for s in shapes]
-    offs = np.concatenate([[0], np.cumsum([(n + 127) // 128 * 128 for n in sizes])]).astype(np.int64)
-    res = []
-    for hs in host_sets:
-        if hs is None:
-            flat = torch.empty(int(offs[-1]), device=dev)
-        else:
-            buf = np.zeros(int(offs[-1]), np.float32)
-            for i, n in enumerate(sizes):
-                buf[offs[i]:offs[i] + n] = hs[i]
-            flat = torch.from_numpy(buf).to(dev)
-        views = [flat[int(offs[i]):int(offs[i]) + sizes[i]].view(shapes[i]) for i in range(len(shapes))]
-        res.append((flat, views, [mx.nd.from_torch(t) for t in views]))
-    return res
-
-
 def run_dense_single(mx, torch, stream, args, workload, steps, warmup, full):
     """One dense workload on one GPU: parity, device-resident timing, and (full) the front-end
     variants and the host-buffer arm."""
@@ -510,10 +491,12 @@ def run_dense_single(mx, torch, stream, args, workload, steps, warmup, full):
     n_elem = sum(sizes)
     w0 = flat_set(weight_seed(), sizes)
     g0 = flat_set(grad_seed(0), sizes)
-    (_wf, _wv, w_nd), (_gf, _gv, grads), (_of, outs_t, outs) = device_sets(
-        mx, torch, dev, shapes, [w0, g0, None])
+    # library-owned NDArrays (what the reference's callers hold), one per tensor
+    ctx = mx.gpu(0)
+    grads = [mx.nd.array(g0[k].reshape(shapes[k]), ctx) for k in keys]
+    outs = [mx.nd.empty(s, ctx) for s in shapes]
     kv = mx.kv.create("device")
-    kv.init(keys, w_nd)
+    kv.init(keys, [mx.nd.array(w0[k].reshape(shapes[k]), ctx) for k in keys])
     kv.set_optimizer(make_optimizer(mx, workload, 1))
     torch.cuda.synchronize()
     # ---- parity: the first two steps of this very store against the CPU oracle
@@ -521,7 +504,7 @@ def run_dense_single(mx, torch, stream, args, workload, steps, warmup, full):
         kv.pushpull(keys, grads, out=outs)      # python front-end: hands lr / multipliers over
     mx.nd.waitall()
     torch.cuda.synchronize()
-    got = [t.cpu().numpy() for t in outs_t]
+    got = [o.asnumpy() for o in outs]
     want = oracle_expected(workload, 1, 2)
     parity = compare_sets(got, want, exact=True)
     parity["after_steps"] = 2

@@ -176,6 +176,37 @@ B200KV_DLL int MXKVStoreSendCommmandToServers(KVStoreHandle handle, int cmd_id,
 B200KV_DLL int MXKVStoreGetNumDeadNode(KVStoreHandle handle, const int node_id, int* number,
                                        const int timeout_sec);                        /* :3035 */
 
+/* ---- engine ABI for external schedulers (include/mxnet/c_api.h:99-110, 3323-3351) -------------
+ * An external operation joins the dependency graph by naming the arrays it reads (const) and the
+ * arrays it writes (mutable). rctx points at {int32 dev_type; int32 dev_id; void* stream;
+ * void* aux_stream; bool is_bulk} (mxnet::RunContext's layout; `stream` is the compute lane's
+ * cudaStream_t on a GPU context -- the reference hands out an mshadow::Stream<gpu>* there);
+ * on_complete points at {void (*callback)(void* engine, void* param, const void* error);
+ * void* engine; void* param} (mxnet::engine::CallbackOnComplete's layout; `error` is a
+ * const dmlc::Error* = std::runtime_error* or NULL). A C host completes with
+ * B200KVEngineOnComplete. A reported failure is parked on the mutable arrays and surfaces as -1 /
+ * MXGetLastError at the next MXNDArrayWaitToRead / WaitToWrite of one of them, or at
+ * MXNDArrayWaitAll (src/engine/threaded_engine.h:380-387). */
+typedef const void* ContextHandle;          /* -> {int32 dev_type; int32 dev_id} (mxnet::Context) */
+typedef const void* EngineFnPropertyHandle;
+typedef void (*EngineAsyncFunc)(void* rctx, void* on_complete, void* param);   /* c_api.h:105 */
+typedef void (*EngineSyncFunc)(void* rctx, void* param);                       /* c_api.h:107 */
+typedef void (*EngineFuncParamDeleter)(void* param);                           /* c_api.h:109 */
+B200KV_DLL int MXEnginePushAsyncND(EngineAsyncFunc async_func, void* func_param,
+                                   EngineFuncParamDeleter deleter, ContextHandle ctx_handle,
+                                   NDArrayHandle* const_nds_handle, int num_const_nds,
+                                   NDArrayHandle* mutable_nds_handle, int num_mutable_nds,
+                                   EngineFnPropertyHandle prop_handle, int priority,
+                                   const char* opr_name, bool wait);            /* c_api.h:3323 */
+B200KV_DLL int MXEnginePushSyncND(EngineSyncFunc sync_func, void* func_param,
+                                  EngineFuncParamDeleter deleter, ContextHandle ctx_handle,
+                                  NDArrayHandle* const_nds_handle, int num_const_nds,
+                                  NDArrayHandle* mutable_nds_handle, int num_mutable_nds,
+                                  EngineFnPropertyHandle prop_handle, int priority,
+                                  const char* opr_name);                        /* c_api.h:3345 */
+/* completion entry for hosts that cannot call a C++ CallbackOnComplete: error == NULL = success */
+B200KV_DLL int B200KVEngineOnComplete(void* on_complete, const char* error);
+
 /* ============================== Part B: B200 extensions ===================================== */
 
 /* Natively fused optimizer: replaces the per-key Python updater callback (kvstore.py:34-41 ->
@@ -204,6 +235,8 @@ B200KV_DLL int B200KVStoreSetOptimizerState(KVStoreHandle handle, int key, int s
                                             NDArrayHandle value);
 B200KV_DLL int B200KVStoreGetUpdateCount(KVStoreHandle handle, int key, int* out);
 B200KV_DLL int B200KVStoreSetUpdateCount(KVStoreHandle handle, int key, int count);
+/* Optimizer.num_update: the largest per-key update count so far (optimizer.py:412-430) */
+B200KV_DLL int B200KVStoreGetNumUpdate(KVStoreHandle handle, int* out);
 
 /* Deferred bucket execution: push/pull/pushpull calls are queued and fused into one launch per
  * device when the queued bytes reach the bucket size, when any array is waited on / read / exported,

@@ -21,6 +21,17 @@ def eq(a, b):
     return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
 
 
+@pytest.fixture(params=["bitmap", "sort"])
+def union_path(request, monkeypatch):
+    """both id-union front-ends of a push / pull: the bitmap rank (tables up to 8 M rows) and the
+    radix sort of (id, position) pairs it falls back to (B200KV_RSP_SORT=1 forces it)"""
+    if request.param == "sort":
+        monkeypatch.setenv("B200KV_RSP_SORT", "1")
+    else:
+        monkeypatch.delenv("B200KV_RSP_SORT", raising=False)
+    return request.param
+
+
 def make_rsp(mx, rng, shape, nnr, ctx, integer=False):
     idx = np.sort(rng.choice(shape[0], nnr, replace=False)).astype(np.int64)
     if integer:
@@ -54,7 +65,7 @@ def test_row_sparse_pull_from_dense_init(mx):
 
 
 @pytest.mark.parametrize("nsrc", [1, 2, 4, 8])
-def test_sparse_aggregator_bit_exact(mx, oracle, nsrc):
+def test_sparse_aggregator_bit_exact(mx, oracle, nsrc, union_path):
     # test_kvstore.py:178-227: push several row_sparse values of one key, pull everything
     rng = np.random.default_rng(nsrc)
     shape = (1000, 48)
@@ -84,7 +95,7 @@ def test_sparse_aggregator_bit_exact(mx, oracle, nsrc):
         assert eq(out2.data.asnumpy(), rv.reshape(out2.data.shape))
 
 
-def test_empty_and_ragged_inputs(mx, oracle):
+def test_empty_and_ragged_inputs(mx, oracle, union_path):
     rng = np.random.default_rng(3)
     shape = (50, 5)            # row length not a multiple of 4: scalar row path
     kv = mx.kv.create('device')
@@ -106,7 +117,7 @@ def test_empty_and_ragged_inputs(mx, oracle):
     assert np.array_equal(out.indices.asnumpy(), [i[0]]) and eq(out.data.asnumpy()[0], v[0])
 
 
-def test_large_table(mx, oracle):
+def test_large_table(mx, oracle, union_path):
     # test_kvstore_gpu.py:126-134 uses a 793470-row table; sizes here keep the oracle in seconds
     rng = np.random.default_rng(4)
     shape = (793470, 16)
@@ -124,7 +135,7 @@ def test_large_table(mx, oracle):
 
 
 @pytest.mark.parametrize("optname,clip", [('sgd', None), ('sgd_mom', 0.3), ('adam', None), ('adam', 0.3)])
-def test_fused_lazy_sparse_update(mx, oracle, optname, clip):
+def test_fused_lazy_sparse_update(mx, oracle, optname, clip, union_path):
     """Embedding-style key: weight holds every row, gradients are row_sparse, optimizer on the store
     (trainer.py:177-191 forces update_on_kvstore for sparse parameters)."""
     rng = np.random.default_rng(5)
