@@ -547,12 +547,16 @@ int PushExternal(void (*async_fn)(void*, void*, void*), void (*sync_fn)(void*, v
   std::vector<Var*> rd, wr;
   for (int i = 0; i < num_const; ++i) if (!ND(const_nds[i]).is_none()) rd.push_back(ND(const_nds[i]).var());
   for (int i = 0; i < num_mutable; ++i) if (!ND(mutable_nds[i]).is_none()) wr.push_back(ND(mutable_nds[i]).var());
-  // an operation whose inputs carry a parked failure is not run; the failure moves to its outputs
-  // (ThreadedEngine::OnStart / OnComplete exception propagation)
-  for (Var* v : rd) {
-    if (v->err && !v->err->empty()) {
-      for (Var* w : wr) eng->SetError(w, *v->err);
-      return 0;
+  // an operation that touches an array carrying a parked failure is not run; the failure moves to
+  // everything it was to write (ThreadedEngine::OnStart: exceptions of const AND mutable vars
+  // propagate, src/engine/threaded_engine.h:380-387)
+  for (const std::vector<Var*>* set : {&rd, &wr}) {
+    for (Var* v : *set) {
+      if (v->err && !v->err->empty()) {
+        const std::string msg = *v->err;
+        for (Var* w : wr) if (w != v) eng->SetError(w, msg);
+        return 0;
+      }
     }
   }
   const bool gpu = ctx.dev_type == kGPU;

@@ -152,14 +152,17 @@ def test_failed_async_op_surfaces_at_wait(mx):
     with pytest.raises(mx.base.MXNetError, match="failing_op2"):
         mx.nd.waitall()
     mx.nd.waitall()
-    # a later successful write clears the slate
+    # an operation that WRITES a failed array is skipped as well and the failure stays parked;
+    # once it has been reported the array is usable again
     push_async(mx, fn, Ctx(1, 0), [], [b], name=b"failing_op3")
     push_sync(mx, nop, Ctx(1, 0), [], [b])
+    assert not ran
+    with pytest.raises(mx.base.MXNetError, match="failing_op3"):
+        b.wait_to_read()
+    push_sync(mx, nop, Ctx(1, 0), [], [b])
+    assert ran
     b.wait_to_read()
-    try:
-        mx.nd.waitall()
-    except mx.base.MXNetError:
-        pass
+    mx.nd.waitall()
 
 
 def test_tree_environment_switches_are_accepted(mx, monkeypatch):

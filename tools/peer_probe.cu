@@ -76,6 +76,67 @@ __global__ void __launch_bounds__(kThreads) v0_chunk_cta(Args a) {
   }
 }
 
+
+// ---- V0B: V0 plus the product's cross-GPU barriers (signal pads, st.release.sys / ld.acquire.sys)
+// mode 1 = start + end barrier (product), 2 = start barrier only; timeline of GPU 0 in `tl`
+struct Bar {
+  unsigned* pads[kMaxN];   // per GPU: [2][kMaxN][32] words (start flags, end flags), peer mapped
+  unsigned* counter;       // this GPU's finished-CTA counter
+  unsigned epoch;
+  unsigned long long* tl;  // [4] accumulators: start-wait, data, end-wait, (kernel begin stamp)
+};
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void bar_signal_wait(const Args& a, const Bar& b, int phase, bool signal) {
+  const int t = threadIdx.x;
+  if (t < a.n && t != a.rank) {
+    const int base = phase * kMaxN * 32;
+    if (signal) st_release_sys(b.pads[t] + base + a.rank * 32, b.epoch);
+    const unsigned* mine = b.pads[a.rank] + base + t * 32;
+    while ((int)(ld_acquire_sys(mine) - b.epoch) < 0) __nanosleep(32);
+  }
+}
+template <int N, int MODE>
+__global__ void __launch_bounds__(kThreads) v0b_barriers(Args a, Bar b) {
+  __shared__ unsigned s_last;
+  unsigned long long t0 = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) t0 = gtime();
+  bar_signal_wait(a, b, 0, blockIdx.x == 0);
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && b.tl) { const unsigned long long t1 = gtime(); atomicAdd(&b.tl[0], t1 - t0); b.tl[3] = t1; }
+  const long long base = owned_chunk_base(a, blockIdx.x);
+  for (int v = threadIdx.x; v < kChunk / 4; v += kThreads) {
+    const long long e = base + v * 4;
+    float4 g[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) g[i] = ldcs(a.g[i] + e);
+    float4 w = ldcs(a.w + e), m = ldcs(a.m + e);
+    float4 s = g[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) s = add4(s, g[i]);
+    upd(w, m, s);
+    stcs(a.m + e, m);
+    stcs(a.w + e, w);
+#pragma unroll
+    for (int i = 0; i < N; ++i) stcs(a.out[i] + e, w);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned done = atomicAdd(b.counter, 1u);
+    s_last = (done == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    unsigned long long t2 = 0;
+    if (threadIdx.x == 0) { t2 = gtime(); if (b.tl) atomicAdd(&b.tl[1], t2 - b.tl[3]); }
+    __threadfence_system();
+    if (MODE == 1) { bar_signal_wait(a, b, 1, true); __syncthreads(); }
+    if (threadIdx.x == 0) { *b.counter = 0; if (b.tl) atomicAdd(&b.tl[2], gtime() - t2); }
+  }
+}
+
 // V1: U vectors per thread, every load issued before the first store; grid = chunks or persistent
 template <int N, int U, bool PERSIST, bool WB>
 __global__ void __launch_bounds__(kThreads) v1_unrolled(Args a) {
@@ -332,6 +393,35 @@ static void run_all(long long nelem) {
   run_variant("V5 pure peer read  (S(N-1)/N in)", n, nelem, G, [&](int d) { v5_pure_read<N><<<148 * 8, kThreads, 0, G[d].st>>>(A[d], G[d].sink); }, (n - 1.0) / n);
   run_variant("V6 pure peer write (S(N-1)/N out)", n, nelem, G, [&](int d) { v6_pure_write<N><<<148 * 8, kThreads, 0, G[d].st>>>(A[d]); }, (n - 1.0) / n);
   run_variant("V0 chunk-per-CTA, 1 vector/thread (product r1)", n, nelem, G, [&](int d) { v0_chunk_cta<N><<<A[d].n_chunks_owned, kThreads, 0, G[d].st>>>(A[d]); }, f);
+  {
+    // barrier emulation (same process: plain peer-mapped pads)
+    std::vector<unsigned*> pads(n), counters(n);
+    std::vector<unsigned long long*> tls(n);
+    for (int d = 0; d < n; ++d) {
+      CK(cudaSetDevice(d));
+      CK(cudaMalloc(&pads[d], 2 * kMaxN * 32 * 4)); CK(cudaMemset(pads[d], 0, 2 * kMaxN * 32 * 4));
+      CK(cudaMalloc(&counters[d], 256)); CK(cudaMemset(counters[d], 0, 256));
+      CK(cudaMalloc(&tls[d], 64)); CK(cudaMemset(tls[d], 0, 64));
+      CK(cudaDeviceSynchronize());
+    }
+    unsigned epoch = 0;
+    auto mk = [&](int d, unsigned ep) { Bar b; for (int i = 0; i < n; ++i) b.pads[i] = pads[i]; b.counter = counters[d]; b.epoch = ep; b.tl = tls[d]; return b; };
+    for (int mode = 1; mode <= 2; ++mode) {
+      for (int d = 0; d < n; ++d) { CK(cudaSetDevice(d)); CK(cudaMemset(tls[d], 0, 64)); CK(cudaDeviceSynchronize()); }
+      int calls = 0;
+      char nm[96];
+      snprintf(nm, sizeof nm, "V0B V0 + %s", mode == 1 ? "start+end barriers (product)" : "start barrier only");
+      run_variant(nm, n, nelem, G, [&](int d) {
+        if (d == 0) { ++epoch; ++calls; }
+        if (mode == 1) v0b_barriers<N, 1><<<A[d].n_chunks_owned, kThreads, 0, G[d].st>>>(A[d], mk(d, epoch));
+        else v0b_barriers<N, 2><<<A[d].n_chunks_owned, kThreads, 0, G[d].st>>>(A[d], mk(d, epoch));
+      }, f);
+      unsigned long long h[4];
+      CK(cudaSetDevice(0)); CK(cudaMemcpy(h, tls[0], 32, cudaMemcpyDeviceToHost));
+      printf("      GPU0 per step: start-barrier wait %.2f us, data phase %.2f us, end-barrier wait %.2f us (%d steps)\n",
+             h[0] / 1e3 / calls, h[1] / 1e3 / calls, h[2] / 1e3 / calls, calls);
+    }
+  }
   run_variant("V1 chunk-per-CTA, U=2", n, nelem, G, [&](int d) { v1_unrolled<N, 2, false, false><<<A[d].n_chunks_owned, kThreads, 0, G[d].st>>>(A[d]); }, f);
   if (N <= 4) run_variant("V1 chunk-per-CTA, U=4", n, nelem, G, [&](int d) { v1_unrolled<N, (N <= 4 ? 4 : 2), false, false><<<A[d].n_chunks_owned, kThreads, 0, G[d].st>>>(A[d]); }, f);
   for (int k : {1, 2, 4, 8}) {
