@@ -936,7 +936,13 @@ void KVStore::ExecCallbackPush(KeyEntry& e, const std::vector<NDArray>& srcs_in)
 // =================================================================================================
 NDArray KVStore::GetOptimizerState(int key, int state_id) {
   KeyEntry& e = Entry(key);
-  KV_CHECK_EQ(e.stype, kDefaultStorage) << "optimizer state access for row_sparse keys: see rsp path";
+  if (e.stype == kRowSparseStorage) {
+    // states of a row_sparse table are dense [rows, row_len] arrays; a table sharded by row range
+    // over this process's GPUs is folded back onto its home GPU first
+    KV_CHECK(!e.rsp_group) << "key " << key << ": the table is sharded over the ranks of a peer group; "
+                           << "every rank holds the state of its own row range only";
+    if (!e.rsp_devs.empty()) UnshardRsp(e);
+  }
   int dev = e.striped ? devset_[0] : e.home;
   KV_CHECK(dev >= 0) << "key " << key << " has no optimizer state yet";
   if (e.striped) EnsureWhole(e, dev);

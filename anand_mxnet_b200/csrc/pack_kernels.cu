@@ -12,6 +12,8 @@
 // moved by the other threads with plain byte loads. Copy-only, HBM-bound: 2 bytes of traffic per
 // byte packed.
 #include <cstdio>
+#include <cstdlib>
+#include <string>
 
 #include "common.h"
 #include "kernels.h"
@@ -126,10 +128,60 @@ __global__ void __launch_bounds__(kPackThreads) pack_bulk_kernel(const PackItem*
   }
 }
 
+// Register-path variant for lists with a pinned-HOST side: the SMs issue the PCIe reads / writes
+// themselves (16-byte accesses, four per thread in flight), exactly what the fused kernel does when
+// it reads gradients from host memory. Measured on B200 (profiles/r02_pcie_and_pack.txt): bulk-copy
+// (TMA) transfers across PCIe sustain ~32 GB/s per direction with both directions busy, SM-issued
+// loads / stores ~39 GB/s.
+constexpr int kLdstThreads = 256;
+__global__ void __launch_bounds__(kLdstThreads) pack_ldst_kernel(const PackItem* items, int n_items) {
+  for (int t = blockIdx.x; t < n_items; t += gridDim.x) {
+    const PackItem it = items[t];
+    const uint32_t nb = bulk_bytes(it);           // 16-byte aligned prefix
+    const uint4* s = static_cast<const uint4*>(it.src);
+    uint4* d = static_cast<uint4*>(it.dst);
+    const uint32_t nvec = nb / 16;
+    for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += 4 * kLdstThreads) {
+      uint4 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t v = v0 + u * kLdstThreads;
+        if (v < nvec) x[u] = __ldcs(s + v);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t v = v0 + u * kLdstThreads;
+        if (v < nvec) __stcs(d + v, x[u]);
+      }
+    }
+    const unsigned char* sb = static_cast<const unsigned char*>(it.src);
+    unsigned char* db = static_cast<unsigned char*>(it.dst);
+    for (uint64_t b = nb + threadIdx.x; b < it.bytes; b += kLdstThreads) db[b] = sb[b];
+  }
+}
+
 }  // namespace
 
 void LaunchPackBulk(const PackItem* d_items, int n_items, uint64_t, cudaStream_t stream, int max_ctas) {
   if (n_items <= 0) return;
+  if (max_ctas > 0) {
+    // a host-side list (callers pass max_ctas > 0 only for those); B200KV_PACK_MODE=tma keeps the
+    // bulk-copy engine for them
+    static const bool tma_host = []() {
+      const char* z = std::getenv("B200KV_PACK_MODE");
+      return z != nullptr && std::string(z) == "tma";
+    }();
+    if (!tma_host) {
+      static const int host_ctas = []() {
+        const char* z = std::getenv("B200KV_PACK_HOST_CTAS");
+        return z ? std::max(1, std::atoi(z)) : 96;
+      }();
+      const int grid = n_items < host_ctas ? n_items : host_ctas;
+      pack_ldst_kernel<<<grid, kLdstThreads, 0, stream>>>(d_items, n_items);
+      KV_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   const int smem = kStages * kPackTileBytes;
   // per-device attribute: set on every launch (cheap) so multi-GPU processes are covered
   KV_CUDA(cudaFuncSetAttribute(pack_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

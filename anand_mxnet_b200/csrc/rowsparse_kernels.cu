@@ -296,54 +296,78 @@ __global__ void bm_mark_push_kernel(RspSources s, int64_t lo, int64_t hi, uint32
   for (int64_t j = tid; j < table_words; j += nth) srcpos[j] = 0u;   // source table of the union rows
 }
 
-// one CTA per group: prefix[w] = number of set bits in the words before w; count[g] = set bits
-__global__ void __launch_bounds__(kScanThreads) bm_scan_kernel(const uint32_t* bitmap, int64_t nwords,
-                                                               uint32_t* prefix, int64_t* d_count) {
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t s_total;
-  bitmap += static_cast<int64_t>(blockIdx.x) * nwords;
-  prefix += static_cast<int64_t>(blockIdx.x) * nwords;
+// Rank of every bitmap word. Grid (blocks of 1024 words, groups): each CTA scans the popcounts of
+// its 1024 words (one word per thread) -> prefix[w] = set bits before w INSIDE the block, and
+// publishes the block's total; the last CTA of a group to finish turns the totals into exclusive
+// block bases and writes the group's count. rank(word w) = block_base[w / 1024] + prefix[w].
+constexpr int kScanBlock = kScanThreads;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t c, uint32_t* wsum, uint32_t* total) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t per_warp = (((nwords + 31) / 32) + 31) / 32 * 32;   // words per warp, multiple of 32
-  const int64_t wb = warp * per_warp;
-  const int64_t we = min(wb + per_warp, nwords);
-  uint32_t cnt = 0;
-  for (int64_t w = wb + lane; w < we; w += 32) cnt += __popc(bitmap[w]);
+  uint32_t incl = c;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) wsum[warp] = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
   __syncthreads();
   if (warp == 0) {
     const uint32_t v = wsum[lane];
-    uint32_t incl = v;
+    uint32_t wi = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
     }
-    wsum[lane] = incl - v;
-    if (lane == 31) s_total = incl;
+    wsum[lane] = wi - v;
+    if (lane == 31) *total = wi;
   }
   __syncthreads();
-  uint32_t base = wsum[warp];
-  for (int64_t w0 = wb; w0 < we; w0 += 32) {
-    const int64_t w = w0 + lane;
-    const uint32_t c = w < we ? __popc(bitmap[w]) : 0u;
-    uint32_t incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (w < we) prefix[w] = base + incl - c;
-    base += __shfl_sync(0xffffffffu, incl, 31);
+  const uint32_t excl = wsum[warp] + incl - c;
+  __syncthreads();   // wsum is reused by the caller's next round
+  return excl;
+}
+
+__global__ void __launch_bounds__(kScanThreads) bm_scan_kernel(const uint32_t* bitmap, int64_t nwords,
+                                                               int nblocks, uint32_t* prefix,
+                                                               uint32_t* block_base, uint32_t* done,
+                                                               int64_t* d_count) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t s_total, s_last;
+  const int g = blockIdx.y;
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
+  const uint32_t c = w < nwords ? __popc(bitmap[g * nwords + w]) : 0u;
+  const uint32_t excl = block_exclusive_scan(c, wsum, &s_total);
+  if (w < nwords) prefix[g * nwords + w] = excl;
+  if (threadIdx.x == 0) {
+    block_base[static_cast<int64_t>(g) * nblocks + blockIdx.x] = s_total;
+    __threadfence();
+    s_last = (atomicAdd(&done[g], 1u) == static_cast<uint32_t>(nblocks) - 1u) ? 1u : 0u;
   }
-  if (threadIdx.x == 0) d_count[blockIdx.x] = s_total;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  uint32_t running = 0;
+  uint32_t* bb = block_base + static_cast<int64_t>(g) * nblocks;
+  for (int b0 = 0; b0 < nblocks; b0 += kScanBlock) {
+    const int i = b0 + threadIdx.x;
+    const uint32_t v = i < nblocks ? __ldcg(bb + i) : 0u;
+    const uint32_t e = block_exclusive_scan(v, wsum, &s_total);
+    if (i < nblocks) bb[i] = running + e;
+    running += s_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    d_count[g] = running;
+    done[g] = 0;   // ready for the next call (the memset of the bitmap covers it as well)
+  }
 }
 
 // every (source, position) pair finds its union row: uid[u] = id, srcpos[u][k] = position + 1
 __global__ void bm_scatter_push_kernel(RspSources s, int64_t lo, int64_t hi, const uint32_t* bitmap,
-                                       const uint32_t* prefix, int64_t* uid, uint32_t* srcpos) {
+                                       const uint32_t* prefix, const uint32_t* block_base, int64_t* uid,
+                                       uint32_t* srcpos) {
   const int64_t total = s.start[s.nsrc];
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -352,7 +376,7 @@ __global__ void bm_scatter_push_kernel(RspSources s, int64_t lo, int64_t hi, con
     if (id < lo || id >= hi) continue;
     const int64_t r = id - lo;
     const uint32_t word = bitmap[r >> 5];
-    const uint32_t u = prefix[r >> 5] + __popc(word & ((1u << (r & 31)) - 1u));
+    const uint32_t u = block_base[r >> 15] + prefix[r >> 5] + __popc(word & ((1u << (r & 31)) - 1u));
     uid[u] = id;
     srcpos[static_cast<int64_t>(u) * s.nsrc + k] = static_cast<uint32_t>(i - s.start[k]) + 1u;
   }
@@ -422,7 +446,8 @@ __global__ void bm_mark_pull_kernel(const RetainItem* items, int nitems, int64_t
 
 constexpr int kBmMaxItems = 1024;
 // uniq[off[k] + j] = j-th smallest requested id of item k; off[] = prefix of the items' counts
-__global__ void bm_emit_pull_kernel(const uint32_t* bitmap, const uint32_t* prefix, const int64_t* count,
+__global__ void bm_emit_pull_kernel(const uint32_t* bitmap, const uint32_t* prefix,
+                                    const uint32_t* block_base, int nblocks, const int64_t* count,
                                     int nitems, int64_t nwords, int64_t* uniq, int64_t* off) {
   __shared__ int64_t s_off[kBmMaxItems + 1];
   if (threadIdx.x == 0) {
@@ -441,7 +466,7 @@ __global__ void bm_emit_pull_kernel(const uint32_t* bitmap, const uint32_t* pref
     if (word == 0u) continue;
     const int k = static_cast<int>(j / nwords);
     const int64_t w = j - k * nwords;
-    int64_t* dst = uniq + s_off[k] + prefix[j];
+    int64_t* dst = uniq + s_off[k] + block_base[static_cast<int64_t>(k) * nblocks + (w >> 10)] + prefix[j];
     while (word) {
       const int b = __ffs(word) - 1;
       *dst++ = (w << 5) + b;
@@ -566,7 +591,9 @@ struct MergeLayout {
 struct BmMergeLayout {
   bool ok = false;
   int64_t nwords = 0;
-  size_t bitmap = 0, prefix = 0, uid = 0, srcpos = 0, total = 0;
+  int nblocks = 0;
+  size_t bitmap = 0, done = 0, prefix = 0, block_base = 0, uid = 0, srcpos = 0, total = 0;
+  size_t zero_bytes = 0;   // bitmap + done counter: cleared before every use
 };
 
 BmMergeLayout LayoutMergeBm(int64_t n, int id_bits, int nsrc, int64_t lo, int64_t hi) {
@@ -578,9 +605,13 @@ BmMergeLayout LayoutMergeBm(int64_t n, int id_bits, int nsrc, int64_t lo, int64_
   l.nwords = (top - lo + 31) / 32;
   if (l.nwords > kBitmapMaxWords) return l;
   l.ok = true;
+  l.nblocks = static_cast<int>((l.nwords + kScanBlock - 1) / kScanBlock);
   l.bitmap = 0;
-  l.prefix = up(static_cast<size_t>(l.nwords) * 4);
-  l.uid = l.prefix + up(static_cast<size_t>(l.nwords) * 4);
+  l.done = up(static_cast<size_t>(l.nwords) * 4);
+  l.zero_bytes = l.done + 256;
+  l.prefix = l.zero_bytes;
+  l.block_base = l.prefix + up(static_cast<size_t>(l.nwords) * 4);
+  l.uid = l.block_base + up(static_cast<size_t>(l.nblocks) * 4);
   l.srcpos = l.uid + up(static_cast<size_t>(n) * 8);
   l.total = l.srcpos + up(static_cast<size_t>(n) * std::max(nsrc, 1) * 4) + 256;
   return l;
@@ -659,43 +690,81 @@ __global__ void retain_bounds_kernel(const int64_t* uniq, const int64_t* d_count
   off[k] = lo;
 }
 
+// Persistent warps over the (item, unique id) rows of the batch. A row's bookkeeping (which item,
+// which id: three dependent loads) is fetched for the NEXT row before the current row is copied, so
+// the copy loop never waits for it.
+struct RetainRow {
+  int k;         // item, -1: past the item's unique count (nothing to do)
+  int64_t j;     // position among the item's unique ids
+  int64_t id;
+};
+
+__device__ __forceinline__ RetainRow retain_fetch(const RetainItem* items, int nitems, int64_t i,
+                                                 int64_t total, int id_bits, const int64_t* uniq,
+                                                 const int64_t* off) {
+  RetainRow r{-1, 0, 0};
+  if (i >= total) return r;
+  const int k = find_item(items, nitems, i);
+  const int64_t j = i - items[k].start;
+  const int64_t o = off[k];
+  if (j >= off[k + 1] - o) return r;
+  r.k = k;
+  r.j = j;
+  r.id = uniq[o + j] & ((int64_t{1} << id_bits) - 1);
+  return r;
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 retain_kernel(const RetainItem* items, int nitems, int64_t total, int id_bits, const int64_t* uniq,
               const int64_t* off) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (i >= total) return;
   const int lane = threadIdx.x & 31;
-  const int k = find_item(items, nitems, i);
-  const RetainItem it = items[k];
-  const int64_t j = i - it.start;          // j-th unique id of item k
-  if (j >= off[k + 1] - off[k]) return;
-  const int64_t id = uniq[off[k] + j] & ((int64_t{1} << id_bits) - 1);
-  if (lane == 0) it.out_idx[j] = id;
-  int64_t srow = -1;
-  const float* src_base = it.src_val;
-  if (it.shard_vbase != nullptr) {
-    // the table is cut into row ranges over several GPUs: vbase[d] + id*row_len is row `id`
-    src_base = it.shard_vbase[id / it.rows_per_shard];
-    srow = id;
-  } else if (it.src_dense_rows) {
-    srow = id;
-  } else if (it.src_nnr > 0) {
-    const int64_t lb = warp_lower_bound(it.src_idx, it.src_nnr, id, lane);
-    if (lb < it.src_nnr && it.src_idx[lb] == id) srow = lb;
-  }
-  float* out = it.out_val + j * it.row_len;
-  const float* src = srow >= 0 ? src_base + srow * it.row_len : nullptr;
-  const bool vec = (it.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(it.out_val) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(src_base) & 15) == 0);
-  if (vec) {
-    const int64_t nv = it.row_len / 4;
-    for (int64_t v = lane; v < nv; v += 32) {
-      const float4 x = src ? __ldcs(reinterpret_cast<const float4*>(src) + v)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-      __stcs(reinterpret_cast<float4*>(out) + v, x);
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kWarpsPerBlock;
+  int64_t i = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  RetainRow cur = retain_fetch(items, nitems, i, total, id_bits, uniq, off);
+  while (i < total) {
+    const RetainRow nxt = retain_fetch(items, nitems, i + nwarps, total, id_bits, uniq, off);
+    if (cur.k >= 0) {
+      const RetainItem it = items[cur.k];
+      const int64_t id = cur.id;
+      if (lane == 0) it.out_idx[cur.j] = id;
+      int64_t srow = -1;
+      const float* src_base = it.src_val;
+      if (it.shard_vbase != nullptr) {
+        // the table is cut into row ranges over several GPUs: vbase[d] + id*row_len is row `id`
+        src_base = it.shard_vbase[id / it.rows_per_shard];
+        srow = id;
+      } else if (it.src_dense_rows) {
+        srow = id;
+      } else if (it.src_nnr > 0) {
+        const int64_t lb = warp_lower_bound(it.src_idx, it.src_nnr, id, lane);
+        if (lb < it.src_nnr && it.src_idx[lb] == id) srow = lb;
+      }
+      float* out = it.out_val + cur.j * it.row_len;
+      const float* src = srow >= 0 ? src_base + srow * it.row_len : nullptr;
+      const bool vec = (it.row_len % 4 == 0) && ((reinterpret_cast<uintptr_t>(it.out_val) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(src_base) & 15) == 0);
+      if (vec) {
+        const int64_t nv = it.row_len / 4;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t v0 = lane; v0 < nv; v0 += 128) {   // 4 x 16 bytes in flight per lane
+          float4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t v = v0 + 32 * u;
+            x[u] = (src && v < nv) ? __ldcs(reinterpret_cast<const float4*>(src) + v) : zero;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t v = v0 + 32 * u;
+            if (v < nv) __stcs(reinterpret_cast<float4*>(out) + v, x[u]);
+          }
+        }
+      } else {
+        for (int64_t c = lane; c < it.row_len; c += 32) out[c] = src ? src[c] : 0.f;
+      }
     }
-  } else {
-    for (int64_t c = lane; c < it.row_len; c += 32) out[c] = src ? src[c] : 0.f;
+    cur = nxt;
+    i += nwarps;
   }
 }
 
@@ -705,7 +774,8 @@ struct RetainLayout {
   // region the sort path uses for its keys and temporaries
   bool bm = false;
   int64_t nwords = 0;
-  size_t bm_bitmap = 0, bm_prefix = 0;
+  int nblocks = 0;
+  size_t bm_bitmap = 0, bm_done = 0, bm_zero_bytes = 0, bm_prefix = 0, bm_block_base = 0;
 };
 
 RetainLayout LayoutRetain(int nitems, int64_t n, int id_bits = 0) {
@@ -731,10 +801,14 @@ RetainLayout LayoutRetain(int nitems, int64_t n, int id_bits = 0) {
     if (nwords <= kBitmapMaxWords && nwords * nitems <= kBitmapMaxTotalWords) {
       l.bm = true;
       l.nwords = nwords;
+      l.nblocks = static_cast<int>((nwords + kScanBlock - 1) / kScanBlock);
       const size_t bytes = up(static_cast<size_t>(nwords) * nitems * 4);
       l.bm_bitmap = l.temp;
-      l.bm_prefix = l.temp + bytes;
-      l.total = std::max(l.total, l.bm_prefix + bytes + 256);
+      l.bm_done = l.bm_bitmap + bytes;
+      l.bm_zero_bytes = bytes + up(static_cast<size_t>(nitems) * 4);
+      l.bm_prefix = l.bm_bitmap + l.bm_zero_bytes;
+      l.bm_block_base = l.bm_prefix + bytes;
+      l.total = std::max(l.total, l.bm_block_base + up(static_cast<size_t>(l.nblocks) * nitems * 4) + 256);
     }
   }
   return l;
@@ -781,12 +855,16 @@ void LaunchRspMerge(const RspSources& srcs, int id_bits, int64_t row_len, int64_
     uint32_t* prefix = reinterpret_cast<uint32_t*>(ws + bl.prefix);
     int64_t* uid = reinterpret_cast<int64_t*>(ws + bl.uid);
     uint32_t* srcpos = reinterpret_cast<uint32_t*>(ws + bl.srcpos);
-    KV_CUDA(cudaMemsetAsync(bitmap, 0, static_cast<size_t>(bl.nwords) * 4, stream));
+    uint32_t* block_base = reinterpret_cast<uint32_t*>(ws + bl.block_base);
+    uint32_t* done = reinterpret_cast<uint32_t*>(ws + bl.done);
+    KV_CUDA(cudaMemsetAsync(bitmap, 0, bl.zero_bytes, stream));
     const int64_t table_words = total * srcs.nsrc;
     bm_mark_push_kernel<<<GridFor(std::max(total, table_words / 4), 256), 256, 0, stream>>>(
         srcs, lo, top, bitmap, srcpos, table_words);
-    bm_scan_kernel<<<1, kScanThreads, 0, stream>>>(bitmap, bl.nwords, prefix, d_nnr);
-    bm_scatter_push_kernel<<<GridFor(total, 256), 256, 0, stream>>>(srcs, lo, top, bitmap, prefix, uid, srcpos);
+    bm_scan_kernel<<<dim3(bl.nblocks, 1), kScanThreads, 0, stream>>>(bitmap, bl.nwords, bl.nblocks, prefix,
+                                                                       block_base, done, d_nnr);
+    bm_scatter_push_kernel<<<GridFor(total, 256), 256, 0, stream>>>(srcs, lo, top, bitmap, prefix, block_base,
+                                                                     uid, srcpos);
     KV_CUDA(cudaGetLastError());
     if (row_len <= 0) return;
     MergeSumBm q;
@@ -868,11 +946,14 @@ void LaunchUniqueBatch(const RetainItem* h_items, int nitems, int64_t total, int
     // bitmap unique: mark every item's ids in its own bitmap, rank them, emit them in order
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(ws + l.bm_bitmap);
     uint32_t* prefix = reinterpret_cast<uint32_t*>(ws + l.bm_prefix);
-    KV_CUDA(cudaMemsetAsync(bitmap, 0, static_cast<size_t>(l.nwords) * nitems * 4, stream));
+    uint32_t* block_base = reinterpret_cast<uint32_t*>(ws + l.bm_block_base);
+    uint32_t* done = reinterpret_cast<uint32_t*>(ws + l.bm_done);
+    KV_CUDA(cudaMemsetAsync(bitmap, 0, l.bm_zero_bytes, stream));
     bm_mark_pull_kernel<<<GridFor(total, 256), 256, 0, stream>>>(items, nitems, total, l.nwords, bitmap);
-    bm_scan_kernel<<<nitems, kScanThreads, 0, stream>>>(bitmap, l.nwords, prefix, count);
-    bm_emit_pull_kernel<<<GridFor(l.nwords * nitems, 256), 256, 0, stream>>>(bitmap, prefix, count, nitems,
-                                                                              l.nwords, uniq, d_off);
+    bm_scan_kernel<<<dim3(l.nblocks, nitems), kScanThreads, 0, stream>>>(bitmap, l.nwords, l.nblocks, prefix,
+                                                                          block_base, done, count);
+    bm_emit_pull_kernel<<<GridFor(l.nwords * nitems, 256), 256, 0, stream>>>(
+        bitmap, prefix, block_base, l.nblocks, count, nitems, l.nwords, uniq, d_off);
     KV_CUDA(cudaGetLastError());
     return;
   }
@@ -894,7 +975,7 @@ void LaunchRetainBatch(int nitems, int64_t total, int id_bits, const int64_t* d_
   char* ws = static_cast<char*>(workspace);
   const RetainItem* items = reinterpret_cast<const RetainItem*>(ws + l.items);
   const int64_t* uniq = reinterpret_cast<const int64_t*>(ws + l.uniq);
-  const int blocks = static_cast<int>((total + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const int blocks = static_cast<int>(std::min<int64_t>((total + kWarpsPerBlock - 1) / kWarpsPerBlock, 148 * 8));
   retain_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(items, nitems, total, id_bits, uniq, d_off);
   KV_CUDA(cudaGetLastError());
 }

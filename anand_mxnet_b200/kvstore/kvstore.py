@@ -3,8 +3,8 @@ method (each method = one ``_LIB.MXKVStore*`` call wrapped in ``check_call``).
 
 The one behavioural addition: ``set_optimizer`` hands SGD / Adam / Test to the library's fused
 kernels (``B200KVStoreSetOptimizer``) instead of installing the per-key Python updater callback;
-any other optimizer -- or ``B200KV_FUSED_OPTIMIZER=0`` -- keeps the reference behaviour
-(``_set_updater(opt.get_updater(optimizer))``)."""
+any other optimizer object -- or ``B200KV_FUSED_OPTIMIZER=0`` -- keeps the reference behaviour
+(``_set_updater(get_updater(optimizer))``: the object's own ``update`` runs per key)."""
 import ctypes
 import os
 import pickle
@@ -26,7 +26,6 @@ def _updater_wrapper(updater):
     return updater_handle
 
 
-_FUSED_KINDS = {'SGD': 'sgd', 'Adam': 'adam', 'Test': 'test'}
 
 
 class KVStore(KVStoreBase):
@@ -40,7 +39,8 @@ class KVStore(KVStoreBase):
         self._str_updater_func = None
         self._fused = None       # the Optimizer object whose step runs in the fused kernels
         self._fused_sent = {}    # last scalars handed to the library
-        self._mult_sent = set()
+        self._mult_sent = {}
+        self._keys = []          # every key this front-end initialised, in order
 
     def __del__(self):
         try:
@@ -60,6 +60,9 @@ class KVStore(KVStoreBase):
 
     def init(self, key, value):
         ckeys, cvals, use_str_keys = _ctype_key_value(key, value)
+        for k in (key if isinstance(key, (list, tuple)) else [key]):
+            if k not in self._keys:
+                self._keys.append(k)
         if use_str_keys:
             check_call(_LIB.MXKVStoreInitEx(self.handle, mx_uint(len(ckeys)), ckeys, cvals))
         else:
@@ -141,36 +144,31 @@ class KVStore(KVStoreBase):
     # ------------------------------------------------------------------ optimizer
     def set_optimizer(self, optimizer):
         """kvstore.py:543-590. Single-node stores: install the optimizer as the store's updater --
-        natively fused for SGD / Adam / Test, through the updater callback otherwise."""
-        kind = _FUSED_KINDS.get(type(optimizer).__name__)
-        fused_ok = kind is not None and os.environ.get('B200KV_FUSED_OPTIMIZER', '1') != '0' \
-            and type(optimizer).__module__ == opt.__name__
-        if fused_ok:
-            self._set_fused(optimizer, kind)
+        natively fused for SGD / Adam / Test (a hyper-parameter record, or an object of the
+        reference's classes of those names), through the updater callback otherwise."""
+        kind = opt.fused_kind(optimizer)
+        if kind is not None and os.environ.get('B200KV_FUSED_OPTIMIZER', '1') != '0':
+            self._set_fused(opt.record_of(optimizer))
         else:
             self._fused = None
             self._set_updater(opt.get_updater(optimizer))
 
-    def _set_fused(self, optimizer, kind):
-        o = optimizer
-        params = {'learning_rate': o.learning_rate, 'wd': o.wd, 'rescale_grad': o.rescale_grad,
-                  'clip_gradient': o.clip_gradient if o.clip_gradient else 0.0,
-                  'multi_precision': bool(o.multi_precision),
-                  'begin_num_update': o.begin_num_update}
-        if kind == 'sgd':
-            params['momentum'] = o.momentum
-            params['lazy_update'] = bool(o.lazy_update)
-        elif kind == 'adam':
-            params.update(beta1=o.beta1, beta2=o.beta2, epsilon=o.epsilon,
-                          lazy_update=bool(o.lazy_update))
+    def _set_fused(self, record):
+        params = record.op_params()
         keys = list(params.keys())
         vals = [repr(float(v)) if isinstance(v, float) else str(v) for v in params.values()]
-        check_call(_LIB.B200KVStoreSetOptimizer(self.handle, c_str(kind), mx_uint(len(keys)),
+        check_call(_LIB.B200KVStoreSetOptimizer(self.handle, c_str(record.kind), mx_uint(len(keys)),
                                                 c_str_array(keys), c_str_array(vals)))
-        self._fused = o
+        self._fused = record
         self._updater = None
-        self._fused_sent = {'lr': o.learning_rate, 'rescale': o.rescale_grad}
-        self._mult_sent = set()
+        self._fused_sent = {'lr': record.learning_rate, 'rescale': record.rescale_grad,
+                            'rest': self._rest_of(params)}
+        self._mult_sent = {}
+
+    @staticmethod
+    def _rest_of(params):
+        return tuple(sorted((k, v) for k, v in params.items()
+                            if k not in ('learning_rate', 'rescale_grad', 'begin_num_update')))
 
     def _native_key(self, key):
         if isinstance(key, int):
@@ -180,31 +178,39 @@ class KVStore(KVStoreBase):
         return k.value
 
     def _sync_fused(self, key):
-        """Hand the per-step scalars and the per-key multipliers of the Python Optimizer object
-        (lr / lr_scheduler, rescale_grad, lr_mult, wd_mult) to the library when they changed."""
+        """Hand what may have changed on the Python side since the last call to the library: the
+        per-key (lr, wd) multipliers of the keys about to be pushed, the learning rate (scheduler
+        included), rescale_grad."""
         o = self._fused
         if o is None:
             return
+        src = getattr(o, '_source', None)
+        if src is not None:      # an optimizer object of the reference's classes: re-read its fields
+            for name in ('lr', 'wd', 'rescale_grad', 'lr_mult', 'wd_mult', 'idx2name', 'param_dict'):
+                setattr(o, name, getattr(src, name))
+            for name in ('momentum', 'clip_gradient', 'beta1', 'beta2', 'epsilon'):
+                if hasattr(src, name):
+                    setattr(o, name, getattr(src, name))
+        rest = self._rest_of(o.op_params())
+        if rest != self._fused_sent['rest']:
+            # wd / momentum / clip_gradient / betas changed on the live optimizer: re-configure (the
+            # library keeps update counts, multipliers and states of an optimizer of the same kind)
+            mult = self._mult_sent
+            self._set_fused(o)
+            self._mult_sent = mult
         keys = key if isinstance(key, (list, tuple)) else [key]
-        new = [k for k in keys if k not in self._mult_sent]
-        if new:
-            nk = [self._native_key(k) for k in new]
-            lrm = o._get_lrs(new)
-            wdm = o._get_wds(new)
-            base_lr = o.learning_rate
-            lr_mult = [(l / base_lr) if base_lr != 0 else 1.0 for l in lrm]
-            wd_mult = [(w / o.wd) if o.wd != 0 else 1.0 for w in wdm]
-            # exact multipliers (not ratios) when they are directly available
-            for i, k in enumerate(new):
-                lm, wm = _exact_mults(o, k)
-                if lm is not None:
-                    lr_mult[i] = lm
-                if wm is not None:
-                    wd_mult[i] = wm
+        changed = []
+        for k in keys:
+            m = o.multipliers(k)
+            if self._mult_sent.get(k) != m:
+                self._mult_sent[k] = m
+                changed.append((self._native_key(k), m))
+        if changed:
+            n = len(changed)
             check_call(_LIB.B200KVStoreSetKeyMultipliers(
-                self.handle, mx_uint(len(nk)), (ctypes.c_int * len(nk))(*nk),
-                (ctypes.c_double * len(nk))(*lr_mult), (ctypes.c_double * len(nk))(*wd_mult)))
-            self._mult_sent.update(new)
+                self.handle, mx_uint(n), (ctypes.c_int * n)(*[c[0] for c in changed]),
+                (ctypes.c_double * n)(*[c[1][0] for c in changed]),
+                (ctypes.c_double * n)(*[c[1][1] for c in changed])))
         if o.lr_scheduler is not None:
             # Optimizer._update_count then _get_lr (optimizer.py:412-441): the scheduler sees
             # num_update = max over every index's count, this push included
@@ -248,10 +254,22 @@ class KVStore(KVStoreBase):
         return size.value
 
     def save_optimizer_states(self, fname, dump_optimizer=False):
-        """Same pickle layout as Updater.get_states (optimizer.py:2155-2161): {index: state}."""
+        """Same pickle as Updater.get_states (optimizer.py:2155-2161): {index: state}, or
+        (states, optimizer) with dump_optimizer. Fused route: the states are fetched from the
+        library in the layout the reference's optimizer would have created -- SGD: momentum, or
+        (momentum, fp32 master) under multi_precision (optimizer.py:584-594); Adam: (mean, var), or
+        (fp32 master, (mean, var)) (optimizer.py:256-268) -- and the optimizer record carries the
+        library's update counts, so a resumed Adam keeps its bias-correction step."""
         if self._fused is not None:
             states = self._fused_states()
-            payload = pickle.dumps((states, self._fused) if dump_optimizer else states)
+            if dump_optimizer:
+                target = getattr(self._fused, '_source', None) or self._fused
+                counts = {k: self._native_count(k) for k in self._keys}
+                target._index_update_count = counts
+                target.num_update = max([target.num_update] + list(counts.values()))
+                payload = pickle.dumps((states, target))
+            else:
+                payload = pickle.dumps(states)
         else:
             assert self._updater is not None, "Cannot save states for distributed training"
             payload = self._updater.get_states(dump_optimizer)
@@ -264,16 +282,30 @@ class KVStore(KVStoreBase):
         if self._fused is not None:
             states = pickle.loads(data)
             if isinstance(states, tuple) and len(states) == 2:
-                states = states[0]
+                states, saved = states
+                if opt.fused_kind(saved) is not None:       # Updater.set_states swaps the optimizer in
+                    self._set_fused(opt.record_of(saved))
+                counts = getattr(saved, '_index_update_count', None) or {}
+                for k, c in counts.items():
+                    if k in self._keys:
+                        check_call(_LIB.B200KVStoreSetUpdateCount(self.handle,
+                                                                  ctypes.c_int(self._native_key(k)),
+                                                                  ctypes.c_int(int(c))))
             self._load_fused_states(states)
         else:
             assert self._updater is not None, "Cannot load states for distributed training"
             self._updater.set_states(data)
 
+    def _native_count(self, key):
+        c = ctypes.c_int()
+        check_call(_LIB.B200KVStoreGetUpdateCount(self.handle, ctypes.c_int(self._native_key(key)),
+                                                  ctypes.byref(c)))
+        return c.value
+
     def _fused_states(self):
-        kind = _FUSED_KINDS[type(self._fused).__name__]
+        kind = self._fused.kind
         out = {}
-        for k in sorted(self._mult_sent, key=str):
+        for k in self._keys:
             nk = self._native_key(k)
 
             def get(sid):
@@ -282,21 +314,37 @@ class KVStore(KVStoreBase):
                                                      ctypes.byref(h)) != 0:
                     return None
                 return NDArray(h)
+            w32 = get(2)
             if kind == 'sgd':
-                out[k] = get(0)
+                mom = get(0)
+                out[k] = (mom, w32) if w32 is not None else mom
             elif kind == 'adam':
-                out[k] = (get(0), get(1))
+                mv = (get(0), get(1))
+                if mv[0] is None and w32 is None:
+                    continue                                # never pushed: no state yet
+                out[k] = (w32, mv) if w32 is not None else mv
         return out
 
     def _load_fused_states(self, states):
+        kind = self._fused.kind
         for k, st in states.items():
             nk = self._native_key(k)
-            parts = st if isinstance(st, (tuple, list)) else (st,)
-            for sid, s in enumerate(parts):
-                if s is None:
+            slots = {}                                      # state_id -> array
+            if kind == 'sgd':
+                if isinstance(st, (tuple, list)):
+                    slots[0], slots[2] = st[0], st[1]
+                else:
+                    slots[0] = st
+            elif kind == 'adam':
+                if isinstance(st, (tuple, list)) and len(st) == 2 and isinstance(st[1], (tuple, list)):
+                    slots[2], (slots[0], slots[1]) = st[0], st[1]
+                elif isinstance(st, (tuple, list)):
+                    slots[0], slots[1] = st[0], st[1]
+            for sid, arr in slots.items():
+                if arr is None:
                     continue
                 check_call(_LIB.B200KVStoreSetOptimizerState(self.handle, ctypes.c_int(nk),
-                                                             ctypes.c_int(sid), s.handle))
+                                                             ctypes.c_int(sid), arr.handle))
 
     def _set_updater(self, updater):
         """kvstore.py:658-696"""
@@ -324,26 +372,3 @@ class KVStore(KVStoreBase):
 
     def _send_command_to_servers(self, head, body):
         check_call(_LIB.MXKVStoreSendCommmandToServers(self.handle, mx_uint(head), c_str(body)))
-
-
-def _exact_mults(o, index):
-    """Optimizer._get_lrs / _get_wds lookup order (optimizer.py:432-509), returning the multipliers
-    themselves so the library multiplies exactly as the reference does (lr * mult in double)."""
-    lm = wm = None
-    if index in o.param_dict:
-        lm = o.param_dict[index].lr_mult
-        wm = o.param_dict[index].wd_mult
-        return lm, wm
-    if index in o.lr_mult:
-        lm = o.lr_mult[index]
-    elif index in o.idx2name:
-        lm = o.lr_mult.get(o.idx2name[index], 1.0)
-    else:
-        lm = 1.0
-    if index in o.wd_mult:
-        wm = o.wd_mult[index]
-    elif index in o.idx2name:
-        wm = o.wd_mult.get(o.idx2name[index], 1.0)
-    else:
-        wm = 1.0
-    return lm, wm

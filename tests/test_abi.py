@@ -96,12 +96,23 @@ def test_registry_and_teststore(mx):
 
 
 def test_optimizer_bookkeeping(mx):
-    """lr / wd multipliers and update counts (optimizer.py:412-509), no device work involved."""
+    """the hyper-parameter record kv.set_optimizer takes: per-parameter lr / wd multipliers with the
+    reference's lookup order (optimizer.py:432-509), no device work involved."""
     opt = mx.optimizer.SGD(learning_rate=0.1, wd=0.01, param_idx2name={0: 'fc_weight', 1: 'fc_bias'})
     opt.set_lr_mult({'fc_bias': 2.0})
-    assert opt._get_lrs([0, 1]) == [0.1, 0.2]
-    assert opt._get_wds([0, 1]) == [0.01, 0.0]          # biases get wd_mult 0 by name
-    opt._update_count([0, 1])
-    opt._update_count(0)
-    assert opt.num_update == 2 and opt._index_update_count == {0: 2, 1: 1}
-    assert mx.optimizer.create('adam', learning_rate=3e-4).lr == 3e-4
+    assert opt.multipliers(0) == (1.0, 1.0)
+    assert opt.multipliers(1) == (2.0, 0.0)            # biases get wd_mult 0 by name
+    opt.set_wd_mult({1: 0.5})                            # an index entry beats the name rule
+    assert opt.multipliers(1) == (2.0, 0.5)
+
+    class P(object):
+        lr_mult, wd_mult = 3.0, 4.0
+    opt.param_dict = {0: P()}                            # a Parameter object beats both tables
+    assert opt.multipliers(0) == (3.0, 4.0)
+    adam = mx.optimizer.create('adam', learning_rate=3e-4)
+    assert adam.lr == 3e-4 and adam.kind == 'adam' and adam.beta2 == 0.999
+    assert adam.op_params()['epsilon'] == 1e-8 and mx.optimizer.fused_kind(adam) == 'adam'
+    with pytest.raises(ValueError):
+        mx.optimizer.create('lars')                      # no fused kernel: callback route only
+    with pytest.raises(TypeError):
+        mx.optimizer.get_updater(opt)                    # a record carries no update rule

