@@ -13,6 +13,7 @@
 #include <set>
 
 #include "group.h"
+#include "nccl_dyn.h"
 #include "kvstore.h"
 #include "scalar_parse.h"
 
@@ -101,8 +102,17 @@ bool KVStore::CallSignature(int tag, const std::vector<int>& vkeys, const std::v
                             const std::vector<int>* okeys, const std::vector<NDArray>* outs,
                             std::vector<uint64_t>* sig) {
   sig->clear();
-  sig->reserve(4 + 3 * vkeys.size() + (okeys ? 3 * okeys->size() : 0));
-  sig->push_back(static_cast<uint64_t>(tag));
+  sig->reserve(5 + 3 * vkeys.size() + (okeys ? 3 * okeys->size() : 0));
+  // one-rank-per-GPU calls with host-resident operands are staged through the arena: consecutive
+  // calls alternate between two generations of staging buffers (two cached launches per call
+  // pattern), so step k's transfer out overlaps step k+1's kernel
+  bool host_operand = false;
+  if (dist_) {
+    for (auto& a : values) host_operand = host_operand || (!a.is_none() && !a.on_gpu());
+    if (outs != nullptr) for (auto& a : *outs) host_operand = host_operand || (!a.is_none() && !a.on_gpu());
+  }
+  if (host_operand) stage_gen_ ^= 1; else stage_gen_ = 0;
+  sig->push_back(static_cast<uint64_t>(tag) * 2 + static_cast<uint64_t>(stage_gen_));
   sig->push_back(vkeys.size());
   for (size_t i = 0; i < vkeys.size(); ++i) {
     const NDArray& a = values[i];
@@ -308,6 +318,19 @@ void KVStore::RunPrepared(Prepared& P) {
   const bool fused_opt = P.is_push && opt_.enabled && (opt_kind == kOptSGD || opt_kind == kOptAdam);
   if (P.pack_in) RunPackList(*P.pack_in);
   for (auto& io : P.stage_in) CopyFromTo(io.first, io.second);
+  if (!P.nccl_bucket.is_none()) {
+    // NCCL fallback: sum the packed gradients of all ranks in place, on the compute lane's stream
+    PeerGroup* g = PeerGroup::Get();
+    KV_CHECK(g != nullptr) << "the peer group was destroyed while a store still uses it";
+    const int dev = g->dev();
+    NcclComm comm = g->NcclCommunicator();
+    eng->BeginWrite(dev, *P.nccl_bucket.var());
+    DeviceGuard guard(dev);
+    Nccl::Get()->AllReduceSum(P.nccl_bucket.data(), P.nccl_bucket.data(), P.nccl_bucket.Size(), P.dtype, comm,
+                              eng->Stream(dev));
+    eng->CountLaunch("ncclAllReduce", P.nccl_bucket.ByteSize());
+    eng->MarkWrite(dev, eng->Issue(dev), P.nccl_bucket.var());
+  }
 
   // ---- optimizer bookkeeping: update counts first (Optimizer._update_count, optimizer.py:412-430)
   if (fused_opt) {
@@ -363,6 +386,7 @@ void KVStore::RunPrepared(Prepared& P) {
   // ---- launch, one kernel per owner
   DenseLaunch L = P.scalars;
   L.max_src = P.plan->max_src;
+  L.nvls = P.plan->nvls;
   L.dtype = P.dtype;
   L.opt = opt_kind;
   L.order = order_local_ ? kOrderLocal : kOrderDevice;

@@ -103,77 +103,104 @@ template <> struct IO<float, 1> {
   static __device__ __forceinline__ void st(float* p, const float (&x)[1]) { __stcs(p, x[0]); }
 };
 
-// Process V consecutive elements starting at element `e` of the chunk.
-template <typename T, int MAXSRC, int OPT, int V>
-__device__ __forceinline__ void process(const KeyDesc& k, uint32_t base, int n_src, int n_out,
-                                        int order, const Hyper& h) {
-  float acc[V];
-  float wv[V], s1[V], s2[V];
+// Process U groups of V consecutive elements: group u starts at element off + (v0 + u*kThreads)*V
+// and exists while its vector index is below nvec. EVERY load of every group is issued before the
+// first arithmetic instruction or store (stores to possibly aliasing pointers would otherwise pin
+// the loads of the next group behind them): U x (n_src + 1 + states) 16-byte loads in flight per
+// thread, which is what covers NVLink latency when the sources are peer memory.
+template <typename T, int MAXSRC, int OPT, int V, int U>
+__device__ __forceinline__ void process(const KeyDesc& k, uint32_t off, uint32_t v0, uint32_t nvec,
+                                        int n_src, int n_out, int order, const Hyper& h) {
+  float acc[U][V];
+  float wv[U][V], s1[U][V], s2[U][V];
   const bool has_mom = k.s1 != nullptr;
   const bool mp = k.w32 != nullptr;
+  uint32_t base[U];
+  bool on[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint32_t v = v0 + u * kThreads;
+    on[u] = v < nvec;
+    base[u] = off + v * V;
+  }
   if (OPT != kOptPullOnly) {
-    // ---- issue every load before the first use: n_src gradient vectors + w (+ state)
-    float g[MAXSRC][V];
+    float g[U][MAXSRC][V];
 #pragma unroll
-    for (int i = 0; i < MAXSRC; ++i) {
-      if (i < n_src) IO<T, V>::ld(static_cast<const T*>(k.src[i]) + base, g[i]);
-    }
-    if (OPT != kOptAssign) {
-      if (mp) {
-        IO<float, V>::ld(k.w32 + base, wv);
-      } else {
-        IO<T, V>::ld(static_cast<const T*>(k.w) + base, wv);
+    for (int u = 0; u < U; ++u) {
+      if (!on[u]) continue;
+#pragma unroll
+      for (int i = 0; i < MAXSRC; ++i) {
+        if (i < n_src) IO<T, V>::ld(static_cast<const T*>(k.src[i]) + base[u], g[u][i]);
       }
-      if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::ld(k.s1 + base, s1);
-      if (OPT == kOptAdam) IO<float, V>::ld(k.s2 + base, s2);
-    }
-    // ---- merged gradient in the reference's association; 16-bit dtypes round after every add,
-    // as mshadow's half arithmetic does (3rdparty/mshadow/mshadow/half.h:45-66)
-#pragma unroll
-    for (int j = 0; j < V; ++j) acc[j] = g[0][j];
-    if (order == kOrderDevice) {
-      // ((g0+g1)+g2)+...   (ndarray_function-inl.h:402-431)
-#pragma unroll
-      for (int i = 1; i < MAXSRC; ++i) {
-        if (i < n_src) {
-#pragma unroll
-          for (int j = 0; j < V; ++j) acc[j] = Cvt<T>::round(__fadd_rn(acc[j], g[i][j]));
+      if (OPT != kOptAssign) {
+        if (mp) {
+          IO<float, V>::ld(k.w32 + base[u], wv[u]);
+        } else {
+          IO<T, V>::ld(static_cast<const T*>(k.w) + base[u], wv[u]);
         }
+        if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::ld(k.s1 + base[u], s1[u]);
+        if (OPT == kOptAdam) IO<float, V>::ld(k.s2 + base[u], s2[u]);
       }
-    } else {
-      // g0 + (((g1+g2)+g3)+g4) + (((g5+..  (comm.h:357-392)
+    }
 #pragma unroll
-      for (int i = 1; i < MAXSRC; i += 4) {
-        if (i < n_src) {
-          float t[V];
+    for (int u = 0; u < U; ++u) {
+      if (!on[u]) continue;
+      // ---- merged gradient in the reference's association; 16-bit dtypes round after every add,
+      // as mshadow's half arithmetic does (3rdparty/mshadow/mshadow/half.h:45-66)
 #pragma unroll
-          for (int j = 0; j < V; ++j) t[j] = g[i][j];
+      for (int j = 0; j < V; ++j) acc[u][j] = g[u][0][j];
+      if (order == kOrderDevice) {
+        // ((g0+g1)+g2)+...   (ndarray_function-inl.h:402-431)
 #pragma unroll
-          for (int q = 1; q < 4; ++q) {
-            if (i + q < MAXSRC && i + q < n_src) {
+        for (int i = 1; i < MAXSRC; ++i) {
+          if (i < n_src) {
 #pragma unroll
-              for (int j = 0; j < V; ++j) t[j] = Cvt<T>::round(__fadd_rn(t[j], g[i + q][j]));
-            }
+            for (int j = 0; j < V; ++j) acc[u][j] = Cvt<T>::round(__fadd_rn(acc[u][j], g[u][i][j]));
           }
+        }
+      } else {
+        // g0 + (((g1+g2)+g3)+g4) + (((g5+..  (comm.h:357-392)
 #pragma unroll
-          for (int j = 0; j < V; ++j) acc[j] = Cvt<T>::round(__fadd_rn(acc[j], t[j]));
+        for (int i = 1; i < MAXSRC; i += 4) {
+          if (i < n_src) {
+            float t[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) t[j] = g[u][i][j];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+              if (i + q < MAXSRC && i + q < n_src) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) t[j] = Cvt<T>::round(__fadd_rn(t[j], g[u][i + q][j]));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[u][j] = Cvt<T>::round(__fadd_rn(acc[u][j], t[j]));
+          }
         }
       }
-    }
-    // ---- optimizer step
-    if (OPT != kOptAssign) {
+      // ---- optimizer step
+      if (OPT != kOptAssign) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = step<OPT>(wv[j], acc[j], s1[j], s2[j], has_mom, h);
-      if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::st(k.s1 + base, s1);
-      if (OPT == kOptAdam) IO<float, V>::st(k.s2 + base, s2);
-      if (mp) IO<float, V>::st(k.w32 + base, acc);
+        for (int j = 0; j < V; ++j) acc[u][j] = step<OPT>(wv[u][j], acc[u][j], s1[u][j], s2[u][j], has_mom, h);
+        if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::st(k.s1 + base[u], s1[u]);
+        if (OPT == kOptAdam) IO<float, V>::st(k.s2 + base[u], s2[u]);
+        if (mp) IO<float, V>::st(k.w32 + base[u], acc[u]);
+      }
+      IO<T, V>::st(static_cast<T*>(k.w) + base[u], acc[u]);
     }
-    IO<T, V>::st(static_cast<T*>(k.w) + base, acc);
   } else {
-    IO<T, V>::ld(static_cast<const T*>(k.w) + base, acc);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (on[u]) IO<T, V>::ld(static_cast<const T*>(k.w) + base[u], acc[u]);
+    }
   }
   // ---- broadcast to every pull target (peer stores ride NVLink)
-  for (int o = 0; o < n_out; ++o) IO<T, V>::st(static_cast<T*>(k.out[o]) + base, acc);
+  for (int o = 0; o < n_out; ++o) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (on[u]) IO<T, V>::st(static_cast<T*>(k.out[o]) + base[u], acc[u]);
+    }
+  }
 }
 
 // ---- NVLS variant of one fp32 vector: the cross-rank sum happens INSIDE the NVSwitch
@@ -212,28 +239,58 @@ template <> struct MM<1> {
   }
 };
 
-template <int OPT, int V>
-__device__ __forceinline__ void process_nvls(const KeyDesc& k, uint32_t base, const Hyper& h) {
-  float acc[V], wv[V], s1[V], s2[V];
+// U groups per thread, every multimem.ld_reduce (and the local weight / state loads) in flight before
+// the first store: a switch-reduced load takes several microseconds to come back, one at a time per
+// thread leaves the links idle most of the time.
+template <int OPT, int V, int U>
+__device__ __forceinline__ void process_nvls(const KeyDesc& k, uint32_t off, uint32_t v0, uint32_t nvec,
+                                             const Hyper& h) {
+  float acc[U][V], wv[U][V], s1[U][V], s2[U][V];
   const bool has_mom = k.s1 != nullptr;
   float* w = static_cast<float*>(k.w);
-  if (OPT != kOptPullOnly) {
-    MM<V>::ld_reduce(static_cast<const float*>(k.src[kMaxSrc - 1]) + base, acc);
-    if (OPT != kOptAssign) {
-      IO<float, V>::ld(w + base, wv);
-      if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::ld(k.s1 + base, s1);
-      if (OPT == kOptAdam) IO<float, V>::ld(k.s2 + base, s2);
+  uint32_t base[U];
+  bool on[U];
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = step<OPT>(wv[j], acc[j], s1[j], s2[j], has_mom, h);
-      if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::st(k.s1 + base, s1);
-      if (OPT == kOptAdam) IO<float, V>::st(k.s2 + base, s2);
+  for (int u = 0; u < U; ++u) {
+    const uint32_t v = v0 + u * kThreads;
+    on[u] = v < nvec;
+    base[u] = off + v * V;
+  }
+  if (OPT != kOptPullOnly) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!on[u]) continue;
+      MM<V>::ld_reduce(static_cast<const float*>(k.src[kMaxSrc - 1]) + base[u], acc[u]);
+      if (OPT != kOptAssign) {
+        IO<float, V>::ld(w + base[u], wv[u]);
+        if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::ld(k.s1 + base[u], s1[u]);
+        if (OPT == kOptAdam) IO<float, V>::ld(k.s2 + base[u], s2[u]);
+      }
     }
-    IO<float, V>::st(w + base, acc);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!on[u]) continue;
+      if (OPT != kOptAssign) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[u][j] = step<OPT>(wv[u][j], acc[u][j], s1[u][j], s2[u][j], has_mom, h);
+        if ((OPT == kOptSGD && has_mom) || OPT == kOptAdam) IO<float, V>::st(k.s1 + base[u], s1[u]);
+        if (OPT == kOptAdam) IO<float, V>::st(k.s2 + base[u], s2[u]);
+      }
+      IO<float, V>::st(w + base[u], acc[u]);
+    }
   } else {
-    IO<float, V>::ld(w + base, acc);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (on[u]) IO<float, V>::ld(w + base[u], acc[u]);
+    }
   }
   const int n_mc = static_cast<int>(k.nvls) - 1;
-  for (int o = 0; o < n_mc; ++o) MM<V>::st(static_cast<float*>(k.out[kMaxDst - 2 + o]) + base, acc);
+  for (int o = 0; o < n_mc; ++o) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (on[u]) MM<V>::st(static_cast<float*>(k.out[kMaxDst - 2 + o]) + base[u], acc[u]);
+    }
+  }
 }
 
 struct KernelArgs {
@@ -302,9 +359,16 @@ __device__ __forceinline__ void peer_signal_and_wait(const KernelArgs& a, int ph
   }
 }
 
-template <typename T, int MAXSRC, int OPT>
-__global__ void __launch_bounds__(kThreads) dense_fused_kernel(const KernelArgs a) {
+// NVLS: the instantiation for launches whose sums happen in the NVSwitch (fp32, MAXSRC = 1).
+// U (groups of V elements per thread with all loads in flight): 1 for one local source -- the
+// HBM-bound case already runs at 0.95 of the copy peak --, 2 when peer memory is read, 4 for the
+// switch-reduced loads.
+template <typename T, int MAXSRC, int OPT, bool NVLS>
+__global__ void __launch_bounds__(kThreads, (MAXSRC == 1 && !NVLS) ? 5 : 1)
+dense_fused_kernel(const KernelArgs a) {
   constexpr int V = 16 / sizeof(T);
+  // the gradient registers of a thread (MAXSRC x V x U floats) are kept to 64
+  constexpr int U = NVLS ? 4 : ((MAXSRC >= 2 && MAXSRC * V * 2 <= 64) ? 2 : 1);
   __shared__ KeyDesc sk;
   __shared__ uint32_t s_last;
   if (a.pads != nullptr) {
@@ -328,15 +392,20 @@ __global__ void __launch_bounds__(kThreads) dense_fused_kernel(const KernelArgs 
   h.beta1 = a.beta1; h.beta2 = a.beta2; h.eps = a.eps;
   const int n_src = sk.n_src, n_out = sk.n_out;
   const uint32_t nvec = sk.vec_ok ? c.len / V : 0;
-  if (sizeof(T) == 4 && sk.nvls != 0) {
-    for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) process_nvls<OPT, 4>(sk, c.off + v * 4, h);
-    for (uint32_t e = nvec * 4 + threadIdx.x; e < c.len; e += kThreads) process_nvls<OPT, 1>(sk, c.off + e, h);
-  } else {
-    for (uint32_t v = threadIdx.x; v < nvec; v += kThreads) {
-      process<T, MAXSRC, OPT, V>(sk, c.off + v * V, n_src, n_out, a.order, h);
+  if (NVLS) {
+    // (host side: NVLS plans are fp32 and every key of the launch carries multicast addresses)
+    for (uint32_t v = threadIdx.x; v < nvec; v += kThreads * U) process_nvls<OPT, 4, U>(sk, c.off, v, nvec, h);
+    const uint32_t ntail = c.len - nvec * 4;
+    for (uint32_t e = threadIdx.x; e < ntail; e += kThreads) {
+      process_nvls<OPT, 1, 1>(sk, c.off + nvec * 4, e, ntail, h);
     }
-    for (uint32_t e = nvec * V + threadIdx.x; e < c.len; e += kThreads) {
-      process<T, MAXSRC, OPT, 1>(sk, c.off + e, n_src, n_out, a.order, h);
+  } else {
+    for (uint32_t v = threadIdx.x; v < nvec; v += kThreads * U) {
+      process<T, MAXSRC, OPT, V, U>(sk, c.off, v, nvec, n_src, n_out, a.order, h);
+    }
+    const uint32_t ntail = c.len - nvec * V;
+    for (uint32_t e = threadIdx.x; e < ntail; e += kThreads) {
+      process<T, MAXSRC, OPT, 1, 1>(sk, c.off + nvec * V, e, ntail, n_src, n_out, a.order, h);
     }
   }
   }  // blockIdx.x < n_chunks
@@ -360,17 +429,21 @@ __global__ void __launch_bounds__(kThreads) dense_fused_kernel(const KernelArgs 
   }
 }
 
-template <typename T, int MAXSRC, int OPT>
+template <typename T, int MAXSRC, int OPT, bool NVLS = false>
 void launch_one(const DenseLaunch& p, cudaStream_t s) {
   KernelArgs a{p.keys, p.chunks, reinterpret_cast<const float2*>(p.hyper), p.lrs, p.wds, p.order, p.momentum,
                p.rescale, p.clip, p.beta1, p.beta2, p.eps, p.signal_pads, p.counter, p.rank, p.world,
                p.epoch, p.n_chunks, p.err_word, p.timeout_ns};
   const int grid = p.n_chunks > 0 ? p.n_chunks : 1;  // a rank with no chunk still joins the barriers
-  dense_fused_kernel<T, MAXSRC, OPT><<<grid, kThreads, 0, s>>>(a);
+  dense_fused_kernel<T, MAXSRC, OPT, NVLS><<<grid, kThreads, 0, s>>>(a);
 }
 
 template <typename T, int OPT>
 void launch_src(const DenseLaunch& p, cudaStream_t s) {
+  if (p.nvls) {
+    if constexpr (sizeof(T) == 4) return launch_one<T, 1, OPT, true>(p, s);
+    KV_FATAL << "NVLS launches are float32";
+  }
   if (OPT == kOptPullOnly || p.max_src <= 1) return launch_one<T, 1, OPT>(p, s);
   if (p.max_src <= 2) return launch_one<T, 2, OPT>(p, s);
   if (p.max_src <= 4) return launch_one<T, 4, OPT>(p, s);

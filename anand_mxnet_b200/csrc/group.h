@@ -67,6 +67,12 @@ class PeerGroup {
   uint32_t NextEpoch() { return ++epoch_; }
   // barrier part of a fused launch: pads, counter, rank / world, a fresh epoch, the time-out policy
   void FillLaunch(struct DenseLaunch* L);
+  // false when the ranks' arenas could not be IPC-mapped (no GPU peer access between them, or
+  // B200KV_GROUP_NO_IPC=1): stores then use the NCCL fallback collective instead of peer memory
+  bool ipc_ok() const { return ipc_ok_; }
+  // NCCL communicator over the group's ranks, created on first use (unique id from rank 0 through
+  // the launcher's all-gather callback). Collective: every rank must call it at the same point.
+  void* NcclCommunicator();
 
  private:
   PeerGroup() {}
@@ -82,6 +88,17 @@ class PeerGroup {
   uint32_t** d_pads_ = nullptr;
   uint32_t* d_counter_ = nullptr;
   uint32_t epoch_ = 0;
+  bool ipc_ok_ = true;
+  void* nccl_comm_ = nullptr;
+  // host-side mailbox between the ranks of the node (POSIX shared memory, created at Init through
+  // ONE exchange over the launcher's callback): later all-gathers of a few KB -- operand offsets
+  // when a launch is planned, the (ids, rows, count) descriptor of every row_sparse push -- take a
+  // microsecond of spinning on shared memory instead of a trip through the launcher's transport
+  void InitMailbox();
+  bool MailboxAllGather(const void* send, void* recv, size_t nbytes);
+  char* mbox_ = nullptr;
+  size_t mbox_bytes_ = 0;
+  uint64_t mbox_seq_ = 0;
 };
 
 // Pure host logic, testable without a GPU: rank-major gather of equal-length int64 vectors through

@@ -67,6 +67,7 @@ struct DenseLaunch {
   const float* wds = nullptr;         // device arrays (override hyper when set)
   int n_chunks = 0;
   int max_src = 0;     // max n_src over the keys (selects the unroll variant)
+  bool nvls = false;   // every key of the launch carries NVSwitch multicast addresses (KeyDesc::nvls)
   int dtype = 0;       // key dtype: kFloat32 / kFloat16 / kBfloat16
   int opt = kOptAssign;
   int order = kOrderDevice;

@@ -133,6 +133,9 @@ struct Prepared {
   int dtype = kFloat32;
   bool is_push = false;
   bool group = false;                                    // one-rank-per-GPU launch (group.h)
+  // NCCL fallback (kvstore 'nccl', or a peer group without peer memory): the sources were packed
+  // into `nccl_bucket`, which is all-reduced in place before the (local, one-source) fused kernel
+  NDArray nccl_bucket;
   std::vector<DenseOp> ops;                              // device-side operands
   std::vector<std::pair<NDArray, NDArray>> stage_in;     // (host source, device staging buffer)
   std::vector<std::pair<NDArray, NDArray>> stage_out;    // (device staging buffer, host out)
@@ -206,6 +209,8 @@ class KVStore {
                     std::vector<Prepared>* out);
   void RunPrepared(Prepared& p);
   void PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::vector<Prepared>* out);
+  void PrepareDenseNccl(std::vector<DenseOp>& ops, int opt_kind, std::vector<Prepared>* out);
+  void BroadcastInitNccl(const std::vector<int>& keys);
   std::shared_ptr<Plan> GetPlanGroup(const std::vector<DenseOp>& ops, int opt_kind, int fixed_owner = -1);
   void BroadcastInitGroup(const std::vector<int>& keys);
   // call-level cache: a repeated C call (same keys, same arrays) skips grouping/validation/planning
@@ -247,6 +252,8 @@ class KVStore {
 
   std::string type_;
   bool dist_ = false;         // created inside a one-rank-per-GPU peer group
+  int stage_gen_ = 0;         // staging-buffer generation of the call being prepared / replayed (0 / 1)
+  bool nccl_ = false;         // cross-rank sums go through ncclAllReduce (type 'nccl', or no peer memory)
   int rank_ = 0, group_size_ = 1;
   bool order_local_ = true;   // 'local' => CommCPU association, 'device' => left fold
   int key_type_ = -1;         // -1 undefined, 0 string, 1 int (kvstore_local.h:60-64)

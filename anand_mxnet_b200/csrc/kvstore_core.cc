@@ -9,6 +9,7 @@
 #include <set>
 
 #include "group.h"
+#include "nccl_dyn.h"
 #include "scalar_parse.h"
 
 namespace b200kv {
@@ -74,6 +75,11 @@ KVStore::KVStore(const std::string& type) : type_(type) {
     dist_ = g->world() > 1;
     rank_ = g->rank();
     group_size_ = g->world();
+    // KVStoreNCCL's role (src/kvstore/kvstore_nccl.h): asked for by name, or forced when the ranks
+    // share no NVLink peer memory. Dense keys only, as in the reference.
+    nccl_ = dist_ && (t.find("nccl") != std::string::npos || !g->ipc_ok() ||
+                      std::getenv("B200KV_FORCE_NCCL") != nullptr);
+    if (nccl_) Nccl::Get();   // fail at creation, with a clear message, when libnccl is missing
   }
   // Deferred bucket execution. Default ("auto"): calls that name ONE key -- the way Trainer and
   // tools/bandwidth/measure.py drive the store, one call per parameter -- are queued and fused into
@@ -174,7 +180,9 @@ void KVStore::InitImpl(const std::vector<int>& keys, const std::vector<NDArray>&
     }
     local_[keys[i]] = std::move(e);
   }
-  if (dist_) BroadcastInitGroup(keys);
+  if (dist_) {
+    if (nccl_) BroadcastInitNccl(keys); else BroadcastInitGroup(keys);
+  }
 }
 
 void KVStore::SetUpdater(UpdaterFn fn, StrUpdaterFn sfn, void* handle) {
@@ -753,7 +761,11 @@ DevState& KVStore::StateOn(KeyEntry& e, int dev, int opt_kind) {
 
 // Host-resident values (CPU-context NDArrays) take part through per-key staging buffers on a GPU:
 // the reference's 'local' store stages the other way round (GPU -> pinned host, comm.h:146-164).
+// Two generations of staging buffers (stage_gen_): a store whose calls alternate between them lets
+// the transfer out of step k (D2H lane, reads generation g's out buffers) overlap the fused kernel of
+// step k+1 (writes generation 1-g's), instead of the kernel waiting for the drain.
 NDArray KVStore::StageSrc(KeyEntry& e, size_t slot, const NDArray& host_src, int dev) {
+  slot = slot * 2 + stage_gen_;
   if (e.stage_src.size() <= slot) e.stage_src.resize(slot + 1);
   NDArray& st = e.stage_src[slot];
   if (st.is_none() || st.dev() != dev) st = NDArray(e.shape, Context::GPU(dev), e.dtype);
@@ -762,6 +774,7 @@ NDArray KVStore::StageSrc(KeyEntry& e, size_t slot, const NDArray& host_src, int
 }
 
 NDArray KVStore::StageOut(KeyEntry& e, size_t slot, const NDArray&, int dev) {
+  slot = slot * 2 + stage_gen_;
   if (e.stage_out.size() <= slot) e.stage_out.resize(slot + 1);
   NDArray& st = e.stage_out[slot];
   if (st.is_none() || st.dev() != dev) st = NDArray(e.shape, Context::GPU(dev), e.dtype);

@@ -166,6 +166,8 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     U.row_len = row_len;
   }
   if (dist_) {
+    KV_CHECK(!nccl_) << "kvstore 'nccl' handles dense keys only, as the reference's does "
+                     << "(src/kvstore/kvstore_nccl.h:62-70); use kvstore 'device' for row_sparse keys";
     KV_CHECK(fused) << "one-rank-per-GPU store: row_sparse keys need a fused lazy optimizer on the "
                     << "store (set_optimizer(SGD / Adam)); updater callbacks and plain assignment are "
                     << "single-process features";

@@ -1,0 +1,136 @@
+"""NCCL as the fallback collective of the rank-per-GPU store (src/kvstore/kvstore_nccl.h's role):
+`mx.kv.create('nccl')` inside a peer group, and `'device'` in a group WITHOUT peer memory
+(B200KV_GROUP_NO_IPC=1 stands in for GPUs that cannot map each other). The cross-rank sum is
+ncclAllReduce on a packed bucket, the optimizer step the local fused kernel. NCCL chooses the
+association of the sum, so results are held to the reference's own bound (tests/nightly/
+test_kvstore.py:95-98: sum|delta| / sum|ref| < 1e-6) against the 'local' oracle, as SURVEY 8c asks
+for the NCCL path. One process per GPU, gloo bootstrap on 127.0.0.1."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+SHAPES = [(4, 4), (100, 100), (3,), (1027,), (70001, 3), (1500, 1500)]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _grad(rank, step, k, shape):
+    return np.random.default_rng(1000 * rank + 17 * step + k).uniform(-1, 1, shape).astype(np.float32)
+
+
+def _worker(rank, world, port, q, kvtype, no_ipc):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "oracle")]
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["LOCAL_RANK"] = str(rank)
+    os.environ["B200KV_IPC_ARENA_MB"] = "512"
+    os.environ["B200KV_NVLS"] = "0"
+    if no_ipc:
+        os.environ["B200KV_GROUP_NO_IPC"] = "1"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    errors = []
+    try:
+        import kvoracle as K
+        import anand_mxnet_b200 as mx
+        mx.dist.init_peer_group(rank, symmetric_memory=False)
+        ctx = mx.gpu(rank)
+        keys = list(range(len(SHAPES)))
+
+        def close(a, b):
+            a, b = np.ascontiguousarray(a, np.float64), np.ascontiguousarray(b, np.float64)
+            return a.shape == b.shape and np.abs(a - b).sum() <= 1e-6 * max(np.abs(b).sum(), 1e-30)
+
+        for optname in (None, 'sgd', 'adam'):
+            kv = mx.kv.create(kvtype)
+            assert kv.rank == rank and kv.num_workers == world
+            model = K.LocalKVStoreModel('device')
+            w0 = [np.random.default_rng(50 + k).uniform(-1, 1, s).astype(np.float32) for k, s in enumerate(SHAPES)]
+            # every rank offers a different init value: rank 0's wins (kvstore.py:136-141)
+            kv.init(keys, [mx.nd.array(w + np.float32(rank), ctx) for w in w0])
+            for k in keys:
+                model.init(k, w0[k])
+            if optname == 'sgd':
+                kv.set_optimizer(mx.optimizer.SGD(learning_rate=0.1, momentum=0.9, wd=1e-4, rescale_grad=1.0 / world))
+                model.set_optimizer('sgd', lr=0.1, momentum=0.9, wd=1e-4, rescale_grad=1.0 / world)
+            elif optname == 'adam':
+                kv.set_optimizer(mx.optimizer.Adam(learning_rate=1e-3, wd=0.01, rescale_grad=1.0 / world))
+                model.set_optimizer('adam', lr=1e-3, wd=0.01, rescale_grad=1.0 / world)
+            outs = [mx.nd.empty(s, ctx) for s in SHAPES]
+            before = mx.base.kernel_launch_count()
+            for step in range(3):
+                grads = [mx.nd.array(_grad(rank, step, k, s), ctx) for k, s in enumerate(SHAPES)]
+                kv.pushpull(keys, grads, out=outs)
+                for k, s in enumerate(SHAPES):
+                    model.push(k, [_grad(r, step, k, s) for r in range(world)])
+                for k in keys:
+                    if not close(outs[k].asnumpy(), model.pull(k)):
+                        errors.append("%s opt=%s step %d key %d" % (kvtype, optname, step, k))
+            # host-resident gradients and outs take the same route
+            hg = [mx.nd.array(_grad(rank, 9, k, s), mx.cpu()) for k, s in enumerate(SHAPES)]
+            ho = [mx.nd.empty(s, mx.cpu()) for s in SHAPES]
+            kv.pushpull(keys, hg, out=ho)
+            for k, s in enumerate(SHAPES):
+                model.push(k, [_grad(r, 9, k, s) for r in range(world)])
+                if not close(ho[k].asnumpy(), model.pull(k)):
+                    errors.append("%s opt=%s host key %d" % (kvtype, optname, k))
+            assert mx.base.kernel_launch_count() > before
+            name, _ = mx.base.last_kernel_info()
+            # row_sparse keys are refused, as by the reference's KVStoreNCCL
+            if optname == 'sgd':
+                kv.init('emb', mx.nd.array(np.ones((8, 4), np.float32), ctx).tostype('row_sparse'))
+                try:
+                    kv.push('emb', mx.nd.sparse.row_sparse_array(
+                        (np.ones((1, 4), np.float32), np.array([2], np.int64)), shape=(8, 4), ctx=ctx))
+                    mx.nd.waitall()
+                    errors.append("row_sparse push was accepted by the nccl store")
+                except mx.base.MXNetError:
+                    pass
+        mx.nd.waitall()
+        dist.barrier()
+        mx.dist.destroy_peer_group()
+    except Exception:  # noqa
+        import traceback
+        errors.append(traceback.format_exc())
+    finally:
+        q.put((rank, errors))
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kvtype,no_ipc", [("nccl", False), ("device", True)])
+def test_nccl_fallback_parity(kvtype, no_ipc):
+    import torch
+    import torch.multiprocessing as mp
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, kvtype, no_ipc)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = []
+    try:
+        results = [q.get(timeout=300) for _ in procs]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    for rank, errors in results:
+        assert not errors, (rank, errors[:3])
