@@ -111,7 +111,8 @@ bool KVStore::CallSignature(int tag, const std::vector<int>& vkeys, const std::v
     for (auto& a : values) host_operand = host_operand || (!a.is_none() && !a.on_gpu());
     if (outs != nullptr) for (auto& a : *outs) host_operand = host_operand || (!a.is_none() && !a.on_gpu());
   }
-  if (host_operand) stage_gen_ ^= 1; else stage_gen_ = 0;
+  static const bool two_gens = std::getenv("B200KV_STAGE_SINGLE") == nullptr;
+  if (host_operand && two_gens) stage_gen_ ^= 1; else stage_gen_ = 0;
   sig->push_back(static_cast<uint64_t>(tag) * 2 + static_cast<uint64_t>(stage_gen_));
   sig->push_back(vkeys.size());
   for (size_t i = 0; i < vkeys.size(); ++i) {
@@ -188,7 +189,7 @@ void KVStore::ExecDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stri
 void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_stripe,
                            std::vector<Prepared>* out) {
   if (ops.empty()) return;
-  if (dist_) {
+  if (dist_ && !force_local_) {
     (void)allow_stripe;
     PrepareDenseGroup(ops, opt_kind, out);
     return;

@@ -18,6 +18,8 @@
 // Arithmetic: IEEE fp32 round-to-nearest with NO fused multiply-add (explicit __f*_rn intrinsics;
 // the file is also compiled with -fmad=false) so results are bit-identical to the reference's CPU
 // build (`-O3 -msse3`), i.e. to oracle/kvoracle.c. Expression trees per optimizer are cited below.
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -359,16 +361,17 @@ __device__ __forceinline__ void peer_signal_and_wait(const KernelArgs& a, int ph
   }
 }
 
-// NVLS: the instantiation for launches whose sums happen in the NVSwitch (fp32, MAXSRC = 1).
-// U (groups of V elements per thread with all loads in flight): 1 for one local source -- the
-// HBM-bound case already runs at 0.95 of the copy peak --, 2 when peer memory is read, 4 for the
-// switch-reduced loads.
-template <typename T, int MAXSRC, int OPT, bool NVLS>
-__global__ void __launch_bounds__(kThreads, (MAXSRC == 1 && !NVLS) ? 5 : 1)
+// NVLS: the instantiation for launches whose sums happen in the NVSwitch (fp32, MAXSRC = 1); UN =
+// groups of V elements per thread with every load in flight before the first store.
+// Measured (profiles/r02_peer_probe_n2.txt, r02_run5 bench): for local and peer-memory sources one
+// group per thread is best -- the kernel is limited by the link, not by loads in flight, and the
+// registers of a second group cost resident CTAs (N=2: 0.185 ms with one group, 0.217 ms with two);
+// the switch-reduced loads of the NVLS mode take the deeper variant (B200KV_NVLS_UNROLL).
+template <typename T, int MAXSRC, int OPT, bool NVLS, int UN>
+__global__ void __launch_bounds__(kThreads, (NVLS && UN > 1) ? 1 : (MAXSRC == 1 ? 5 : 1))
 dense_fused_kernel(const KernelArgs a) {
   constexpr int V = 16 / sizeof(T);
-  // the gradient registers of a thread (MAXSRC x V x U floats) are kept to 64
-  constexpr int U = NVLS ? 4 : ((MAXSRC >= 2 && MAXSRC * V * 2 <= 64) ? 2 : 1);
+  constexpr int U = UN;
   __shared__ KeyDesc sk;
   __shared__ uint32_t s_last;
   if (a.pads != nullptr) {
@@ -429,19 +432,97 @@ dense_fused_kernel(const KernelArgs a) {
   }
 }
 
-template <typename T, int MAXSRC, int OPT, bool NVLS = false>
+// ---- the other mshadow dtypes (float64, int32, int64, uint8, int8): reduce / assign / broadcast
+// only -- the reference's reducers are instantiated for every dtype (MSHADOW_TYPE_SWITCH,
+// src/kvstore/comm.h:273, ndarray_function-inl.h:399) while its optimizer operators are floating
+// point. Same chunk list, same association orders, native arithmetic of T, element-wise path.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) dense_plain_kernel(const KernelArgs a, int opt) {
+  __shared__ KeyDesc sk;
+  __shared__ uint32_t s_last;
+  if (a.pads != nullptr) {
+    peer_signal_and_wait(a, 0, blockIdx.x == 0);
+    __syncthreads();
+  }
+  if (static_cast<int>(blockIdx.x) < a.n_chunks) {
+    const ChunkDesc c = a.chunks[blockIdx.x];
+    constexpr int NW = sizeof(KeyDesc) / 16;
+    const uint4* gk = reinterpret_cast<const uint4*>(a.keys + c.key);
+    if (threadIdx.x < NW) reinterpret_cast<uint4*>(&sk)[threadIdx.x] = gk[threadIdx.x];
+    __syncthreads();
+    const int n_src = sk.n_src, n_out = sk.n_out;
+    for (uint32_t e = threadIdx.x; e < c.len; e += kThreads) {
+      const uint32_t i = c.off + e;
+      T acc;
+      if (opt != kOptPullOnly) {
+        acc = static_cast<const T*>(sk.src[0])[i];
+        if (a.order == kOrderDevice) {
+          for (int k = 1; k < n_src; ++k) acc = static_cast<T>(acc + static_cast<const T*>(sk.src[k])[i]);
+        } else {
+          for (int k = 1; k < n_src; k += 4) {
+            T t = static_cast<const T*>(sk.src[k])[i];
+            for (int q = 1; q < 4 && k + q < n_src; ++q) t = static_cast<T>(t + static_cast<const T*>(sk.src[k + q])[i]);
+            acc = static_cast<T>(acc + t);
+          }
+        }
+        static_cast<T*>(sk.w)[i] = acc;
+      } else {
+        acc = static_cast<const T*>(sk.w)[i];
+      }
+      for (int o = 0; o < n_out; ++o) static_cast<T*>(sk.out[o])[i] = acc;
+    }
+  }
+  if (a.pads != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const uint32_t done = atomicAdd(a.counter, 1u);
+      s_last = (done == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence_system();
+      peer_signal_and_wait(a, 1, true);
+      __syncthreads();
+      if (threadIdx.x == 0) *a.counter = 0;
+    }
+  }
+}
+
+template <typename T>
+void launch_plain(const DenseLaunch& p, cudaStream_t s) {
+  KV_CHECK(p.opt == kOptAssign || p.opt == kOptPullOnly)
+      << "optimizers on the store run on float32 / float16 / bfloat16 keys; " << DTypeName(p.dtype)
+      << " keys are reduced, assigned and pulled";
+  KV_CHECK(!p.nvls);
+  KernelArgs a{p.keys, p.chunks, reinterpret_cast<const float2*>(p.hyper), p.lrs, p.wds, p.order, p.momentum,
+               p.rescale, p.clip, p.beta1, p.beta2, p.eps, p.signal_pads, p.counter, p.rank, p.world,
+               p.epoch, p.n_chunks, p.err_word, p.timeout_ns};
+  const int grid = p.n_chunks > 0 ? p.n_chunks : 1;
+  dense_plain_kernel<T><<<grid, kThreads, 0, s>>>(a, p.opt);
+}
+
+template <typename T, int MAXSRC, int OPT, bool NVLS = false, int UN = 1>
 void launch_one(const DenseLaunch& p, cudaStream_t s) {
   KernelArgs a{p.keys, p.chunks, reinterpret_cast<const float2*>(p.hyper), p.lrs, p.wds, p.order, p.momentum,
                p.rescale, p.clip, p.beta1, p.beta2, p.eps, p.signal_pads, p.counter, p.rank, p.world,
                p.epoch, p.n_chunks, p.err_word, p.timeout_ns};
   const int grid = p.n_chunks > 0 ? p.n_chunks : 1;  // a rank with no chunk still joins the barriers
-  dense_fused_kernel<T, MAXSRC, OPT, NVLS><<<grid, kThreads, 0, s>>>(a);
+  dense_fused_kernel<T, MAXSRC, OPT, NVLS, UN><<<grid, kThreads, 0, s>>>(a);
 }
 
 template <typename T, int OPT>
 void launch_src(const DenseLaunch& p, cudaStream_t s) {
   if (p.nvls) {
-    if constexpr (sizeof(T) == 4) return launch_one<T, 1, OPT, true>(p, s);
+    if constexpr (sizeof(T) == 4) {
+      static const int unroll = []() {
+        const char* z = std::getenv("B200KV_NVLS_UNROLL");
+        return z ? std::atoi(z) : 4;
+      }();
+      if (unroll >= 4) return launch_one<T, 1, OPT, true, 4>(p, s);
+      if (unroll >= 2) return launch_one<T, 1, OPT, true, 2>(p, s);
+      return launch_one<T, 1, OPT, true, 1>(p, s);
+    }
     KV_FATAL << "NVLS launches are float32";
   }
   if (OPT == kOptPullOnly || p.max_src <= 1) return launch_one<T, 1, OPT>(p, s);
@@ -473,8 +554,12 @@ void LaunchDenseFused(const DenseLaunch& p, cudaStream_t stream) {
     case kFloat32: launch_opt<float>(p, stream); break;
     case kFloat16: launch_opt<__half>(p, stream); break;
     case kBfloat16: launch_opt<__nv_bfloat16>(p, stream); break;
-    default: KV_FATAL << "dense KVStore kernels support float32/float16/bfloat16, got "
-                      << DTypeName(p.dtype);
+    case kFloat64: launch_plain<double>(p, stream); break;
+    case kInt32: launch_plain<int32_t>(p, stream); break;
+    case kInt64: launch_plain<int64_t>(p, stream); break;
+    case kUint8: launch_plain<uint8_t>(p, stream); break;
+    case kInt8: launch_plain<int8_t>(p, stream); break;
+    default: KV_FATAL << "dense KVStore kernels: unsupported dtype " << DTypeName(p.dtype);
   }
   KV_CUDA(cudaGetLastError());
 }

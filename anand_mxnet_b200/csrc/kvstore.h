@@ -233,6 +233,8 @@ class KVStore {
                                 const std::vector<int>& devs, bool striped);
 
   NDArray CompressedReduce(KeyEntry& e, const std::vector<NDArray>& srcs);  // compress.cc
+  void CompressedReduceGroup(const std::vector<KeyEntry*>& es, std::vector<std::vector<NDArray>>* srcs);
+  bool force_local_ = false;  // the launch being prepared needs no cross-rank step (operands already merged)
   float gc_threshold_ = 0.5f;
 
   // row_sparse machinery (rowsparse.cc)
@@ -241,6 +243,7 @@ class KVStore {
                             RspUpdateLaunch U);
   // one rank per GPU: every rank owns a row range; gradients of the peers are read through IPC
   void PushRowSparseGroup(KeyEntry& e, const NDArray& src, RspUpdateLaunch U);
+  NDArray MergeRowSparseGroup(KeyEntry& e, const NDArray& src);   // no fused optimizer: replicated merge
   void GroupBarrier();   // cross-rank barrier on this rank's compute lane (signal pads)
   void ShardRsp(KeyEntry& e, const std::vector<int>& devs);
   void UnshardRsp(KeyEntry& e);

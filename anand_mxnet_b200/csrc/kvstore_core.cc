@@ -508,11 +508,37 @@ void KVStore::PushImpl(const std::vector<int>& keys, const std::vector<NDArray>&
   std::vector<DenseOp> fused, pulls;
   std::set<int> pushed;
   const bool callback = updater_ != nullptr && !opt_.enabled;
+  // 2-bit compression in a peer group: all dense keys of the call are quantised, exchanged and
+  // decoded in one batch (two cross-rank barriers per call, not per key); their merged gradients
+  // are identical on every rank, so the rest of the push is a local, one-source launch
+  const bool gc_group = gc_type_ == "2bit" && dist_;
+  if (gc_group) {
+    KV_CHECK(!nccl_) << "kvstore 'nccl' does not compress gradients (src/kvstore/kvstore_nccl.h:62-70)";
+    std::vector<KeyEntry*> es;
+    std::vector<std::vector<NDArray>> vals;
+    std::vector<size_t> which;
+    for (size_t i = 0; i < uniq.size(); ++i) {
+      if (grouped[i][0].stype() != kDefaultStorage) continue;
+      KeyEntry& e = Entry(uniq[i]);
+      for (auto& s : grouped[i]) KV_CHECK_EQ(s.Size(), e.size) << "push: shape mismatch for key " << e.key;
+      es.push_back(&e);
+      vals.push_back(grouped[i]);
+      which.push_back(i);
+    }
+    if (!es.empty()) CompressedReduceGroup(es, &vals);
+    for (size_t j = 0; j < which.size(); ++j) grouped[which[j]] = vals[j];
+  }
+  struct LocalScope {   // launches prepared below skip the cross-rank plan when the sums are done
+    bool* flag;
+    bool old;
+    LocalScope(bool* f, bool v) : flag(f), old(*f) { *f = v; }
+    ~LocalScope() { *flag = old; }
+  } local_scope(&force_local_, gc_group);
   for (size_t i = 0; i < uniq.size(); ++i) {
     KeyEntry& e = Entry(uniq[i]);
     std::vector<NDArray>& srcs = grouped[i];
     pushed.insert(e.key);
-    if (gc_type_ == "2bit" && srcs[0].stype() == kDefaultStorage) {
+    if (gc_type_ == "2bit" && !gc_group && srcs[0].stype() == kDefaultStorage) {
       // CommDevice::Reduce -> ReduceCompressed (comm.h:507-509): quantise every value with its
       // residual, decode + sum on the owner; the optimizer then sees that merged gradient
       for (auto& s : srcs) KV_CHECK_EQ(s.Size(), e.size) << "push: shape mismatch for key " << e.key;

@@ -133,7 +133,7 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
     double wdd = opt_.wd * (wm == opt_.wd_mult.end() ? 1.0 : wm->second);
     DevState& s = e.dev[home];
     const std::vector<int64_t> dshape = e.shape;
-    const bool sharded_now = !e.rsp_devs.empty() || e.rsp_group || dist_;   // state lives with the shards
+    const bool sharded_now = !e.rsp_devs.empty() || e.rsp_group || (dist_ && fused);   // state lives with the shards
     auto zero_state = [&](NDArray* a) {
       if (!a->is_none() || sharded_now) return;
       *a = NDArray(dshape, Context::GPU(home), kFloat32);
@@ -168,12 +168,13 @@ void KVStore::PushRowSparse(KeyEntry& e, const std::vector<NDArray>& srcs_in) {
   if (dist_) {
     KV_CHECK(!nccl_) << "kvstore 'nccl' handles dense keys only, as the reference's does "
                      << "(src/kvstore/kvstore_nccl.h:62-70); use kvstore 'device' for row_sparse keys";
-    KV_CHECK(fused) << "one-rank-per-GPU store: row_sparse keys need a fused lazy optimizer on the "
-                    << "store (set_optimizer(SGD / Adam)); updater callbacks and plain assignment are "
-                    << "single-process features";
     KV_CHECK_EQ(srcs.size(), 1u) << "one-rank-per-GPU store: push one row_sparse value per key and rank";
-    PushRowSparseGroup(e, srcs[0], U);
-    return;
+    if (fused) {
+      PushRowSparseGroup(e, srcs[0], U);   // table and optimizer state sharded by row range
+      return;
+    }
+    merged = MergeRowSparseGroup(e, srcs[0]);
+    total = 0;   // the merge is done: skip the single-process union below
   }
   if (fused && total > 0 && parts.size() >= 2 && std::getenv("B200KV_RSP_SHARD_OFF") == nullptr) {
     // sources on several GPUs: every GPU merges and updates its own row range of the table
@@ -736,6 +737,75 @@ void KVStore::GroupBarrier() {
   DeviceGuard guard(g->dev());
   LaunchDenseFused(L, eng->Stream(g->dev()));
   eng->CountLaunch("group_barrier", 0);
+}
+
+// One rank per GPU, NO fused optimizer on the store (plain assignment, an updater callback, or a
+// standard -- non-lazy -- update): what the reference does with the merged gradient happens on
+// every rank alike, so every rank builds the SAME merged row_sparse gradient -- the union of all
+// ranks' rows, summed in rank order, read through IPC -- and the caller carries on as the
+// single-process store does (kvstore_local.h:208-245); the stored value stays replicated.
+NDArray KVStore::MergeRowSparseGroup(KeyEntry& e, const NDArray& src_in) {
+  PeerGroup* g = PeerGroup::Get();
+  KV_CHECK(g != nullptr);
+  Engine* eng = Engine::Get();
+  const int dev = g->dev(), W = g->world();
+  KV_CHECK(!e.rsp_group) << "key " << e.key << " is sharded over the ranks by a fused optimizer; it "
+                         << "cannot go back to a replicated value";
+  NDArray src = src_in;
+  if (!src.on_gpu() || src.dev() != dev ||
+      (src.storage_initialized() && !(g->InArena(src.data()) && g->InArena(src.row_ids())))) {
+    src = src_in.Copy(Context::GPU(dev));
+  }
+  const int64_t my_nnr = src.storage_initialized() ? src.nnr() : 0;
+  if (my_nnr > 0) {
+    KV_CHECK(g->InArena(src.data()) && g->InArena(src.row_ids()))
+        << "IPC arena exhausted; raise B200KV_IPC_ARENA_MB";
+  }
+  const std::vector<int64_t> all = g->AllGatherI64(
+      {my_nnr > 0 ? g->OffsetOf(src.row_ids()) : 0, my_nnr > 0 ? g->OffsetOf(src.data()) : 0, my_nnr,
+       static_cast<int64_t>(e.key)});
+  RspSources S;
+  int64_t total = 0;
+  for (int r = 0; r < W; ++r) {
+    KV_CHECK_EQ(all[4 * r + 3], static_cast<int64_t>(e.key))
+        << "one-rank-per-GPU store: rank " << r << " pushed a different row_sparse key";
+    const int64_t n = all[4 * r + 2];
+    if (n == 0) continue;
+    S.idx[S.nsrc] = static_cast<const int64_t*>(g->PeerPtr(r, all[4 * r]));
+    S.val[S.nsrc] = static_cast<const float*>(g->PeerPtr(r, all[4 * r + 1]));
+    S.start[S.nsrc] = total;
+    total += n;
+    ++S.nsrc;
+  }
+  S.start[S.nsrc] = total;
+  NDArray merged = NDArray::RowSparse(e.shape, Context::GPU(dev), e.dtype);
+  const int64_t row_len = static_cast<int64_t>(src.RowLength());
+  eng->BeginRead(dev, *src.var());
+  GroupBarrier();   // every rank's gradient is complete before anybody reads it
+  NDArray d_nnr, ws;
+  if (total > 0) {
+    DeviceGuard gd(dev);
+    merged.CheckAndAllocRows(total);
+    d_nnr = NDArray({1}, Context::GPU(dev), kInt64);
+    const int bits = BitsFor(e.shape[0]);
+    ws = NDArray({static_cast<int64_t>(RspMergeWorkspaceBytes(total, bits, S.nsrc))}, Context::GPU(dev), kUint8);
+    LaunchRspMerge(S, bits, row_len, merged.row_ids(), static_cast<float*>(merged.data()),
+                   static_cast<int64_t*>(d_nnr.data()), ws.data(), ws.ByteSize(), eng->Stream(dev));
+    eng->CountLaunch("rsp_merge(replicated)", total * 24);
+    eng->CountLaunch("rsp_sum(replicated)", static_cast<uint64_t>(total) * row_len * 8);
+  }
+  GroupBarrier();   // everybody has read the peers' gradients: they may be reused
+  const uint64_t seq = eng->Issue(dev);
+  eng->MarkRead(dev, seq, src.var());
+  eng->MarkWrite(dev, seq, merged.var());
+  if (total > 0) {
+    eng->MarkWrite(dev, seq, d_nnr.var());
+    eng->MarkWrite(dev, seq, ws.var());
+    CountFence f(dev, 1);
+    f.Post(static_cast<const int64_t*>(d_nnr.data()), eng->Stream(dev));
+    merged.SetNnr(f.Wait()[0]);
+  }
+  return merged;
 }
 
 void KVStore::PushRowSparseGroup(KeyEntry& e, const NDArray& src_in, RspUpdateLaunch U) {

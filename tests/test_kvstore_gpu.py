@@ -397,6 +397,46 @@ def test_resnet50_sized_properties(mx):
         assert torch.equal(a, b)
 
 
+# ------------------------------------------------------------------ the other mshadow dtypes
+@pytest.mark.parametrize("dtype", [np.float64, np.int32, np.int64, np.uint8, np.int8])
+@pytest.mark.parametrize("kvtype", ['local', 'device'])
+def test_reduce_other_dtypes(mx, dtype, kvtype):
+    """the reference's reducers exist for every mshadow dtype (MSHADOW_TYPE_SWITCH, comm.h:273,
+    ndarray_function-inl.h:399): push of n values / pull, in both association orders"""
+    rng = np.random.default_rng(77)
+    shape = (1027, 5)
+    kv = mx.kv.create(kvtype)
+    kv.init(0, mx.nd.array(np.zeros(shape, dtype), mx.gpu(0), dtype))
+    for n in (1, 3, 6):
+        if np.issubdtype(dtype, np.floating):
+            vals = [rng.uniform(-1, 1, shape).astype(dtype) for _ in range(n)]
+        else:
+            info = np.iinfo(dtype)
+            vals = [rng.integers(info.min // 8, info.max // 8, shape).astype(dtype) for _ in range(n)]
+        kv.push(0, [mx.nd.array(v, mx.gpu(0), dtype) for v in vals])
+        out = mx.nd.empty(shape, mx.gpu(0), dtype)
+        kv.pull(0, out=out)
+        # the association of the store type, in the dtype's own arithmetic
+        if kvtype == 'device':
+            want = vals[0].copy()
+            for v in vals[1:]:
+                want = (want + v).astype(dtype)
+        else:
+            want = vals[0].copy()
+            for i in range(1, n, 4):
+                t = vals[i].copy()
+                for q in range(1, 4):
+                    if i + q < n:
+                        t = (t + vals[i + q]).astype(dtype)
+                want = (want + t).astype(dtype)
+        got = out.asnumpy()
+        assert got.dtype == np.dtype(dtype) and eq(got, want), (dtype, n)
+    with pytest.raises(mx.MXNetError, match="optimizers on the store run on float32"):
+        kv.set_optimizer(mx.optimizer.Test(rescale_grad=1.0))
+        kv.push(0, mx.nd.array(np.ones(shape, dtype), mx.gpu(0), dtype))
+        mx.nd.waitall()
+
+
 # ------------------------------------------------------------------ TMA pack kernel
 def test_pack_bulk_copy(mx):
     """Many arrays (3 elements .. 4 MB, fp32 and 16-bit, aligned and ragged byte sizes) copied by

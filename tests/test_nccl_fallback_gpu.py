@@ -92,9 +92,9 @@ def _worker(rank, world, port, q, kvtype, no_ipc):
             name, _ = mx.base.last_kernel_info()
             # row_sparse keys are refused, as by the reference's KVStoreNCCL
             if optname == 'sgd':
-                kv.init('emb', mx.nd.array(np.ones((8, 4), np.float32), ctx).tostype('row_sparse'))
+                kv.init(99, mx.nd.array(np.ones((8, 4), np.float32), ctx).tostype('row_sparse'))
                 try:
-                    kv.push('emb', mx.nd.sparse.row_sparse_array(
+                    kv.push(99, mx.nd.sparse.row_sparse_array(
                         (np.ones((1, 4), np.float32), np.array([2], np.int64)), shape=(8, 4), ctx=ctx))
                     mx.nd.waitall()
                     errors.append("row_sparse push was accepted by the nccl store")
