@@ -111,7 +111,10 @@ bool KVStore::CallSignature(int tag, const std::vector<int>& vkeys, const std::v
     for (auto& a : values) host_operand = host_operand || (!a.is_none() && !a.on_gpu());
     if (outs != nullptr) for (auto& a : *outs) host_operand = host_operand || (!a.is_none() && !a.on_gpu());
   }
-  static const bool two_gens = std::getenv("B200KV_STAGE_SINGLE") == nullptr;
+  // (measured at 2 ranks, profiles/r02_e2e_group.txt: alternating generations 3.24 ms/step, one
+  // generation 3.13 -- the extra overlap makes the pack kernels and the fused kernel contend -- so
+  // the second generation is opt-in: B200KV_STAGE_DOUBLE=1)
+  static const bool two_gens = std::getenv("B200KV_STAGE_DOUBLE") != nullptr;
   if (host_operand && two_gens) stage_gen_ ^= 1; else stage_gen_ = 0;
   sig->push_back(static_cast<uint64_t>(tag) * 2 + static_cast<uint64_t>(stage_gen_));
   sig->push_back(vkeys.size());

@@ -361,6 +361,14 @@ __device__ __forceinline__ void peer_signal_and_wait(const KernelArgs& a, int ph
   }
 }
 
+template <typename T, int MAXSRC, int OPT, bool NVLS, int UN>
+constexpr int MinBlocks() {
+  if (sizeof(T) != 4 || (NVLS && UN > 1) || MAXSRC > 8) return 1;   // 16-bit packs carry 8 values per load
+  if (MAXSRC == 1) return 5;
+  const int adam = OPT == kOptAdam ? 1 : 0;                            // two more state vectors
+  return (MAXSRC <= 2 ? 5 : 4) - adam;
+}
+
 // NVLS: the instantiation for launches whose sums happen in the NVSwitch (fp32, MAXSRC = 1); UN =
 // groups of V elements per thread with every load in flight before the first store.
 // Measured (profiles/r02_peer_probe_n2.txt, r02_run5 bench): for local and peer-memory sources one
@@ -368,7 +376,9 @@ __device__ __forceinline__ void peer_signal_and_wait(const KernelArgs& a, int ph
 // registers of a second group cost resident CTAs (N=2: 0.185 ms with one group, 0.217 ms with two);
 // the switch-reduced loads of the NVLS mode take the deeper variant (B200KV_NVLS_UNROLL).
 template <typename T, int MAXSRC, int OPT, bool NVLS, int UN>
-__global__ void __launch_bounds__(kThreads, (NVLS && UN > 1) ? 1 : (MAXSRC == 1 ? 5 : 1))
+// resident CTAs per SM matter more than registers here (every CTA starts with two dependent
+// descriptor loads): the caps below keep the register budgets of the round-1 kernel (48 / 48 / 64)
+__global__ void __launch_bounds__(kThreads, MinBlocks<T, MAXSRC, OPT, NVLS, UN>())
 dense_fused_kernel(const KernelArgs a) {
   constexpr int V = 16 / sizeof(T);
   constexpr int U = UN;

@@ -161,6 +161,26 @@ def run_dense(mx, torch, dist, stream, local, rank, world, workload, steps, warm
                                "peak": None, "frac": None,
                                "note": "the N=1 line measures the pinned-copy peak of the box (both "
                                        "directions busy); all N ranks share the host's memory system"}}
+    if os.environ.get("B200KV_E2E_DIAG"):
+        # where does the host-buffer step spend its time? one direction at a time
+        diag = {}
+        dgr = [mx.nd.array(g0[k].reshape(shapes[k]), ctx) for k in keys]
+        dou = [mx.nd.empty(s, ctx) for s in shapes]
+        for name, vv, oo in (("h2d_only(host grads -> device weights)", hgrads, dou),
+                             ("d2h_only(device grads -> host weights)", dgr, houts)):
+            kvd = mx.kv.create("device")
+            kvd.init(keys, weights0)
+            kvd.set_optimizer(make_optimizer(mx, workload, world))
+            for _ in range(2):
+                kvd.pushpull(keys, vv, out=oo)
+            st = c_step_fn(mx, kvd, keys, vv, oo)
+            st()
+            mx.nd.waitall()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t = time_region(torch, stream, st, e2e_steps, after=mx.nd.waitall)
+            diag[name] = _max_over_ranks(torch, dist, dev, t)
+        res["e2e"]["diagnostics_ms"] = diag
     return res
 
 
