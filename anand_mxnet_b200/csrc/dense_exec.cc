@@ -30,7 +30,11 @@ static uint64_t Mix(uint64_t h, uint64_t v) {
 PackList::~PackList() { Engine::Get()->Free(dev, d_items, bytes_items); }
 
 // Moves the same-GPU pairs of `pairs` into a PackList (tiles of <= 16 KB uploaded once).
-std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>* pairs) {
+// dma_min_bytes > 0: pairs with a host side of at least that size are LEFT to the copy engines
+// (CopyFromTo on the copy lanes). Measured at 2 ranks (profiles/r02_e2e_group.txt): SM-driven packing
+// of both directions at once sustains ~33 GB/s per direction, the copy engines ~49, but a DMA
+// carries ~10 us of fixed cost -- so big arrays go by DMA and the many small ones by one pack launch.
+std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>* pairs, size_t dma_min_bytes) {
   std::vector<std::pair<NDArray, NDArray>> rest;
   auto pl = std::make_shared<PackList>();
   std::vector<PackItem> items;
@@ -43,7 +47,9 @@ std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>
     if (from.on_gpu() && to.on_gpu() && from.dev() == to.dev()) pdev = from.dev();
     else if (from.on_gpu() && to.kernel_visible_host()) pdev = from.dev();
     else if (to.on_gpu() && from.kernel_visible_host()) pdev = to.dev();
-    if (pdev < 0 || (pl->dev >= 0 && pdev != pl->dev)) {
+    const bool host_side = !from.on_gpu() || !to.on_gpu();
+    if (pdev < 0 || (pl->dev >= 0 && pdev != pl->dev) ||
+        (host_side && dma_min_bytes > 0 && from.ByteSize() >= dma_min_bytes)) {
       rest.push_back(pr);
       continue;
     }

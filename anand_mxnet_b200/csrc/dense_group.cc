@@ -18,7 +18,6 @@ namespace b200kv {
 
 void PlanChunks(uint64_t goff, size_t size, uint32_t key_slot, int ndev, int owner_fixed,
                 std::vector<std::vector<ChunkDesc>>* per_slot);  // kvstore_core.cc
-std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>* pairs);  // dense_exec.cc
 
 namespace {
 constexpr int kMaxLocalOut = 2;   // pull targets per key per rank
@@ -199,8 +198,12 @@ void KVStore::PrepareDenseGroup(std::vector<DenseOp>& ops, int opt_kind, std::ve
     for (auto& op : P.ops) StateOn(*op.e, dev, opt_kind);
     // operands that live outside the IPC arena on this GPU (a framework's own tensors) are packed
     // into / unpacked from arena staging buffers by one TMA bulk-copy launch each way
-    P.pack_in = BuildPackList(&P.stage_in);
-    P.pack_out = BuildPackList(&P.stage_out);
+    static const size_t dma_min = []() {
+      const char* z = std::getenv("B200KV_DMA_MIN_KB");
+      return static_cast<size_t>(z ? std::max(0, std::atoi(z)) : 1024) << 10;
+    }();
+    P.pack_in = BuildPackList(&P.stage_in, dma_min);
+    P.pack_out = BuildPackList(&P.stage_out, dma_min);
     P.plan = GetPlanGroup(P.ops, opt_kind);
     out->push_back(std::move(P));
   }

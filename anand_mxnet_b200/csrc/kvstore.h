@@ -122,7 +122,7 @@ struct PackList {
   ~PackList();
 };
 
-std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>* pairs);
+std::shared_ptr<PackList> BuildPackList(std::vector<std::pair<NDArray, NDArray>>* pairs, size_t dma_min_bytes = 0);
 void RunPackList(PackList& pl);
 
 // Everything one fused launch group needs at run time, computed once per distinct call signature:

@@ -33,6 +33,7 @@ run_bench bench_n8 8 --steps 20 --warmup 5
 B200KV_NVLS_UNROLL=1 run_bench bench_n8_nvls_u1 8 --steps 20 --warmup 5 --no-config-legs
 B200KV_NVLS_UNROLL=2 run_bench bench_n8_nvls_u2 8 --steps 20 --warmup 5 --no-config-legs
 B200KV_NVLS=0 run_bench bench_n8_nvls0 8 --steps 20 --warmup 5 --no-config-legs
+B200KV_DMA_MIN_KB=0 run_bench bench_n8_packonly 8 --steps 10 --warmup 3 --no-config-legs
 run_bench bench_n4 4 --steps 20 --warmup 5
 B200KV_NVLS=1 run_bench bench_n4_nvls1 4 --steps 20 --warmup 5 --no-config-legs
 run_bench bench_rsp_n8 8 --workload rsp --steps 20
