@@ -374,7 +374,9 @@ constexpr int MinBlocks() {
 // Measured (profiles/r02_peer_probe_n2.txt, r02_run5 bench): for local and peer-memory sources one
 // group per thread is best -- the kernel is limited by the link, not by loads in flight, and the
 // registers of a second group cost resident CTAs (N=2: 0.185 ms with one group, 0.217 ms with two);
-// the switch-reduced loads of the NVLS mode take the deeper variant (B200KV_NVLS_UNROLL).
+// the same holds for the switch-reduced loads of the NVLS mode (8 ranks: 0.258 / 0.273 / 0.286 ms
+// with 1 / 2 / 4 groups, profiles/r02_run8_8gpu_*): B200KV_NVLS_UNROLL keeps the deeper variants
+// selectable.
 template <typename T, int MAXSRC, int OPT, bool NVLS, int UN>
 // resident CTAs per SM matter more than registers here (every CTA starts with two dependent
 // descriptor loads): the caps below keep the register budgets of the round-1 kernel (48 / 48 / 64)
@@ -527,7 +529,7 @@ void launch_src(const DenseLaunch& p, cudaStream_t s) {
     if constexpr (sizeof(T) == 4) {
       static const int unroll = []() {
         const char* z = std::getenv("B200KV_NVLS_UNROLL");
-        return z ? std::atoi(z) : 4;
+        return z ? std::atoi(z) : 1;   // measured at 8 ranks: 1 -> 0.258 ms, 2 -> 0.273, 4 -> 0.286
       }();
       if (unroll >= 4) return launch_one<T, 1, OPT, true, 4>(p, s);
       if (unroll >= 2) return launch_one<T, 1, OPT, true, 2>(p, s);

@@ -60,6 +60,7 @@ struct KeyEntry {
   int home = -1;        // GPU holding the whole authoritative value (-1: still on host)
   bool striped = false; // authoritative value is striped over the store's device set
   std::map<int, DevState> dev;
+  uint8_t queued = 0;   // deferred bucket execution: bit 0 = a push of this key is queued, bit 1 = a pull
   NDArray merged;       // reduce target of the updater-callback path (on `home`)
   NDArray rsp;          // row_sparse stored value (on `home` or host)
   // Row-range sharding of a row_sparse table whose stored value holds every row and whose
@@ -281,7 +282,7 @@ class KVStore {
   bool TryDefer(int kind, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
                 const std::vector<int>& okeys, const std::vector<NDArray>& outs, int priority);
   std::vector<PendingOp> pending_;
-  std::unordered_set<int> pending_pushed_, pending_pulled_;
+  std::vector<KeyEntry*> pending_entries_;      // keys with a queued push (KeyEntry::queued bit 0) / pull (bit 1)
   size_t pending_bytes_ = 0, bucket_bytes_ = 0;
   bool bucket_auto_ = true;                      // queue single-key calls (see the constructor)
   size_t auto_bucket_bytes_ = static_cast<size_t>(256) << 20;

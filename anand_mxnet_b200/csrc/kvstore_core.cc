@@ -368,42 +368,48 @@ bool KVStore::TryDefer(int kind, const std::vector<int>& vkeys, const std::vecto
     for (auto& o : outs) if (o.external()) return false;
     cap = auto_bucket_bytes_;
   }
+  (void)kind;
   size_t bytes = 0;
+  // a second push of a key, or a push after a queued pull of it, must not be merged with the
+  // queued one: run what is queued first (KeyEntry::queued: bit 0 = push queued, bit 1 = pull)
+  bool conflict = false;
+  KeyEntry* last = nullptr;
   for (size_t i = 0; i < vkeys.size(); ++i) {
-    KeyEntry& e = Entry(vkeys[i]);  // un-initialised keys still fail synchronously
+    KeyEntry& e = (last != nullptr && last->key == vkeys[i]) ? *last : Entry(vkeys[i]);  // un-initialised keys still fail synchronously
+    last = &e;
     const NDArray& v = values[i];
     if (v.stype() != kDefaultStorage || e.stype != kDefaultStorage) return false;
     KV_CHECK_EQ(v.Size(), e.size) << "push: shape mismatch for key " << e.key;
     KV_CHECK_EQ(v.dtype(), e.dtype) << "push: dtype mismatch for key " << e.key;
     bytes += v.ByteSize();
+    conflict = conflict || e.queued != 0;
   }
   for (size_t i = 0; i < okeys.size(); ++i) {
-    KeyEntry& e = Entry(okeys[i]);
+    KeyEntry& e = (last != nullptr && last->key == okeys[i]) ? *last : Entry(okeys[i]);
+    last = &e;
     const NDArray& o = outs[i];
     if (o.stype() != kDefaultStorage || e.stype != kDefaultStorage) return false;
     KV_CHECK_EQ(o.Size(), e.size) << "pull: shape mismatch for key " << e.key;
     KV_CHECK_EQ(o.dtype(), e.dtype) << "pull: dtype mismatch for key " << e.key;
     bytes += o.ByteSize();
   }
-  // a second push of a key, or a push after a queued pull of it, must not be merged with the
-  // queued one: run what is queued first
-  bool conflict = false;
-  for (int k : vkeys) {
-    if (pending_pushed_.count(k) || pending_pulled_.count(k)) conflict = true;
-  }
-  if (kind == 2) {
-    // pushpull whose pull side targets keys already pushed in this queue is fine; nothing to do
-  }
   if (conflict) Flush();
-  PendingOp op;
+  pending_.emplace_back();
+  PendingOp& op = pending_.back();
   op.vkeys = vkeys;
   op.vals = values;
   op.okeys = okeys;
   op.outs = outs;
   op.priority = priority;
-  pending_.push_back(std::move(op));
-  for (int k : vkeys) pending_pushed_.insert(k);
-  for (int k : okeys) pending_pulled_.insert(k);
+  last = nullptr;
+  auto mark = [&](int k, uint8_t bit) {
+    KeyEntry& e = (last != nullptr && last->key == k) ? *last : Entry(k);
+    last = &e;
+    if (e.queued == 0) pending_entries_.push_back(&e);
+    e.queued |= bit;
+  };
+  for (int k : vkeys) mark(k, 1);
+  for (int k : okeys) mark(k, 2);
   pending_bytes_ += bytes;
   if (pending_bytes_ >= cap) Flush();
   return true;
@@ -413,8 +419,8 @@ void KVStore::Flush() {
   if (pending_.empty()) return;
   std::vector<PendingOp> ops;
   ops.swap(pending_);
-  pending_pushed_.clear();
-  pending_pulled_.clear();
+  for (KeyEntry* e : pending_entries_) e->queued = 0;
+  pending_entries_.clear();
   pending_bytes_ = 0;
   // higher priority first; equal priorities (push i and pull i both carry -i) keep call order
   std::stable_sort(ops.begin(), ops.end(),
@@ -437,12 +443,15 @@ void KVStore::Flush() {
 int KVStore::UpdateCount(int key) const {
   auto it = opt_.count.find(key);
   const int c = it == opt_.count.end() ? opt_.begin_num_update : it->second;
-  return c + (pending_pushed_.count(key) ? 1 : 0);
+  auto e = local_.find(key);
+  return c + ((e != local_.end() && (e->second->queued & 1)) ? 1 : 0);
 }
 
 int KVStore::NumUpdate() const {
   int n = opt_.num_update;
-  for (int k : pending_pushed_) n = std::max(n, UpdateCount(k));
+  for (const KeyEntry* e : pending_entries_) {
+    if (e->queued & 1) n = std::max(n, UpdateCount(e->key));
+  }
   return n;
 }
 
