@@ -250,13 +250,24 @@ void KVStore::PrepareDense(std::vector<DenseOp>& ops, int opt_kind, bool allow_s
     static const int kHostMode = []() {
       const char* z = std::getenv("B200KV_HOST_MODE");
       const std::string m = z ? z : "zc";
-      return m == "staged" ? 0 : m == "in_dma" ? 2 : m == "in_tma" ? 3 : m == "pipe" ? 4 : 1;
+      return m == "staged" ? 0 : m == "in_dma" ? 2 : m == "in_tma" ? 3 : m == "pipe" ? 4 : m == "hybrid" ? 5 : 1;
+    }();
+    // hybrid: arrays of at least B200KV_DMA_MIN_KB go through the copy engines in buckets (DMA in,
+    // fused kernel, DMA out pipelined over the three lanes), the many small ones are read / written
+    // by the kernel itself
+    static const size_t kHybridMin = []() {
+      const char* z = std::getenv("B200KV_DMA_MIN_KB");
+      return static_cast<size_t>(z ? std::max(1, std::atoi(z)) : 1024) << 10;
     }();
     // pipe: TMA pack kernels on the two copy lanes move each bucket in / out (one launch per
     // bucket and direction) while the compute lane runs the fused kernel of the bucket between
-    auto direct_in = [&](const NDArray& a) { return a.on_gpu() || (kHostMode == 1 && a.kernel_visible_host()); };
+    auto direct_in = [&](const NDArray& a) {
+      return a.on_gpu() || (kHostMode == 1 && a.kernel_visible_host()) ||
+             (kHostMode == 5 && a.kernel_visible_host() && a.ByteSize() < kHybridMin);
+    };
     auto direct_out = [&](const NDArray& a) {
-      return a.on_gpu() || (kHostMode >= 1 && kHostMode <= 3 && a.kernel_visible_host());
+      return a.on_gpu() || (kHostMode >= 1 && kHostMode <= 3 && a.kernel_visible_host()) ||
+             (kHostMode == 5 && a.kernel_visible_host() && a.ByteSize() < kHybridMin);
     };
     size_t staged = 0;
     for (auto& s : op.srcs) if (!direct_in(s)) staged += s.ByteSize();

@@ -165,11 +165,12 @@ class KVStore {
 
   void Init(const std::vector<int>& keys, const std::vector<NDArray>& values);
   void InitStr(const std::vector<std::string>& keys, const std::vector<NDArray>& values);
-  void Push(const std::vector<int>& keys, const std::vector<NDArray>& values, int priority);
-  void Pull(const std::vector<int>& keys, const std::vector<NDArray>& outs, int priority,
+  // (operand vectors by value: the C entry points hand over temporaries, a queued call keeps them)
+  void Push(std::vector<int> keys, std::vector<NDArray> values, int priority);
+  void Pull(std::vector<int> keys, std::vector<NDArray> outs, int priority,
             bool ignore_sparse);
-  void PushPull(const std::vector<int>& vkeys, const std::vector<int>& okeys,
-                const std::vector<NDArray>& values, const std::vector<NDArray>& outs, int priority);
+  void PushPull(std::vector<int> vkeys, std::vector<int> okeys, std::vector<NDArray> values,
+                std::vector<NDArray> outs, int priority);
   void PullRowSparse(const std::vector<int>& keys, const std::vector<NDArray>& outs,
                      const std::vector<NDArray>& row_ids, int priority);
   std::vector<int> LookupKeys(const std::vector<std::string>& str_keys);
@@ -279,8 +280,9 @@ class KVStore {
     std::vector<NDArray> vals, outs;
     int priority = 0;
   };
-  bool TryDefer(int kind, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
-                const std::vector<int>& okeys, const std::vector<NDArray>& outs, int priority);
+  // queues the call and takes the vectors' contents when it returns true; leaves them alone otherwise
+  bool TryDefer(int kind, std::vector<int>& vkeys, std::vector<NDArray>& values, std::vector<int>& okeys,
+                std::vector<NDArray>& outs, int priority);
   std::vector<PendingOp> pending_;
   std::vector<KeyEntry*> pending_entries_;      // keys with a queued push (KeyEntry::queued bit 0) / pull (bit 1)
   size_t pending_bytes_ = 0, bucket_bytes_ = 0;

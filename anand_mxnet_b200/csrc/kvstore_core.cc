@@ -351,8 +351,8 @@ void KVStore::FlushAll() {
   for (KVStore* kv : LiveStores()) kv->Flush();
 }
 
-bool KVStore::TryDefer(int kind, const std::vector<int>& vkeys, const std::vector<NDArray>& values,
-                       const std::vector<int>& okeys, const std::vector<NDArray>& outs, int priority) {
+bool KVStore::TryDefer(int kind, std::vector<int>& vkeys, std::vector<NDArray>& values,
+                       std::vector<int>& okeys, std::vector<NDArray>& outs, int priority) {
   if ((updater_ != nullptr && !opt_.enabled) || gc_type_ != "none") return false;
   size_t cap = bucket_bytes_;
   if (cap == 0) {
@@ -394,13 +394,6 @@ bool KVStore::TryDefer(int kind, const std::vector<int>& vkeys, const std::vecto
     bytes += o.ByteSize();
   }
   if (conflict) Flush();
-  pending_.emplace_back();
-  PendingOp& op = pending_.back();
-  op.vkeys = vkeys;
-  op.vals = values;
-  op.okeys = okeys;
-  op.outs = outs;
-  op.priority = priority;
   last = nullptr;
   auto mark = [&](int k, uint8_t bit) {
     KeyEntry& e = (last != nullptr && last->key == k) ? *last : Entry(k);
@@ -410,6 +403,13 @@ bool KVStore::TryDefer(int kind, const std::vector<int>& vkeys, const std::vecto
   };
   for (int k : vkeys) mark(k, 1);
   for (int k : okeys) mark(k, 2);
+  pending_.emplace_back();
+  PendingOp& op = pending_.back();
+  op.vkeys = std::move(vkeys);
+  op.vals = std::move(values);
+  op.okeys = std::move(okeys);
+  op.outs = std::move(outs);
+  op.priority = priority;
   pending_bytes_ += bytes;
   if (pending_bytes_ >= cap) Flush();
   return true;
@@ -461,23 +461,25 @@ void KVStore::SetBucketBytes(size_t n) {
   bucket_auto_ = false;  // an explicit size (0 = off) replaces the automatic policy
 }
 
-void KVStore::Push(const std::vector<int>& keys, const std::vector<NDArray>& values, int priority) {
-  if (TryDefer(0, keys, values, {}, {}, priority)) return;
+void KVStore::Push(std::vector<int> keys, std::vector<NDArray> values, int priority) {
+  std::vector<int> no_keys;
+  std::vector<NDArray> no_outs;
+  if (TryDefer(0, keys, values, no_keys, no_outs, priority)) return;
   Flush();
   PushImpl(keys, values, nullptr, nullptr);
 }
 
-void KVStore::PushPull(const std::vector<int>& vkeys, const std::vector<int>& okeys,
-                       const std::vector<NDArray>& values, const std::vector<NDArray>& outs,
-                       int priority) {
+void KVStore::PushPull(std::vector<int> vkeys, std::vector<int> okeys, std::vector<NDArray> values,
+                       std::vector<NDArray> outs, int priority) {
   if (TryDefer(2, vkeys, values, okeys, outs, priority)) return;
   Flush();
   PushImpl(vkeys, values, &okeys, &outs);
 }
 
-void KVStore::Pull(const std::vector<int>& keys, const std::vector<NDArray>& outs, int priority,
-                   bool ignore_sparse) {
-  if (ignore_sparse && TryDefer(1, {}, {}, keys, outs, priority)) return;
+void KVStore::Pull(std::vector<int> keys, std::vector<NDArray> outs, int priority, bool ignore_sparse) {
+  std::vector<int> no_keys;
+  std::vector<NDArray> no_vals;
+  if (ignore_sparse && TryDefer(1, no_keys, no_vals, keys, outs, priority)) return;
   Flush();
   PullImpl(keys, outs, ignore_sparse);
 }
