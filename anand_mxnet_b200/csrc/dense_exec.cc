@@ -425,6 +425,31 @@ void KVStore::RunPrepared(Prepared& P) {
       PeerGroup* g = PeerGroup::Get();
       KV_CHECK(g != nullptr) << "the peer group was destroyed while a store still uses it";
       g->FillLaunch(&L);
+      // gate launch: the start barrier runs in a one-CTA kernel ahead of the fused kernel (same
+      // epoch, start flags only), so a rank whose peers are late -- a checkpoint, an evaluation
+      // pass, a slow data loader on one rank -- waits with ONE resident CTA instead of a grid of
+      // spinning ones, and the SMs stay free for whatever else its streams have queued.
+      // B200KV_GATE=0 puts the wait back inside the fused kernel.
+      static const bool gate = []() {
+        const char* z = std::getenv("B200KV_GATE");
+        return z == nullptr || z[0] != '0';
+      }();
+      if (gate) {
+        DenseLaunch G;
+        G.signal_pads = L.signal_pads;
+        G.counter = L.counter;
+        G.rank = L.rank;
+        G.world = L.world;
+        G.epoch = L.epoch;
+        G.err_word = L.err_word;
+        G.timeout_ns = L.timeout_ns;
+        G.n_chunks = 0;
+        G.dtype = kFloat32;
+        G.opt = kOptAssign;
+        G.barrier_mask = 1;
+        LaunchDenseFused(G, st);
+        L.barrier_mask = 2;
+      }
     }
     L.keys = static_cast<const KeyDesc*>(pd.d_keys);
     L.chunks = static_cast<const ChunkDesc*>(pd.d_chunks);

@@ -311,6 +311,7 @@ struct KernelArgs {
   int n_chunks;
   uint32_t* err_word;
   unsigned long long timeout_ns;
+  int barrier_mask;
 };
 
 // ---- cross-process barrier on IPC-mapped signal pads ------------------------------------------
@@ -386,9 +387,11 @@ dense_fused_kernel(const KernelArgs a) {
   constexpr int U = UN;
   __shared__ KeyDesc sk;
   __shared__ uint32_t s_last;
-  if (a.pads != nullptr) {
+  if (a.pads != nullptr && (a.barrier_mask & 1)) {
     // start barrier: a rank's kernel only starts after its stream produced its gradients, so
-    // "every peer has started" == "every peer's gradients (and pull targets) are ready"
+    // "every peer has started" == "every peer's gradients (and pull targets) are ready". With the
+    // gate launch (group.h) this wait runs in a one-CTA kernel ahead of this one, so that a rank
+    // waiting for a late peer does not hold every SM with spinning CTAs.
     peer_signal_and_wait(a, 0, blockIdx.x == 0);
     __syncthreads();
   }
@@ -424,7 +427,7 @@ dense_fused_kernel(const KernelArgs a) {
     }
   }
   }  // blockIdx.x < n_chunks
-  if (a.pads != nullptr) {
+  if (a.pads != nullptr && (a.barrier_mask & 2)) {
     // end barrier: the LAST CTA of this rank to finish tells every peer "I have read your
     // gradients and written your weights" and waits for the same from them; the kernel -- hence
     // everything the stream runs after it -- completes only when all peers are done with us.
@@ -452,7 +455,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) dense_plain_kernel(const KernelArgs a, int opt) {
   __shared__ KeyDesc sk;
   __shared__ uint32_t s_last;
-  if (a.pads != nullptr) {
+  if (a.pads != nullptr && (a.barrier_mask & 1)) {
     peer_signal_and_wait(a, 0, blockIdx.x == 0);
     __syncthreads();
   }
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(kThreads) dense_plain_kernel(const KernelArgs 
       for (int o = 0; o < n_out; ++o) static_cast<T*>(sk.out[o])[i] = acc;
     }
   }
-  if (a.pads != nullptr) {
+  if (a.pads != nullptr && (a.barrier_mask & 2)) {
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
@@ -509,7 +512,7 @@ void launch_plain(const DenseLaunch& p, cudaStream_t s) {
   KV_CHECK(!p.nvls);
   KernelArgs a{p.keys, p.chunks, reinterpret_cast<const float2*>(p.hyper), p.lrs, p.wds, p.order, p.momentum,
                p.rescale, p.clip, p.beta1, p.beta2, p.eps, p.signal_pads, p.counter, p.rank, p.world,
-               p.epoch, p.n_chunks, p.err_word, p.timeout_ns};
+               p.epoch, p.n_chunks, p.err_word, p.timeout_ns, p.barrier_mask};
   const int grid = p.n_chunks > 0 ? p.n_chunks : 1;
   dense_plain_kernel<T><<<grid, kThreads, 0, s>>>(a, p.opt);
 }
@@ -518,7 +521,7 @@ template <typename T, int MAXSRC, int OPT, bool NVLS = false, int UN = 1>
 void launch_one(const DenseLaunch& p, cudaStream_t s) {
   KernelArgs a{p.keys, p.chunks, reinterpret_cast<const float2*>(p.hyper), p.lrs, p.wds, p.order, p.momentum,
                p.rescale, p.clip, p.beta1, p.beta2, p.eps, p.signal_pads, p.counter, p.rank, p.world,
-               p.epoch, p.n_chunks, p.err_word, p.timeout_ns};
+               p.epoch, p.n_chunks, p.err_word, p.timeout_ns, p.barrier_mask};
   const int grid = p.n_chunks > 0 ? p.n_chunks : 1;  // a rank with no chunk still joins the barriers
   dense_fused_kernel<T, MAXSRC, OPT, NVLS, UN><<<grid, kThreads, 0, s>>>(a);
 }

@@ -82,6 +82,7 @@ struct DenseLaunch {
   // error at its next wait instead of the context dying in a __trap
   uint32_t* err_word = nullptr;
   unsigned long long timeout_ns = 0;
+  int barrier_mask = 3;  // bit 0: start barrier inside this launch, bit 1: end barrier
 };
 
 // Fused reduce (+scale/clip +optimizer step) (+broadcast) over a list of chunks, one CTA per chunk.
