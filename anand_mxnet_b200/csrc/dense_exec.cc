@@ -456,7 +456,8 @@ void KVStore::RunPrepared(Prepared& P) {
     L.hyper = static_cast<const float*>(pd.d_hyper);
     L.n_chunks = pd.n_chunks;
     LaunchDenseFused(L, st);
-    eng->CountLaunch("dense_fused", P.plan->algorithmic_bytes / P.plan->per_dev.size());
+    eng->CountLaunch(P.plan->nvls ? "dense_fused(nvls)" : "dense_fused",
+                     P.plan->algorithmic_bytes / P.plan->per_dev.size());
   }
   if (multi) eng->JoinStreams(P.parts);
 

@@ -229,8 +229,16 @@ void* Engine::Alloc(int dev, size_t bytes, Var* fresh) {
   KV_CHECK(dev >= 0 && dev < ndev_) << "invalid gpu id " << dev;
   DevMem& d = mem_[dev];
   size_t r = RoundSize(bytes);
-  auto it = d.pool.find(r);
-  if (it != d.pool.end()) {
+  auto range = d.pool.equal_range(r);
+  if (range.first != range.second) {
+    // lowest address of the size class: which block an allocation gets then depends only on the SET
+    // of free blocks, not on the order they were freed in -- ranks that released the same arrays in
+    // a different order (garbage collection) still hand out the same arena offsets, which the NVLS
+    // mode needs (a multicast address is one offset in every rank's arena)
+    auto it = range.first;
+    for (auto j = range.first; j != range.second; ++j) {
+      if (j->second.p < it->second.p) it = j;
+    }
     const Block b = it->second;
     d.pool.erase(it);
     if (fresh != nullptr) {
