@@ -7,6 +7,7 @@
 // arena offsets per distinct call signature); running a prepared launch involves no host
 // communication at all -- the kernel's start / end barriers order the ranks.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <map>
 
@@ -351,14 +352,24 @@ std::shared_ptr<Plan> KVStore::GetPlanGroup(const std::vector<DenseOp>& ops, int
   }();
   const bool want_nvls = nvls_env < 0 ? W >= 8 : nvls_env == 1;
   bool nvls = want_nvls && g->has_multicast() && fixed_owner < 0 && W >= 2 && W < kMaxSrc;
+  // why a launch that wanted the switch fell back to peer loads (B200KV_DEBUG_NVLS=1, rank 0)
+  static const bool debug_nvls = std::getenv("B200KV_DEBUG_NVLS") != nullptr;
+  auto reject = [&](size_t k, const char* why, int r, int64_t a, int64_t b) {
+    if (debug_nvls && R == 0 && nvls) {
+      std::fprintf(stderr, "b200kv: NVLS off for this launch: key position %zu (key %d, %zu elements): %s (rank %d: %lld vs rank 0: %lld)\n",
+                   k, ops[k].e->key, ops[k].e->size, why, r, static_cast<long long>(a), static_cast<long long>(b));
+    }
+    nvls = false;
+  };
   for (size_t k = 0; nvls && k < ops.size(); ++k) {
-    if (ops[k].e->dtype != kFloat32) nvls = false;
+    if (ops[k].e->dtype != kFloat32) reject(k, "dtype is not float32", 0, ops[k].e->dtype, 0);
     const int64_t nout = field(0, k, 4);
-    if (nout > 2 || W * nout > kMaxDst - 2) nvls = false;
+    if (nvls && (nout > 2 || W * nout > kMaxDst - 2)) reject(k, "too many pull targets", 0, nout, 0);
     for (int r = 1; nvls && r < W; ++r) {
-      if (field(r, k, 3) != field(0, k, 3) || field(r, k, 4) != nout) nvls = false;
+      if (field(r, k, 3) != field(0, k, 3)) reject(k, "gradient at a different arena offset", r, field(r, k, 3), field(0, k, 3));
+      if (nvls && field(r, k, 4) != nout) reject(k, "different number of pull targets", r, field(r, k, 4), nout);
       for (int i = 0; nvls && i < nout; ++i) {
-        if (field(r, k, 5 + i) != field(0, k, 5 + i)) nvls = false;
+        if (field(r, k, 5 + i) != field(0, k, 5 + i)) reject(k, "pull target at a different arena offset", r, field(r, k, 5 + i), field(0, k, 5 + i));
       }
     }
   }
@@ -379,7 +390,13 @@ std::shared_ptr<Plan> KVStore::GetPlanGroup(const std::vector<DenseOp>& ops, int
   std::vector<ChunkDesc>& own = chunks[R];
   p.n_chunks = static_cast<int>(own.size());
   p.bytes_keys = ops.size() * sizeof(KeyDesc);
-  p.bytes_chunks = std::max<size_t>(own.size(), 1) * sizeof(ChunkDesc);
+  // the tables come out of the arena too: size them alike on every rank (the chunk counts differ
+  // by a few between ranks), or the ranks' later allocations drift apart and the NVLS mode -- one
+  // offset in every rank's arena -- silently falls back to peer loads for everything allocated
+  // afterwards (measured: the BERT leg of bench.py at 8 ranks, 1.21 ms instead of 0.99)
+  size_t max_chunks = 1;
+  for (auto& c : chunks) max_chunks = std::max(max_chunks, c.size());
+  p.bytes_chunks = max_chunks * sizeof(ChunkDesc);
   p.bytes_hyper = ops.size() * 2 * sizeof(float);
   p.d_keys = eng->Alloc(dev, p.bytes_keys);
   p.d_chunks = eng->Alloc(dev, p.bytes_chunks);
