@@ -1000,6 +1000,17 @@ B200KV_DLL int B200KVTestGatherI64(int world, B200KVAllGatherFn allgather, void*
   return 0;
 }
 
+// host-only hook: the shared-memory mailbox between the ranks of a node (group.cc), no GPU needed
+B200KV_DLL int B200KVTestMailbox(int rank, int world, B200KVAllGatherFn allgather, void* ctx,
+                                 const int64_t* mine, int n, int rounds, int64_t* out, int* used_mailbox) {
+  try {
+    PeerGroup::TestMailbox(rank, world, allgather, ctx, mine, n, rounds, out, used_mailbox);
+  } catch (const std::exception& e) {
+    return HandleException(e);
+  }
+  return 0;
+}
+
 int B200KVGetKernelLaunchCount(uint64_t* out) {
   *out = Engine::Get()->launch_count;
   return 0;

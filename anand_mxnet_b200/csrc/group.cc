@@ -134,6 +134,25 @@ bool PeerGroup::MailboxAllGather(const void* send, void* recv, size_t nbytes) {
   return true;
 }
 
+void PeerGroup::TestMailbox(int rank, int world, B200KVAllGatherFnC fn, void* ctx, const int64_t* mine,
+                            int n, int rounds, int64_t* out, int* used_mailbox) {
+  PeerGroup g;
+  g.rank_ = rank;
+  g.world_ = world;
+  g.fn_ = fn;
+  g.ctx_ = ctx;
+  g.InitMailbox();
+  *used_mailbox = g.mbox_ != nullptr ? 1 : 0;
+  std::vector<int64_t> v(mine, mine + n);
+  std::vector<int64_t> all;
+  for (int it = 0; it < rounds; ++it) {
+    for (auto& x : v) x += 1;                 // every round carries different values
+    all = g.AllGatherI64(v);
+  }
+  std::memcpy(out, all.data(), all.size() * sizeof(int64_t));
+  if (g.mbox_ != nullptr) munmap(g.mbox_, g.mbox_bytes_);
+}
+
 void PeerGroup::AllGather(const void* send, void* recv, size_t nbytes) {
   if (MailboxAllGather(send, recv, nbytes)) return;
   KV_CHECK_EQ(fn_(send, recv, nbytes, ctx_), 0) << "all-gather callback failed";

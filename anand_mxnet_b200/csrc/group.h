@@ -73,6 +73,11 @@ class PeerGroup {
   // NCCL communicator over the group's ranks, created on first use (unique id from rank 0 through
   // the launcher's all-gather callback). Collective: every rank must call it at the same point.
   void* NcclCommunicator();
+  // host-only test hook (no GPU): builds the shared-memory mailbox of a `world`-rank job through
+  // the launcher's callback and runs `rounds` all-gathers of `n` int64 values over it; out receives
+  // the last round's result, *used_mailbox whether shared memory (not the callback) carried them
+  static void TestMailbox(int rank, int world, B200KVAllGatherFnC fn, void* ctx, const int64_t* mine,
+                          int n, int rounds, int64_t* out, int* used_mailbox);
 
  private:
   PeerGroup() {}

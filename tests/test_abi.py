@@ -116,3 +116,55 @@ def test_optimizer_bookkeeping(mx):
         mx.optimizer.create('lars')                      # no fused kernel: callback route only
     with pytest.raises(TypeError):
         mx.optimizer.get_updater(opt)                    # a record carries no update rule
+
+
+def test_optimizer_record_rules(mx):
+    """the rest of the record's contract: defaults, scheduler handling, objects of the reference's
+    classes (tests/compat mirror) read as records, pickling without Parameter objects"""
+    import pickle
+    from compat import mxnet_optimizer as mxopt
+
+    class Sched(object):
+        base_lr = 0.5
+
+        def __call__(self, num_update):
+            return self.base_lr / (1 + num_update)
+    sgd = mx.optimizer.SGD(lr_scheduler=Sched(), momentum=0.9)
+    assert sgd.lr is None and sgd.learning_rate == 0.5          # the scheduler supplies the rate
+    sgd.num_update = 4
+    assert sgd.learning_rate == 0.1
+    with pytest.raises(UserWarning):
+        sgd.set_learning_rate(0.3)                              # optimizer.py:356-365
+    s2 = Sched()
+    explicit = mx.optimizer.SGD(learning_rate=0.2, lr_scheduler=s2)
+    assert s2.base_lr == 0.2 and explicit.lr == 0.2             # an explicit rate wins (optimizer.py:117-123)
+    with pytest.raises(TypeError):
+        mx.optimizer.SGD(beta1=0.9)                              # not an SGD parameter
+    p = mx.optimizer.Adam(clip_gradient=None, wd=0.01).op_params()
+    assert p['clip_gradient'] == 0.0 and p['wd'] == 0.01 and p['lazy_update'] is True
+    assert set(mx.optimizer.Test().op_params()) == {'learning_rate', 'wd', 'rescale_grad', 'clip_gradient',
+                                                    'multi_precision', 'begin_num_update'}
+    # an object of the reference's SGD class is recognised by class name + attributes ...
+    ref_sgd = mxopt.SGD(learning_rate=0.05, momentum=0.8, wd=1e-3, param_idx2name={0: 'a_weight', 1: 'a_bias'})
+    assert mx.optimizer.fused_kind(ref_sgd) == 'sgd'
+    rec = mx.optimizer.record_of(ref_sgd)
+    assert rec.kind == 'sgd' and rec.momentum == 0.8 and rec.multipliers(1) == (1.0, 0.0)
+    assert rec.op_params()['learning_rate'] == 0.05
+    # ... one of another class is not (callback route), and get_updater wraps its own update rule
+    lars = mxopt.LARS(learning_rate=0.1)
+    assert mx.optimizer.fused_kind(lars) is None
+    upd = mx.optimizer.get_updater(lars)
+    assert upd.optimizer is lars and upd.states == {}
+    # Parameter objects do not travel with a pickled record (optimizer.py:512-519)
+
+    class P(object):
+        lr_mult, wd_mult = 2.0, 3.0
+    adam = mx.optimizer.Adam(param_dict={7: P()})
+    assert adam.multipliers(7) == (2.0, 3.0)
+    back = pickle.loads(pickle.dumps(adam))
+    assert back.param_dict == {} and back.kind == 'adam' and back.beta1 == 0.9
+    # the callback updater's pickle: {index: state}, or (states, optimizer)
+    upd.states = {3: None}
+    assert pickle.loads(upd.get_states()) == {3: None}
+    st, opt = pickle.loads(upd.get_states(dump_optimizer=True))
+    assert st == {3: None} and type(opt).__name__ == 'LARS'

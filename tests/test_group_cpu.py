@@ -55,3 +55,52 @@ def test_offset_exchange_world2_gloo():
         p.join(timeout=60)
     for rank, ok, msg in results:
         assert ok, (rank, msg)
+
+
+def _mailbox_worker(rank, world, port, q):
+    import random
+    import time
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import anand_mxnet_b200 as mx
+        cb = mx.dist.make_allgather_callback(None)
+        lib = mx.base._LIB
+        ok, msg = True, ""
+        # n = 6: one slot; n = 1000: 8000 bytes = two 4 KB pieces per gather; many rounds so that a
+        # fast rank runs ahead of a slow one (the two-slot protocol must hold it back)
+        for n, rounds in ((6, 300), (1000, 120)):
+            mine = (ctypes.c_int64 * n)(*[100000 * rank + i for i in range(n)])
+            out = (ctypes.c_int64 * (n * world))()
+            used = ctypes.c_int(0)
+            if rank == world - 1:
+                time.sleep(0.05 * random.random())
+            rc = lib.B200KVTestMailbox(rank, world, cb, None, mine, n, rounds, out, ctypes.byref(used))
+            want = [100000 * r + i + rounds for r in range(world) for i in range(n)]
+            if rc != 0 or list(out) != want:
+                ok, msg = False, "n=%d rc=%d %s" % (n, rc, lib.MXGetLastError().decode())
+            if used.value != 1:
+                ok, msg = False, "shared memory mailbox not used (n=%d)" % n
+        q.put((rank, ok, msg))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_shared_memory_mailbox_allgather(world):
+    """the host-side metadata exchange of the rank-per-GPU store (group.cc: shared-memory mailbox
+    built through ONE exchange over the launcher's callback, then spin-wait all-gathers)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mailbox_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, msg in results:
+        assert ok, (rank, msg)
