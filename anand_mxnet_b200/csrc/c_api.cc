@@ -22,6 +22,7 @@
 #include <stdexcept>
 
 #include "kvstore.h"
+#include "nccl_dyn.h"
 #include "ndarray.h"
 #include "ops.h"
 #include "scalar_parse.h"
@@ -1005,6 +1006,19 @@ B200KV_DLL int B200KVTestMailbox(int rank, int world, B200KVAllGatherFn allgathe
                                  const int64_t* mine, int n, int rounds, int64_t* out, int* used_mailbox) {
   try {
     PeerGroup::TestMailbox(rank, world, allgather, ctx, mine, n, rounds, out, used_mailbox);
+  } catch (const std::exception& e) {
+    return HandleException(e);
+  }
+  return 0;
+}
+
+// host-only hook: can the NCCL fallback bind its library? (dlopen + dlsym only, no GPU, no communicator)
+B200KV_DLL int B200KVTestNcclAvailable(int* available, char* version, size_t version_len) {
+  try {
+    *available = Nccl::Available() ? 1 : 0;
+    if (*available && version != nullptr && version_len > 0) {
+      std::snprintf(version, version_len, "%s", Nccl::Get()->version());
+    }
   } catch (const std::exception& e) {
     return HandleException(e);
   }

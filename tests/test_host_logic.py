@@ -126,3 +126,17 @@ def test_oracle_ops_match_live_reference_on_random_cases(seed):
         results.append([a.copy() for a in ws + ms + vs])
     for a, b in zip(*results):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_nccl_fallback_library_binds():
+    """kvstore 'nccl' binds libnccl.so.2 at run time (csrc/nccl_dyn.cc): every entry point the
+    fallback needs resolves here, without a GPU"""
+    import ctypes
+    import anand_mxnet_b200 as mx
+    lib = mx.base._LIB
+    avail = ctypes.c_int(-1)
+    ver = ctypes.create_string_buffer(32)
+    assert lib.B200KVTestNcclAvailable(ctypes.byref(avail), ver, ctypes.c_size_t(32)) == 0
+    assert avail.value == 1, "libnccl.so.2 not loadable in this image"
+    major = int(ver.value.decode().split('.')[0])
+    assert major >= 2
