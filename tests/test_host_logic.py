@@ -140,3 +140,42 @@ def test_nccl_fallback_library_binds():
     assert avail.value == 1, "libnccl.so.2 not loadable in this image"
     major = int(ver.value.decode().split('.')[0])
     assert major >= 2
+
+
+def test_bench_parity_and_config_helpers():
+    """bench.py's checker plumbing: the config block is a pure function of (workload, N) -- the two
+    arms of the driver's comparison print the same dict --, the parity block distinguishes
+    bit equality from the reference's 1e-6 relative-L1 bound, and the seeded sets are reproducible"""
+    import numpy as np
+    import bench
+    for wl in ('resnet50_sgd', 'bert_adam', 'rsp'):
+        for n in (1, 2, 8):
+            assert bench.config_block(wl, n) == bench.config_block(wl, n)
+            assert set(bench.config_block(wl, n)) == {'workload', 'values_per_key', 'value_formula', 'l2'}
+    assert bench.config_block('resnet50_sgd', 2) != bench.config_block('resnet50_sgd', 4)
+    a = [np.arange(10, dtype=np.float32), np.ones(5, np.float32)]
+    same = bench.compare_sets([x.copy() for x in a], a, exact=True)
+    assert same['ok'] and same['max_rel'] == 0.0 and same['tensors_differing'] == 0
+    b = [x.copy() for x in a]
+    b[0][3] = np.nextafter(b[0][3], np.float32(10))            # one ulp off
+    assert not bench.compare_sets(b, a, exact=True)['ok']
+    tol = bench.compare_sets(b, a, exact=False)
+    assert tol['ok'] and 0 < tol['max_rel'] < 1e-6 and tol['tensors_differing'] == 1
+    b[1][0] = 2.0
+    assert not bench.compare_sets(b, a, exact=False)['ok']
+    s1 = bench.flat_set(bench.grad_seed(3), [7, 1, 100])
+    s2 = bench.flat_set(bench.grad_seed(3), [7, 1, 100])
+    assert all(np.array_equal(x, y) for x, y in zip(s1, s2)) and [len(x) for x in s1] == [7, 1, 100]
+    assert all(np.all((x >= -1) & (x < 1)) for x in s1)
+    assert not np.array_equal(bench.flat_set(bench.grad_seed(4), [7])[0], s1[0])
+    assert bench.kernel_label('bert_adam', 4) == 'dense_fused_kernel<float,4,Adam>'
+    assert 'NVLS' in bench.kernel_label('resnet50_sgd', 8, nvls=True)
+    # the oracle model behind the parity block, on a small made-up "workload"
+    bench.WORKLOADS['_tiny'] = dict(shapes=lambda: [(5,), (2, 3)], opt='sgd', bytes_per_elem=24, desc='tiny')
+    try:
+        w1 = bench.oracle_expected('_tiny', 2, 1)
+        w2 = bench.oracle_expected('_tiny', 2, 2)
+        assert [x.shape for x in w1] == [(5,), (6,)] or [x.size for x in w1] == [5, 6]
+        assert not np.array_equal(w1[0], w2[0])
+    finally:
+        del bench.WORKLOADS['_tiny']
