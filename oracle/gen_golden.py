@@ -25,10 +25,66 @@ def u(rng, *shape):
     return rng.uniform(-1, 1, shape).astype(np.float32)
 
 
+def rsp_cases():
+    """row_sparse reduce / retain / unique inputs (own RNG stream, shared with tests/test_oracle.py):
+    duplicates across sources, an empty source, a source holding every row, one source only,
+    unsorted + repeated pull ids, ids the source does not hold."""
+    rng = np.random.default_rng(0xB200 + 5)
+    rows, rl = 211, 19
+    red = {}
+    layouts = {"dup4": [60, 60, 60, 60], "empty_mid": [40, 0, 25], "full_plus": [rows, 30], "single": [50],
+               "nine": [12] * 9, "all_empty": [0, 0]}
+    for tag, counts in layouts.items():
+        idxs = [np.sort(rng.choice(rows, c, replace=False)).astype(np.int64) for c in counts]
+        vals = [u(rng, c, rl) for c in counts]
+        red[tag] = (idxs, vals)
+    src_i = np.sort(rng.choice(rows, 80, replace=False)).astype(np.int64)
+    src_v = u(rng, 80, rl)
+    dense_v = u(rng, rows, rl)
+    ret = {
+        "sorted_unique": (src_i, src_v, np.unique(rng.integers(0, rows, 70)).astype(np.int64), False),
+        "unsorted_dup": (src_i, src_v, rng.integers(0, rows, 90).astype(np.int64), False),
+        "none_present": (src_i, src_v, np.setdiff1d(np.arange(rows), src_i)[:33].astype(np.int64), False),
+        "empty_src": (np.zeros(0, np.int64), np.zeros((0, rl), np.float32),
+                      np.arange(0, rows, 7, dtype=np.int64), False),
+        "dense_src": (np.arange(rows, dtype=np.int64), dense_v, rng.integers(0, rows, 64).astype(np.int64), True),
+    }
+    uniq = {"random": rng.integers(0, rows, 500).astype(np.int64), "one": np.array([7], np.int64),
+            "same": np.full(33, 5, np.int64), "descending": np.arange(100, 0, -1, dtype=np.int64)}
+    return red, ret, uniq
+
+
+def gen_rsp(r):
+    """the reference's own ElementwiseSumRsp / sparse_retain kernels / UniqueImpl (oracle/ref_sparse.cc)"""
+    red, ret, uniq = rsp_cases()
+    d = {}
+    for tag, (idxs, vals) in red.items():
+        for nt in (1, 4):
+            oi, ov = r.rsp_reduce(idxs, vals, nthreads=nt)
+            if nt == 1:
+                d["reduce_%s_idx" % tag], d["reduce_%s_val" % tag] = oi, ov
+            else:       # the reference's threading splits the union rows: same bits for any thread count
+                assert np.array_equal(oi, d["reduce_%s_idx" % tag])
+                assert np.array_equal(ov.view(np.uint32), d["reduce_%s_val" % tag].view(np.uint32))
+    for tag, (si, sv, ids, dense) in ret.items():
+        oi, ov = r.sparse_retain(si, sv, ids, src_dense_rows=dense)
+        d["retain_%s_idx" % tag], d["retain_%s_val" % tag] = oi, ov
+        if tag == "sorted_unique":      # the reference's row-block kernel agrees with its per-id kernel
+            bi, bv = r.sparse_retain(si, sv, ids, row_block=True)
+            assert np.array_equal(bi, oi) and np.array_equal(bv.view(np.uint32), ov.view(np.uint32))
+    for tag, ids in uniq.items():
+        d["unique_%s" % tag] = r.unique(ids)
+    np.savez_compressed(os.path.join(GOLD, "rowsparse_reduce_retain.npz"), **d)
+
+
 def main():
     r = K.ref()
     assert r is not None, "build oracle/_ref first: make -C oracle ref"
     os.makedirs(GOLD, exist_ok=True)
+    if "--rsp-only" in sys.argv:       # add this fixture without rewriting the others' zip timestamps
+        gen_rsp(r)
+        return
+    gen_rsp(r)
     rng = np.random.default_rng(0xB200)
 
     # ---- dense reduce, CommCPU association, 1..9 sources + a >BIGARRAY_BOUND threaded case ----

@@ -317,7 +317,7 @@ class Oracle(object):
     def rsp_reduce(self, idxs, vals):
         """idxs: list of int64 [nnr_s]; vals: list of fp32 [nnr_s, row_len] -> (idx, val)."""
         idxs = [np.ascontiguousarray(i, dtype=np.int64) for i in idxs]
-        vals = [_f32(v).reshape(len(i), -1) for i, v in zip(idxs, vals)]
+        vals = _rows2d(idxs, vals)
         row_len = vals[0].shape[1]
         total = sum(len(i) for i in idxs)
         out_idx = np.empty(max(total, 1), dtype=np.int64)
@@ -330,7 +330,7 @@ class Oracle(object):
     def sparse_retain(self, src_idx, src_val, ids, src_dense_rows=False):
         src_idx = np.ascontiguousarray(src_idx, dtype=np.int64)
         src_val = _f32(src_val)
-        src_val = src_val.reshape(src_val.shape[0], -1)
+        src_val = src_val.reshape(src_val.shape[0], int(np.prod(src_val.shape[1:])))
         ids = np.ascontiguousarray(ids, dtype=np.int64).ravel()
         out_idx = np.empty(ids.size, dtype=np.int64)
         out_val = np.empty((ids.size, src_val.shape[1]), dtype=np.float32)
@@ -370,6 +370,20 @@ class Oracle(object):
         out = np.empty(n, dtype=np.float32)
         self.lib.kvo_dequantize_2bit(n, _ptr(out), _ptr(comp), threshold)
         return out
+
+
+def _rows2d(idxs, vals):
+    """fp32 [nnr_s, row_len] views of the sources' rows; an empty source takes the others' row_len"""
+    vals = [_f32(v) for v in vals]
+    row_len = 1
+    for i, v in zip(idxs, vals):
+        if v.ndim >= 2:
+            row_len = int(np.prod(v.shape[1:]))
+            break
+        if len(i):
+            row_len = v.size // len(i)
+            break
+    return [v.reshape(len(i), row_len) for i, v in zip(idxs, vals)]
 
 
 class Ref(object):
@@ -583,6 +597,50 @@ class Ref(object):
         comp = np.ascontiguousarray(comp).view(np.float32)
         self.lib.mxref_dequantize_2bit(n, _ptr(out), _ptr(comp), -1 * threshold, threshold)
         return out
+
+    # ---- row_sparse reduce / retain / unique: the reference's own code (oracle/ref_sparse.cc) ----
+    def has_sparse(self):
+        return hasattr(self.lib, 'mxref_rsp_reduce')
+
+    def rsp_reduce(self, idxs, vals, nthreads=1):
+        """ElementwiseSumRsp (ndarray_function.cc:155-176); same signature as Oracle.rsp_reduce"""
+        idxs = [np.ascontiguousarray(i, dtype=np.int64) for i in idxs]
+        vals = _rows2d(idxs, vals)
+        row_len = vals[0].shape[1]
+        total = sum(len(i) for i in idxs)
+        out_idx = np.empty(max(total, 1), dtype=np.int64)
+        out_val = np.empty((max(total, 1), row_len), dtype=np.float32)
+        nnr = (ctypes.c_int64 * len(idxs))(*[len(i) for i in idxs])
+        f = self.lib.mxref_rsp_reduce
+        f.restype = ctypes.c_int64
+        f.argtypes = [_I, _P, _P, _P, ctypes.c_int64, _P, _P, _I]
+        n = f(len(idxs), _ptr_array(idxs), nnr, _ptr_array(vals), row_len, _ptr(out_idx), _ptr(out_val),
+              nthreads)
+        return out_idx[:n].copy(), out_val[:n].copy()
+
+    def sparse_retain(self, src_idx, src_val, ids, src_dense_rows=False, row_block=False):
+        """SparseRetainOpForwardRspImpl's kernels (sparse_retain-inl.h:121-262)"""
+        src_idx = np.ascontiguousarray(src_idx, dtype=np.int64)
+        src_val = _f32(src_val)
+        src_val = src_val.reshape(src_val.shape[0], int(np.prod(src_val.shape[1:])))
+        ids = np.ascontiguousarray(ids, dtype=np.int64).ravel()
+        out_idx = np.empty(ids.size, dtype=np.int64)
+        out_val = np.empty((ids.size, src_val.shape[1]), dtype=np.float32)
+        f = self.lib.mxref_sparse_retain
+        f.restype = None
+        f.argtypes = [_P, ctypes.c_int64, _P, ctypes.c_int64, _P, ctypes.c_int64, _I, _I, _P, _P]
+        f(_ptr(src_idx), src_idx.size, _ptr(src_val), src_val.shape[1], _ptr(ids), ids.size,
+          int(bool(src_dense_rows)), int(bool(row_block)), _ptr(out_idx), _ptr(out_val))
+        return out_idx, out_val
+
+    def unique(self, ids):
+        """UniqueImpl<cpu> (kvstore_utils.cc:31-44)"""
+        ids = np.ascontiguousarray(ids, dtype=np.int64).ravel().copy()
+        f = self.lib.mxref_unique
+        f.restype = ctypes.c_int64
+        f.argtypes = [_P, ctypes.c_int64]
+        n = f(_ptr(ids), ids.size)
+        return ids[:n]
 
 
 _oracle = None

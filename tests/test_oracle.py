@@ -247,6 +247,26 @@ def test_rowsparse_reduce_unique_retain(oracle):
     assert np.array_equal(rv, dense[req])
 
 
+def test_rowsparse_reduce_retain_unique_golden(oracle, golden):
+    """oracle vs outputs of the reference's OWN ElementwiseSumRsp / GetUniqueRspRowIdx
+    (src/ndarray/ndarray_function.cc:59-176), sparse_retain kernels (sparse_retain-inl.h:121-262) and
+    UniqueImpl (kvstore_utils.cc:31-44), generated by oracle/gen_golden.py through oracle/ref_sparse.cc.
+    Bit for bit: the sum over sources is taken in list order, rows ascending."""
+    from gen_golden import rsp_cases
+    g = golden("rowsparse_reduce_retain")
+    red, ret, uniq = rsp_cases()
+    for tag, (idxs, vals) in red.items():
+        oi, ov = oracle.rsp_reduce(idxs, vals)
+        assert np.array_equal(oi, g["reduce_%s_idx" % tag]), tag
+        assert eq(ov, g["reduce_%s_val" % tag]), tag
+    for tag, (si, sv, ids, dense) in ret.items():
+        oi, ov = oracle.sparse_retain(si, sv, ids, src_dense_rows=dense)
+        assert np.array_equal(oi, g["retain_%s_idx" % tag]), tag
+        assert eq(ov, g["retain_%s_val" % tag]), tag
+    for tag, ids in uniq.items():
+        assert np.array_equal(oracle.unique(ids), g["unique_%s" % tag]), tag
+
+
 # ---------------------------------------------------------------- live reference (when built here)
 needs_ref = pytest.mark.skipif(K.ref() is None, reason="oracle/_ref/libmxref.so not built")
 
@@ -299,3 +319,38 @@ def test_optimizers_vs_reference_live(oracle, clip):
     oracle.adam_update(a[0], g, a[1], a[2], 1e-3, wd=.01, clip=clip)
     r.adam_update(b[0], g, b[1], b[2], 1e-3, wd=.01, clip=clip)
     assert all(eq(x, y) for x, y in zip(a, b))
+
+
+@needs_ref
+def test_rowsparse_reduce_retain_vs_reference_live(oracle):
+    """random layouts against the reference's own code (oracle/ref_sparse.cc), any thread count"""
+    r = K.ref()
+    if not r.has_sparse():
+        pytest.skip("oracle/_ref/libmxref.so predates ref_sparse.cc")
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        rows, rl = int(rng.integers(1, 400)), int(rng.integers(1, 70))
+        nsrc = int(rng.integers(1, 10))
+        idxs, vals = [], []
+        for _ in range(nsrc):
+            c = int(rng.integers(0, rows + 1)) if rng.random() < 0.8 else 0
+            idxs.append(np.sort(rng.choice(rows, c, replace=False)).astype(np.int64))
+            vals.append(rng.uniform(-1, 1, (c, rl)).astype(np.float32))
+        oi, ov = oracle.rsp_reduce(idxs, vals)
+        ri, rv = r.rsp_reduce(idxs, vals, nthreads=int(rng.integers(1, 6)))
+        assert np.array_equal(oi, ri) and eq(ov, rv), trial
+        ids = rng.integers(0, rows, int(rng.integers(0, 2 * rows + 1))).astype(np.int64)
+        assert np.array_equal(oracle.unique(ids), r.unique(ids)), trial
+        for req in (ids, oracle.unique(ids)):
+            a = oracle.sparse_retain(oi, ov, req)
+            b = r.sparse_retain(oi, ov, req)
+            assert np.array_equal(a[0], b[0]) and eq(a[1], b[1]), trial
+        # ascending unique ids: the reference's row-block kernel is the third witness
+        req = oracle.unique(ids)
+        b = r.sparse_retain(oi, ov, req, row_block=True)
+        a = oracle.sparse_retain(oi, ov, req)
+        assert np.array_equal(a[0], b[0]) and eq(a[1], b[1]), trial
+        dense = rng.uniform(-1, 1, (rows, rl)).astype(np.float32)
+        a = oracle.sparse_retain(np.arange(rows), dense, ids, src_dense_rows=True)
+        b = r.sparse_retain(np.arange(rows), dense, ids, src_dense_rows=True)
+        assert np.array_equal(a[0], b[0]) and eq(a[1], b[1]), trial
