@@ -77,6 +77,70 @@ def gen_rsp(r):
     np.savez_compressed(os.path.join(GOLD, "rowsparse_reduce_retain.npz"), **d)
 
 
+def updater_cases():
+    """optimizer trajectories on the store's dense path: (index, gradient, weight) per key per step
+    through the reference's own Updater (oracle/ref_python.py). 'model' = the same hyper-parameters in
+    kvoracle.LocalKVStoreModel's vocabulary; 'lr_at' = the learning rate the scheduler yields at each
+    step (restated; the live test proves the restatement)."""
+    rng = np.random.default_rng(0xB200 + 6)
+    shapes = [(4, 4), (100, 100), (1027,), (3,), (7001,)]
+
+    def plan(steps):
+        return dict(shapes=shapes, w0=[u(rng, *s) for s in shapes],
+                    grads=[[u(rng, *s) for s in shapes] for _ in range(steps)])
+    cases = {}
+    cases['sgd_mom'] = dict(plan(4), opt=('SGD', dict(learning_rate=0.1, momentum=0.9, wd=1e-4, rescale_grad=1 / 256)),
+                            model=dict(kind='sgd', lr=0.1, momentum=0.9, wd=1e-4, rescale_grad=1 / 256),
+                            lr_mult={1: 0.5, 3: 2.0}, wd_mult={0: 0.0})
+    cases['sgd_plain_clip'] = dict(plan(3), opt=('SGD', dict(learning_rate=0.05, wd=1e-3, clip_gradient=0.02,
+                                                              rescale_grad=0.125)),
+                                   model=dict(kind='sgd', lr=0.05, momentum=0.0, wd=1e-3, clip_gradient=0.02,
+                                              rescale_grad=0.125))
+    cases['sgd_factor_sched'] = dict(plan(5), opt=('SGD', dict(momentum=0.9, wd=1e-4)),
+                                     sched=('FactorScheduler', dict(step=2, factor=0.5, base_lr=0.2)),
+                                     lr_at=[0.2, 0.2, 0.1, 0.1, 0.05],
+                                     model=dict(kind='sgd', lr=0.2, momentum=0.9, wd=1e-4))
+    cases['adam'] = dict(plan(6), opt=('Adam', dict(learning_rate=1e-3, wd=0.01)),
+                         model=dict(kind='adam', lr=1e-3, wd=0.01), lr_mult={2: 0.1})
+    cases['adam_clip_betas'] = dict(plan(4), opt=('Adam', dict(learning_rate=3e-4, beta1=0.8, beta2=0.98,
+                                                                epsilon=1e-6, clip_gradient=0.5, rescale_grad=0.5)),
+                                    model=dict(kind='adam', lr=3e-4, beta1=0.8, beta2=0.98, epsilon=1e-6,
+                                               clip_gradient=0.5, rescale_grad=0.5))
+    cases['test'] = dict(plan(3), opt=('Test', dict(rescale_grad=2.0)), model=dict(kind='test', rescale_grad=2.0))
+    return cases
+
+
+def run_updater_case(opt_mod, sched_mod, case):
+    """one case through an optimizer front-end module (the reference's, or a mirror of it)"""
+    import ref_python as RP
+    name, kw = case['opt']
+    kw = dict(kw)
+    if 'sched' in case:
+        sname, skw = case['sched']
+        kw['lr_scheduler'] = getattr(sched_mod, sname)(**skw)
+    opt = getattr(opt_mod, name)(**kw)
+    if case.get('lr_mult'):
+        opt.set_lr_mult(case['lr_mult'])
+    if case.get('wd_mult'):
+        opt.set_wd_mult(case['wd_mult'])
+    upd = opt_mod.get_updater(opt)          # what KVStore.set_optimizer installs (kvstore.py:450-453)
+    ws = [RP.NDArray(w.copy()) for w in case['w0']]
+    for gs in case['grads']:
+        for k, g in enumerate(gs):
+            upd(k, RP.NDArray(g.copy()), ws[k])   # the store's callback: updater(key, merged, stored)
+    return [w.a for w in ws]
+
+
+def gen_updater():
+    import ref_python as RP
+    d = {}
+    with RP.reference_python() as (opt, sched):
+        for name, case in updater_cases().items():
+            for k, w in enumerate(run_updater_case(opt, sched, case)):
+                d["%s_w%d" % (name, k)] = w
+    np.savez_compressed(os.path.join(GOLD, "updater_trajectories.npz"), **d)
+
+
 def main():
     r = K.ref()
     assert r is not None, "build oracle/_ref first: make -C oracle ref"
@@ -84,7 +148,11 @@ def main():
     if "--rsp-only" in sys.argv:       # add this fixture without rewriting the others' zip timestamps
         gen_rsp(r)
         return
+    if "--updater-only" in sys.argv:
+        gen_updater()
+        return
     gen_rsp(r)
+    gen_updater()
     rng = np.random.default_rng(0xB200)
 
     # ---- dense reduce, CommCPU association, 1..9 sources + a >BIGARRAY_BOUND threaded case ----

@@ -143,6 +143,16 @@ struct Entry { Parser parse; Compute fn; };
 const std::map<std::string, Entry>& Table() {
   using namespace mxnet::op;
   static std::map<std::string, Entry> t = {
+      // the dense optimizer operators of the KVStore path, as optimizer_op.cc:322-703 registers them
+      {"sgd_update", {ParamParser<SGDParam>, SGDUpdate<cpu>}},
+      {"sgd_mom_update", {ParamParser<SGDMomParam>, SGDMomUpdate<cpu>}},
+      {"mp_sgd_update", {ParamParser<SGDParam>, MP_SGDUpdate<cpu>}},
+      {"mp_sgd_mom_update", {ParamParser<SGDMomParam>, MP_SGDMomUpdate<cpu>}},
+      {"multi_sgd_update", {ParamParser<MultiSGDParam>, MultiSGDUpdate<cpu, type_identity, 2>}},
+      {"multi_sgd_mom_update", {ParamParser<MultiSGDMomParam>, MultiSGDMomUpdate<cpu, type_identity, 3>}},
+      {"multi_mp_sgd_update", {ParamParser<MultiSGDParam>, MultiSGDUpdate<cpu, single_precision, 3>}},
+      {"multi_mp_sgd_mom_update", {ParamParser<MultiSGDMomParam>, MultiSGDMomUpdate<cpu, single_precision, 4>}},
+      {"adam_update", {ParamParser<AdamParam>, AdamUpdate<cpu>}},
       {"multi_sum_sq", {ParamParser<MultiSumSqParam>, MultiSumSq<cpu>}},
       {"multi_lars", {ParamParser<LARSParam>, MultiLARS<cpu>}},
       {"preloaded_multi_sgd_update",
