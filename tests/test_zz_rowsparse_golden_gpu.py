@@ -34,7 +34,7 @@ def rsp(mx, idx, val):
 
 def pull(mx, kv, key, ids):
     out = mx.nd.sparse.zeros('row_sparse', (ROWS, RL), mx.gpu(0))
-    kv.row_sparse_pull(key, out=out, row_ids=mx.nd.array(np.asarray(ids, np.int64), mx.gpu(0), np.int64))
+    kv.row_sparse_pull(key, out=out, row_ids=mx.nd.array(np.ascontiguousarray(ids, np.int64), mx.gpu(0), np.int64))
     return out.indices.asnumpy(), out.data.asnumpy()
 
 
