@@ -564,10 +564,10 @@ class Ref(object):
                                    self._clip(clip), rescale, beta1, beta2, lr, wd, eps, nthreads)
         return w
 
-    def sgd_rsp_update(self, w, gidx, gval, lr, wd=0.0, rescale=1.0, clip=None):
+    def sgd_rsp_update(self, w, gidx, gval, lr, wd=0.0, rescale=1.0, clip=None, nthreads=1):
         gidx = np.ascontiguousarray(gidx, dtype=np.int64)
         self.lib.mxref_sgd_rsp_update(gidx.size, w.shape[1], _ptr(w), _ptr(w), _ptr(gidx),
-                                      _ptr(gval), self._clip(clip), lr, wd, rescale, 1)
+                                      _ptr(gval), self._clip(clip), lr, wd, rescale, nthreads)
         return w
 
     def sgd_mom_rsp_update(self, w, mom, gidx, gval, lr, momentum, wd=0.0, rescale=1.0, clip=None):
@@ -618,7 +618,7 @@ class Ref(object):
               nthreads)
         return out_idx[:n].copy(), out_val[:n].copy()
 
-    def sparse_retain(self, src_idx, src_val, ids, src_dense_rows=False, row_block=False):
+    def sparse_retain(self, src_idx, src_val, ids, src_dense_rows=False, row_block=False, nthreads=1):
         """SparseRetainOpForwardRspImpl's kernels (sparse_retain-inl.h:121-262)"""
         src_idx = np.ascontiguousarray(src_idx, dtype=np.int64)
         src_val = _f32(src_val)
@@ -628,9 +628,9 @@ class Ref(object):
         out_val = np.empty((ids.size, src_val.shape[1]), dtype=np.float32)
         f = self.lib.mxref_sparse_retain
         f.restype = None
-        f.argtypes = [_P, ctypes.c_int64, _P, ctypes.c_int64, _P, ctypes.c_int64, _I, _I, _P, _P]
+        f.argtypes = [_P, ctypes.c_int64, _P, ctypes.c_int64, _P, ctypes.c_int64, _I, _I, _P, _P, _I]
         f(_ptr(src_idx), src_idx.size, _ptr(src_val), src_val.shape[1], _ptr(ids), ids.size,
-          int(bool(src_dense_rows)), int(bool(row_block)), _ptr(out_idx), _ptr(out_val))
+          int(bool(src_dense_rows)), int(bool(row_block)), _ptr(out_idx), _ptr(out_val), nthreads)
         return out_idx, out_val
 
     def unique(self, ids):

@@ -96,10 +96,12 @@ int64_t mxref_rsp_reduce(int nsrc, const int64_t* const* idx, const int64_t* nnr
 // (needs ascending ids) instead of the per-id thread kernel.
 void mxref_sparse_retain(const int64_t* src_idx, int64_t src_nnr, const float* src_val, int64_t row_len,
                          const int64_t* ids, int64_t nids, int src_dense_rows, int row_block,
-                         int64_t* out_idx, float* out_val) {
+                         int64_t* out_idx, float* out_val, int nthreads) {
   using namespace mxnet::op;
+  if (nthreads < 1) nthreads = 1;   // Kernel<OP, cpu>::Launch: omp parallel for over the work items
   std::memset(out_val, 0, static_cast<size_t>(nids) * row_len * sizeof(float));   // Kernel<set_zero>
   if (src_dense_rows) {
+#pragma omp parallel for num_threads(nthreads)
     for (int i = 0; i < nids; ++i) {
       SparseRetainCopyIndices::Map(i, out_idx, const_cast<int64_t*>(ids));
       SparseRetainCopyRetainedRowsFromDnsPerRow::Map(i, out_val, src_val, ids, static_cast<size_t>(row_len));
@@ -107,11 +109,13 @@ void mxref_sparse_retain(const int64_t* src_idx, int64_t src_nnr, const float* s
   } else if (row_block) {
     const size_t seg_len = 7;   // any segmentation must give the same result
     const int nseg = static_cast<int>((nids + seg_len - 1) / seg_len);
+#pragma omp parallel for num_threads(nthreads)
     for (int i = 0; i < nseg; ++i) {
       SparseRetainRspRowBlockKernel::Map(i, out_val, out_idx, src_val, src_idx, ids, static_cast<size_t>(nids),
                                          static_cast<size_t>(src_nnr), static_cast<size_t>(row_len), seg_len);
     }
   } else {
+#pragma omp parallel for num_threads(nthreads)
     for (int i = 0; i < nids; ++i) {
       SparseRetainRspThreadKernel::Map(i, out_val, out_idx, src_val, src_idx, ids,
                                        static_cast<size_t>(src_nnr), static_cast<size_t>(row_len));
