@@ -107,6 +107,23 @@ def updater_cases():
                                     model=dict(kind='adam', lr=3e-4, beta1=0.8, beta2=0.98, epsilon=1e-6,
                                                clip_gradient=0.5, rescale_grad=0.5))
     cases['test'] = dict(plan(3), opt=('Test', dict(rescale_grad=2.0)), model=dict(kind='test', rescale_grad=2.0))
+    # fp16 weights and gradients with fp32 master weights (multi_mp_sgd_mom_update); no numpy model
+    p16 = plan(4)
+    p16['w0'] = [w.astype(np.float16) for w in p16['w0']]
+    p16['grads'] = [[g.astype(np.float16) for g in gs] for gs in p16['grads']]
+    cases['sgd_mp_fp16'] = dict(p16, opt=('SGD', dict(learning_rate=0.1, momentum=0.9, wd=1e-4, rescale_grad=1 / 64,
+                                                      multi_precision=True)), model=None)
+    # update_on_kvstore=False: Trainer hands the Updater every parameter of a device at once; LARS and
+    # LAMB aggregate them into multi-tensor operator calls (4 tensors per call)
+    names = ['conv0_weight', 'conv0_bias', 'bn0_gamma', 'bn0_beta', 'fc_weight', 'fc_bias', 'emb_weight']
+    lshapes = [(8, 3, 3, 3), (8,), (8,), (8,), (10, 72), (10,), (37, 5)]
+
+    def lplan(steps):
+        return dict(shapes=lshapes, names=names, mode='list', model=None, w0=[u(rng, *s) for s in lshapes],
+                    grads=[[u(rng, *s) for s in lshapes] for _ in range(steps)])
+    cases['lars_list'] = dict(lplan(3), opt=('LARS', dict(momentum=0.9, wd=1e-4, eta=0.02, eps=1e-6, rescale_grad=1 / 32)),
+                              sched=('FactorScheduler', dict(step=2, factor=0.5, base_lr=0.4)), lr_at=[0.4, 0.4, 0.2])
+    cases['lamb_list'] = dict(lplan(3), opt=('LAMB', dict(learning_rate=2e-3, wd=0.01, rescale_grad=0.25)))
     return cases
 
 
@@ -118,6 +135,8 @@ def run_updater_case(opt_mod, sched_mod, case):
     if 'sched' in case:
         sname, skw = case['sched']
         kw['lr_scheduler'] = getattr(sched_mod, sname)(**skw)
+    if 'names' in case:
+        kw['param_idx2name'] = dict(enumerate(case['names']))
     opt = getattr(opt_mod, name)(**kw)
     if case.get('lr_mult'):
         opt.set_lr_mult(case['lr_mult'])
@@ -126,6 +145,9 @@ def run_updater_case(opt_mod, sched_mod, case):
     upd = opt_mod.get_updater(opt)          # what KVStore.set_optimizer installs (kvstore.py:450-453)
     ws = [RP.NDArray(w.copy()) for w in case['w0']]
     for gs in case['grads']:
+        if case.get('mode') == 'list':              # Trainer._update: updater(indices, grads, weights)
+            upd(list(range(len(ws))), [RP.NDArray(g.copy()) for g in gs], ws)
+            continue
         for k, g in enumerate(gs):
             upd(k, RP.NDArray(g.copy()), ws[k])   # the store's callback: updater(key, merged, stored)
     return [w.a for w in ws]

@@ -43,7 +43,7 @@ def model_run(case):
     return [model.pull(k) for k in range(len(shapes))]
 
 
-@pytest.mark.parametrize("name", sorted(updater_cases()))
+@pytest.mark.parametrize("name", sorted(n for n, c in updater_cases().items() if c['model']))
 def test_model_vs_golden_trajectories(golden, name):
     g = golden("updater_trajectories")
     case = updater_cases()[name]

@@ -24,8 +24,11 @@ def eq(a, b):
     return a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
 
 
+STORE_CASES = sorted(n for n, c in updater_cases().items() if c['model'])
+
+
 @pytest.mark.parametrize("fused", ['1', '0'])
-@pytest.mark.parametrize("name", sorted(updater_cases()))
+@pytest.mark.parametrize("name", STORE_CASES)
 def test_store_trajectory_golden(mx, golden, name, fused, monkeypatch):
     """fused = '1': the optimizer step inside the reduce kernel (native replay of the bookkeeping);
     fused = '0': the reference's callback route (store -> Updater -> optimizer operators)"""
@@ -62,3 +65,53 @@ def test_store_trajectory_golden(mx, golden, name, fused, monkeypatch):
         kv.pushpull(keys, [[mx.nd.array(a, mx.gpu(0))] for a in gs], out=outs)
     for k in keys:
         assert eq(outs[k].asnumpy(), g["%s_w%d" % (name, k)]), (name, fused, k)
+
+
+def test_store_mixed_precision_fp16_golden(mx, golden):
+    """fp16 weights / gradients, fp32 master weights and momentum on the store (multi_precision): the
+    fused kernel against the reference Updater's multi_mp_sgd_mom_update trajectory, fp16 bits equal"""
+    g = golden("updater_trajectories")
+    case = updater_cases()['sgd_mp_fp16']
+    shapes, keys = case['shapes'], list(range(len(case['shapes'])))
+    kv = mx.kv.create('device')
+    for k in keys:
+        kv.init(k, mx.nd.array(case['w0'][k], mx.gpu(0), np.float16))
+    kv.set_optimizer(mx.optimizer.SGD(**case['opt'][1]))
+    outs = [mx.nd.empty(s, mx.gpu(0), np.float16) for s in shapes]
+    for gs in case['grads']:
+        kv.pushpull(keys, [[mx.nd.array(a, mx.gpu(0), np.float16)] for a in gs], out=outs)
+    for k in keys:
+        got = outs[k].asnumpy()
+        assert got.dtype == np.float16
+        assert eq(got.view(np.uint16), g["sgd_mp_fp16_w%d" % k].view(np.uint16)), k
+
+
+@pytest.mark.parametrize("name", ['lars_list', 'lamb_list'])
+def test_local_updater_lars_lamb_golden(mx, golden, name):
+    """update_on_kvstore=False: the LARS / LAMB front-end (tests/compat mirror, pinned to the reference's
+    on the CPU side) over this library's multi-tensor operators on the GPU, against the trajectory of
+    the reference's own classes over its own operators. Layers whose step involves a norm depend on
+    the association of a float sum of squares (2e-6 relative per operator call): held to 1e-5 after
+    three steps; gamma / beta / bias under LARS see no norm and must be bit-equal."""
+    from compat import mxnet_optimizer as mxopt
+    g = golden("updater_trajectories")
+    case = updater_cases()[name]
+    cls, kw = case['opt']
+    kw = dict(kw, param_idx2name=dict(enumerate(case['names'])))
+    if 'sched' in case:
+        class Sched(object):
+            base_lr = case['lr_at'][0]
+
+            def __call__(self, num_update):
+                return case['lr_at'][min(max(num_update, 1), len(case['lr_at'])) - 1]
+        kw['lr_scheduler'] = Sched()
+    opt = getattr(mxopt, cls)(**kw)
+    upd = mxopt.get_updater(opt)
+    ws = [mx.nd.array(w, mx.gpu(0)) for w in case['w0']]
+    for gs in case['grads']:
+        upd(list(range(len(ws))), [mx.nd.array(a, mx.gpu(0)) for a in gs], ws)
+    for k, nm in enumerate(case['names']):
+        got, want = ws[k].asnumpy().astype(np.float64), g["%s_w%d" % (name, k)].astype(np.float64)
+        assert np.all(np.abs(got - want) <= 1e-5 * np.abs(want) + 1e-7), (name, nm)
+        if cls == 'LARS' and nm.endswith(('gamma', 'beta', 'bias')):
+            assert eq(ws[k].asnumpy(), g["%s_w%d" % (name, k)]), (name, nm)
