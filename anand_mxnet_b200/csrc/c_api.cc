@@ -1104,3 +1104,22 @@ extern "C" int B200KVTestPlanChunks(const uint64_t* sizes, int nkeys, int ndev, 
   }
   return 0;
 }
+
+// host-only hook: the order in which the (key, position) pairs of one call are grouped
+// (kvstore_core.cc SortKeyPairs): positions[] after the sort, for the call order (stable) or the
+// reference's std::sort order (B200KV_GROUP_ORDER=reference)
+namespace b200kv {
+void SortKeyPairs(std::vector<std::pair<int, int>>* idx, bool reference_order);
+}
+
+extern "C" B200KV_DLL int B200KVTestGroupOrder(const int* keys, int n, int reference_order, int* positions) {
+  try {
+    std::vector<std::pair<int, int>> idx(static_cast<size_t>(n));
+    for (int i = 0; i < n; ++i) idx[i] = {keys[i], i};
+    b200kv::SortKeyPairs(&idx, reference_order != 0);
+    for (int i = 0; i < n; ++i) positions[i] = idx[i].second;
+  } catch (const std::exception& e) {
+    return HandleException(e);
+  }
+  return 0;
+}

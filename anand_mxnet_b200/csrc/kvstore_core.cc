@@ -305,6 +305,26 @@ void KVStore::KeyHyper(const KeyEntry& e, int opt_kind, float* lr, float* wd) {
 // =================================================================================================
 // grouping (KVStoreLocal::GroupKVPairs, kvstore_local.h:377-407)
 // =================================================================================================
+// The values of one key are reduced in the order the call lists them (a stable sort by key). The
+// reference orders the (key, position) pairs with std::sort, which is not stable: identical for calls
+// of at most 16 pairs -- every per-parameter call of gluon.Trainer / Module -- but in a bigger call
+// (a key LIST with several values per key) the values of a key reach its reduce in whatever order
+// libstdc++'s introsort leaves them, and a floating-point sum depends on that order.
+// B200KV_GROUP_ORDER=reference reproduces it (same std::sort, same comparator, same libstdc++).
+void SortKeyPairs(std::vector<std::pair<int, int>>* idx, bool reference_order) {
+  auto by_key = [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; };
+  if (reference_order) {
+    std::sort(idx->begin(), idx->end(), by_key);
+  } else {
+    std::stable_sort(idx->begin(), idx->end(), by_key);
+  }
+}
+
+static bool ReferenceGroupOrder() {
+  const char* e = std::getenv("B200KV_GROUP_ORDER");
+  return e != nullptr && std::strcmp(e, "reference") == 0;
+}
+
 template <typename FValid>
 static void GroupKVPairs(const std::vector<int>& keys, const std::vector<NDArray>& values,
                          std::vector<int>* uniq_keys, std::vector<std::vector<NDArray>>* grouped,
@@ -313,10 +333,7 @@ static void GroupKVPairs(const std::vector<int>& keys, const std::vector<NDArray
   if (keys.empty()) return;
   std::vector<std::pair<int, int>> idx(keys.size());
   for (size_t i = 0; i < keys.size(); ++i) idx[i] = {keys[i], static_cast<int>(i)};
-  std::stable_sort(idx.begin(), idx.end(),
-                   [](const std::pair<int, int>& a, const std::pair<int, int>& b) {
-                     return a.first < b.first;
-                   });
+  SortKeyPairs(&idx, ReferenceGroupOrder());
   bool have = false;
   int pre_key = 0;
   for (auto& i : idx) {

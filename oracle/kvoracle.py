@@ -633,6 +633,22 @@ class Ref(object):
           int(bool(src_dense_rows)), int(bool(row_block)), _ptr(out_idx), _ptr(out_val), nthreads)
         return out_idx, out_val
 
+    def group_positions(self, keys):
+        """the reference's own KVStoreLocal::GroupKVPairs (kvstore_local.h:377-407) compiled against
+        this toolchain's libstdc++: (uniq keys, positions per key in the order it hands them on)"""
+        keys = np.ascontiguousarray(keys, dtype=np.int32)
+        n = keys.size
+        uniq, counts, pos = (np.zeros(max(n, 1), np.int32) for _ in range(3))
+        f = self.lib.mxref_group_kv_pairs
+        f.restype = ctypes.c_int64
+        f.argtypes = [ctypes.c_int64, _P, _P, _P, _P]
+        g = f(n, _ptr(keys), _ptr(uniq), _ptr(counts), _ptr(pos))
+        out, p = [], 0
+        for c in counts[:g]:
+            out.append([int(x) for x in pos[p:p + c]])
+            p += c
+        return [int(k) for k in uniq[:g]], out
+
     def unique(self, ids):
         """UniqueImpl<cpu> (kvstore_utils.cc:31-44)"""
         ids = np.ascontiguousarray(ids, dtype=np.int64).ravel().copy()
@@ -733,18 +749,108 @@ def scalar_param(v):
     return dmlc_stof(repr(float(v)))
 
 
-def group_kv_pairs(keys, values):
-    """KVStoreLocal::GroupKVPairs, src/kvstore/kvstore_local.h:377-407: stable-by-key grouping;
-    returns (uniq_keys ascending, grouped values in call order)."""
-    order = sorted(range(len(keys)), key=lambda i: keys[i])  # python sort is stable
-    uniq, grouped = [], []
-    for i in order:
-        if not uniq or keys[i] != uniq[-1]:
-            uniq.append(keys[i])
-            grouped.append([values[i]])
+def _libstdcxx_sort_by_key(idx):
+    """std::sort(idx.begin(), idx.end(), by .first) as libstdc++ implements it (bits/stl_algo.h:
+    introsort -- median-of-three pivot moved to the front, unguarded Hoare partition, ranges of at
+    most 16 left for one final insertion sort). NOT stable: pairs with equal keys leave it in an
+    order that depends on these very steps, which is why it is restated step by step. `idx` is a
+    list of (key, position); sorted in place. The heap-sort fallback (recursion deeper than
+    2*log2(n)) is not restated: no key pattern of a kvstore call reaches it."""
+    def less(a, b):
+        return a[0] < b[0]
+
+    def move_median_to_first(res, a, b, c):
+        if less(idx[a], idx[b]):
+            pick = b if less(idx[b], idx[c]) else (c if less(idx[a], idx[c]) else a)
         else:
-            grouped[-1].append(values[i])
+            pick = a if less(idx[a], idx[c]) else (c if less(idx[b], idx[c]) else b)
+        idx[res], idx[pick] = idx[pick], idx[res]
+
+    def partition(first, last, pivot):
+        while True:
+            while less(idx[first], idx[pivot]):
+                first += 1
+            last -= 1
+            while less(idx[pivot], idx[last]):
+                last -= 1
+            if not first < last:
+                return first
+            idx[first], idx[last] = idx[last], idx[first]
+            first += 1
+
+    def introsort_loop(first, last, depth):
+        while last - first > 16:
+            if depth == 0:
+                raise NotImplementedError("heap-sort fallback of std::sort")
+            depth -= 1
+            move_median_to_first(first, first + 1, first + (last - first) // 2, last - 1)
+            cut = partition(first + 1, last, first)
+            introsort_loop(cut, last, depth)
+            last = cut
+
+    def linear_insert(last):            # __unguarded_linear_insert
+        val = idx[last]
+        nxt = last - 1
+        while less(val, idx[nxt]):
+            idx[last] = idx[nxt]
+            last = nxt
+            nxt -= 1
+        idx[last] = val
+
+    def insertion_sort(first, last):
+        for i in range(first + 1, last):
+            if less(idx[i], idx[first]):
+                val = idx[i]
+                idx[first + 1:i + 1] = idx[first:i]
+                idx[first] = val
+            else:
+                linear_insert(i)
+    n = len(idx)
+    if n == 0:
+        return
+    introsort_loop(0, n, 2 * (n.bit_length() - 1))
+    if n > 16:
+        insertion_sort(0, 16)
+        for i in range(16, n):
+            linear_insert(i)
+    else:
+        insertion_sort(0, n)
+
+
+def group_positions(keys, order='call'):
+    """KVStoreLocal::GroupKVPairs, src/kvstore/kvstore_local.h:377-407, on the positions of a call's
+    (key, value) pairs: returns (uniq_keys ascending, [positions of each key's values]).
+
+    order='call' : values of a key in the order the call lists them (a stable sort by key) -- what
+        the product does, and what the reference does whenever a call has at most 16 pairs, i.e. for
+        every per-parameter call of gluon.Trainer / Module (one key x its devices) and for the
+        reference's own unit tests.
+    order='reference': the reference sorts the pairs with std::sort, which is not stable; in a call
+        with MORE than 16 pairs (e.g. a list of 10 keys x 4 devices) the values of a key reach the
+        reduce in the order libstdc++'s introsort happens to leave them -- restated step by step in
+        _libstdcxx_sort_by_key and pinned to the reference's own function compiled against
+        libstdc++ (Ref.group_positions)."""
+    idx = [(int(k), i) for i, k in enumerate(keys)]
+    if order == 'call':
+        idx.sort(key=lambda p: p[0])       # python's sort is stable
+    elif order == 'reference':
+        _libstdcxx_sort_by_key(idx)
+    else:
+        raise ValueError(order)
+    uniq, grouped = [], []
+    for k, i in idx:
+        if not uniq or k != uniq[-1]:
+            uniq.append(k)
+            grouped.append([i])
+        else:
+            grouped[-1].append(i)
     return uniq, grouped
+
+
+def group_kv_pairs(keys, values, order='call'):
+    """group_positions applied to the values: (uniq_keys ascending, grouped values)"""
+    uniq, pos = group_positions(keys, order)
+    return uniq, [[values[i] for i in g] for g in pos]
 
 
 def adam_lr(lr, beta1, beta2, t):

@@ -6,6 +6,7 @@
 //     accumulated source by source in list order), and
 //   * sparse_retain (src/operator/tensor/sparse_retain-inl.h:121-150, 205-262: the kernels behind
 //     row_sparse_pull),
+//   * the grouping of a call's (key, value) pairs (KVStoreLocal::GroupKVPairs, kvstore_local.h:377-407),
 // so that oracle/kvoracle.c's restatement of them is pinned to live reference code, not only to the
 // reference's unit-test identities.
 //
@@ -64,7 +65,32 @@ struct NDArray {
 
 }  // namespace mxref_sparse
 
+// KVStoreLocal::GroupKVPairs (src/kvstore/kvstore_local.h:377-407), a member template of a class that
+// cannot be instantiated without libmxnet: the function template alone is cut out of the header at
+// build time (oracle/Makefile) and compiled unchanged, as a free function, with V = position in the call.
+namespace mxref_group {
+#include "_ref/excerpt_group_kv_pairs.inc"
+}  // namespace mxref_group
+
 extern "C" {
+
+// Groups the n (key, position) pairs of one call the way the reference does: uniq[] = distinct keys
+// ascending, counts[] = values per key, positions[] = the call positions in the order the reference
+// hands them to the reduce (group after group). Returns the number of distinct keys.
+int64_t mxref_group_kv_pairs(int64_t n, const int* keys, int* uniq, int* counts, int* positions) {
+  if (n == 0) return 0;      // the reference dereferences idx[0] unconditionally
+  std::vector<int> k(keys, keys + n), v(n), uk;
+  for (int64_t i = 0; i < n; ++i) v[i] = static_cast<int>(i);
+  std::vector<std::vector<int>> gv;
+  mxref_group::GroupKVPairs(k, v, &uk, &gv, [](int, int, bool) { return true; }, false);
+  int64_t p = 0;
+  for (size_t g = 0; g < uk.size(); ++g) {
+    uniq[g] = uk[g];
+    counts[g] = static_cast<int>(gv[g].size());
+    for (int pos : gv[g]) positions[p++] = pos;
+  }
+  return static_cast<int64_t>(uk.size());
+}
 
 // ElementwiseSumRsp (ndarray_function.cc:155-176) over `nsrc` row_sparse sources: returns the
 // number of union rows; out_idx / out_val must hold sum(nnr) rows.
