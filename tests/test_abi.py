@@ -168,3 +168,104 @@ def test_optimizer_record_rules(mx):
     assert pickle.loads(upd.get_states()) == {3: None}
     st, opt = pickle.loads(upd.get_states(dump_optimizer=True))
     assert st == {3: None} and type(opt).__name__ == 'LARS'
+
+
+# ---------------------------------------------------------------- drop-in boundary: signatures
+_REF_HEADERS = [("/root/reference/include/mxnet/c_api.h", "MXNET_DLL"),
+                ("/root/reference/3rdparty/tvm/nnvm/include/nnvm/c_api.h", "NNVM_DLL")]
+_BASE = {'int', 'char', 'void', 'float', 'double', 'size_t', 'bool', 'uint32_t', 'int64_t', 'uint64_t', 'unsigned',
+         'const', 'int32_t', 'uint8_t'}
+
+
+def _c_declarations(path, macro):
+    """{function: (return type tokens, [parameter type tokens])} and {typedef: tokens} of a C header;
+    parameter names, comments, whitespace and DEFAULT(...) default arguments dropped"""
+    import re
+    txt = open(path).read()
+    txt = re.sub(r'/\*.*?\*/', ' ', txt, flags=re.S)
+    txt = re.sub(r'//[^\n]*', ' ', txt)
+    txt = re.sub(r'DEFAULT\([^)]*\)', ' ', txt)
+    typedefs = {m.group(2): re.findall(r'\w+|\*', m.group(1))
+                for m in re.finditer(r'typedef\s+([\w\s\*]+?)\s*\b(\w+)\s*;', txt)}
+
+    def split(a):
+        parts, depth, cur = [], 0, ''
+        for ch in a:
+            depth += (ch == '(') - (ch == ')')
+            if ch == ',' and depth == 0:
+                parts.append(cur)
+                cur = ''
+            else:
+                cur += ch
+        return parts + [cur]
+
+    def param(p):
+        if '(' in p:                          # function-pointer parameter: compare its text without names
+            return [re.sub(r'\s+', '', re.sub(r'\b\w+\s*(?=[,)])', '', p))]
+        toks = re.findall(r'\w+|\*|\[\]', p)
+        if toks[-1] == '[]':
+            toks = toks[:-2] + ['*']          # T name[]  ==  T* name
+        elif len(toks) >= 2 and toks[-1] != '*' and toks[-1] not in _BASE and toks[-1] not in typedefs \
+                and not toks[-1][0].isupper():
+            toks = toks[:-1]                  # trailing identifier = the parameter's name
+        return toks
+    # function-type typedefs (callbacks): "typedef void (Name)(params);" / "typedef void (*Name)(params);"
+    for m in re.finditer(r'typedef\s+([\w\s\*]+?)\(\s*(\*?)\s*(\w+)\s*\)\s*\(([^;]*?)\)\s*;', txt, flags=re.S):
+        typedefs[m.group(3)] = ['fn' + m.group(2)] + re.findall(r'\w+|\*', m.group(1)) + \
+            ['('] + [x for a in split(m.group(4)) for x in param(a.strip()) + [',']] + [')']
+    fns = {}
+    for m in re.finditer(macro + r'\s+([\w\s\*]+?)\b(\w+)\s*\(([^;{]*?)\)\s*;', txt, flags=re.S):
+        args = m.group(3).strip()
+        fns[m.group(2)] = (re.findall(r'\w+|\*', m.group(1)),
+                           [] if args in ('', 'void') else [param(a.strip()) for a in split(args)])
+    return fns, typedefs
+
+
+def _resolve(toks, typedefs):
+    out = []
+    for t in toks:
+        t = {'mx_uint': 'uint32_t', 'mx_float': 'float', 'unsigned': 'uint32_t'}.get(t, t)
+        seen = set()
+        while t in typedefs and t not in seen and len(typedefs[t]) <= 3:
+            seen.add(t)
+            sub = [x for x in typedefs[t]]
+            if len(sub) == 1:
+                t = sub[0]
+                continue
+            out.extend(_resolve(sub[:-1], typedefs))
+            t = sub[-1]
+        out.append(t)
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(_REF_HEADERS[0][0]), reason="needs /root/reference")
+def test_signatures_match_reference_headers():
+    """every MX* / NN* function include/b200kv_c_api.h declares has, type for type, the signature the
+    reference declares in include/mxnet/c_api.h (or nnvm/c_api.h): return type, parameter count, every
+    parameter's type after resolving the handle typedefs -- so a binding written against the
+    reference's header binds libb200kv.so unchanged"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mine, my_td = _c_declarations(os.path.join(root, "include", "b200kv_c_api.h"), "B200KV_DLL")
+    ref, ref_td = {}, {}
+    for path, macro in _REF_HEADERS:
+        f, t = _c_declarations(path, macro)
+        ref.update(f)
+        ref_td.update(t)
+    checked = 0
+    for name, (ret, params) in sorted(mine.items()):
+        if name.startswith("B200KV"):
+            continue                           # extensions: no reference counterpart
+        assert name in ref, "%s is not a function of the reference's C API" % name
+        rret, rparams = ref[name]
+        assert _resolve(ret, my_td) == _resolve(rret, ref_td), name
+        assert len(params) == len(rparams), (name, params, rparams)
+        for i, (a, b) in enumerate(zip(params, rparams)):
+            assert _resolve(a, my_td) == _resolve(b, ref_td), (name, i, a, b)
+        checked += 1
+    assert checked >= 60
+    # the callback types those functions take
+    for cb in ("MXKVStoreUpdater", "MXKVStoreStrUpdater", "MXKVStoreServerController", "EngineAsyncFunc",
+               "EngineSyncFunc", "EngineFuncParamDeleter"):
+        assert my_td[cb][0].startswith('fn') and my_td[cb][0] == ref_td[cb][0], cb
+        assert _resolve(my_td[cb][1:], {k: v for k, v in my_td.items() if k != cb}) == \
+            _resolve(ref_td[cb][1:], {k: v for k, v in ref_td.items() if k != cb}), cb
