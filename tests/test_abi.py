@@ -269,3 +269,33 @@ def test_signatures_match_reference_headers():
         assert my_td[cb][0].startswith('fn') and my_td[cb][0] == ref_td[cb][0], cb
         assert _resolve(my_td[cb][1:], {k: v for k, v in my_td.items() if k != cb}) == \
             _resolve(ref_td[cb][1:], {k: v for k, v in ref_td.items() if k != cb}), cb
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/python/mxnet/kvstore/kvstore.py"),
+                    reason="needs /root/reference")
+def test_python_kvstore_surface_matches_reference():
+    """boundary B1: every method / property of the reference's python KVStore and KVStoreBase classes
+    (python/mxnet/kvstore/{kvstore,base}.py, parsed, not imported) exists on this package's classes
+    with the same parameter names, defaults and decorators"""
+    import ast
+
+    def methods(path, cls):
+        out = {}
+        for node in ast.parse(open(path).read()).body:
+            if isinstance(node, ast.ClassDef) and node.name == cls:
+                for f in node.body:
+                    if isinstance(f, ast.FunctionDef):
+                        out[f.name] = ([a.arg for a in f.args.args], [ast.unparse(d) for d in f.args.defaults],
+                                       [ast.unparse(d) for d in f.decorator_list])
+        return out
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    total = 0
+    for fname, cls in (("kvstore.py", "KVStore"), ("base.py", "KVStoreBase")):
+        ref = methods("/root/reference/python/mxnet/kvstore/" + fname, cls)
+        mine = methods(os.path.join(root, "anand_mxnet_b200", "kvstore", fname), cls)
+        assert len(ref) >= 10
+        for name, sig in ref.items():
+            assert name in mine, "%s.%s is missing" % (cls, name)
+            assert mine[name] == sig, (cls, name, mine[name], sig)
+            total += 1
+    assert total >= 30
