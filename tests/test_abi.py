@@ -299,3 +299,66 @@ def test_python_kvstore_surface_matches_reference():
             assert mine[name] == sig, (cls, name, mine[name], sig)
             total += 1
     assert total >= 25
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/python/mxnet/kvstore/base.py"),
+                    reason="needs /root/reference")
+def test_key_value_marshalling_vs_reference(mx):
+    """kvstore/base.py:_ctype_key_value here is a one-pass rewrite of the reference's recursive helper
+    (python/mxnet/kvstore/base.py:33-65). The reference's function -- and the ctypes helpers it uses
+    from python/mxnet/base.py -- are compiled from their source text at run time (ast; nothing is
+    imported, libmxnet is not needed) and both are fed the same keys / values: same C key array, same
+    handle order, same str-key flag, same refusals."""
+    import ast
+    import ctypes
+    from array import array
+    from anand_mxnet_b200.base import _LIB
+    from anand_mxnet_b200.kvstore.base import _ctype_key_value as mine
+    from anand_mxnet_b200.ndarray import NDArray
+
+    def functions(path, names):
+        found = {}
+        for n in ast.walk(ast.parse(open(path).read())):
+            if isinstance(n, ast.FunctionDef) and n.name in names and n.col_offset <= 4:
+                if n.name not in found or n.lineno > found[n.name].lineno:
+                    found[n.name] = n            # python-2 / python-3 twins: the later one is python 3's
+        assert sorted(found) == sorted(names), (path, names)
+        return ast.Module(body=sorted(found.values(), key=lambda n: n.lineno), type_ignores=[])
+    ns = {'ctypes': ctypes, 'array': array, 'NDArray': NDArray, 'string_types': (str,), 'py_str': lambda b: b.decode()}
+    exec(compile(functions("/root/reference/python/mxnet/base.py",
+                           ['c_str', 'c_str_array', 'c_array', 'c_array_buf', 'c_handle_array']),
+                 "reference base.py", "exec"), ns)
+    exec(compile(functions("/root/reference/python/mxnet/kvstore/base.py", ['_ctype_key_value']),
+                 "reference kvstore/base.py", "exec"), ns)
+    ref = ns['_ctype_key_value']
+
+    def nd():
+        h = ctypes.c_void_p()
+        assert _LIB.MXNDArrayCreateNone(ctypes.byref(h)) == 0        # an empty handle: no device needed
+        return NDArray(h)
+    a = [nd() for _ in range(12)]
+
+    def flat(res):
+        keys, handles, use_str = res
+        ks = [k.decode() if isinstance(k, bytes) else int(k) for k in keys]
+        hs = [h if isinstance(h, int) else ctypes.cast(h, ctypes.c_void_p).value for h in handles]
+        return ks, hs, bool(use_str)
+    cases = [
+        (3, a[0]), ('w', a[0]), (3, [a[0], a[1], a[2]]), ('w', (a[0], a[1])),
+        ([1, 2, 3], [a[0], a[1], a[2]]), (['a', 'b'], [a[0], a[1]]), ((5, 4), (a[0], a[1])),
+        ([1, 2], [[a[0], a[1]], [a[2], a[3]]]), (['x', 'y'], [[a[0]], [a[1], a[2], a[3]]]),
+        ([7, 7, 8], [a[0], a[1], a[2]]),                                  # duplicate keys = several devices
+        ([1, 2, 3], [a[0], [a[1], a[2]], a[3]]),                          # mixed nesting
+        ([9, 3, 5], [[a[0], a[1]], a[2], [a[3]]]),
+        ([], []), ([4], [[]]),
+        (list(range(157)), [[a[i % 12], a[(i + 1) % 12]] for i in range(157)]),
+    ]
+    for keys, vals in cases:
+        assert flat(mine(keys, vals)) == flat(ref(keys, vals)), (keys,)
+    # what the reference refuses, this refuses
+    for keys, vals in [([1, 'a'], [a[0], a[1]]), ([1, 2], [a[0]]), (1.5, a[0]), ([1.5], [a[0]]),
+                       (['a', 2], [[a[0]], [a[1]]])]:
+        with pytest.raises(AssertionError):
+            ref(keys, vals)
+        with pytest.raises(AssertionError):
+            mine(keys, vals)
