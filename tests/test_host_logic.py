@@ -179,3 +179,35 @@ def test_bench_parity_and_config_helpers():
         assert not np.array_equal(w1[0], w2[0])
     finally:
         del bench.WORKLOADS['_tiny']
+
+
+def test_reference_arm_under_torchrun_two_ranks():
+    """bench.py --impl reference launched the way the driver launches it for N > 1 (torchrun, one
+    process per GPU): rank 0 alone runs the reference's CPU implementation and prints ONE JSON line
+    whose `config` is the one the GPU arm prints at that N; the other rank exits 0 without work.
+    No GPU involved (gloo-free: the arm needs no process group)."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                       cwd=root, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, p.stdout[-2000:]
+    d = json.loads(lines[0])
+    sys.path.insert(0, root)
+    import bench
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1
+    assert d["config"] == bench.config_block("resnet50_sgd", 2)
+    assert d["metric"] == "kvstore_push_pull_GBps" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["ms_per_step"] > 0
