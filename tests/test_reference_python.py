@@ -10,7 +10,7 @@ precision states, LARS's layer split and LAMB's step counts are all the referenc
     AND call for call (same operators, same parameter strings, same order);
   * tests/golden/updater_trajectories.npz (written from it by oracle/gen_golden.py; the reference
     Python cannot travel to the GPU box, the fixture does) -- checked here against the model, and
-    against the CUDA store in tests/test_zz_updater_golden_gpu.py.
+    against the CUDA store in tests/test_updater_reference_fixture_gpu.py.
 
 The live halves need /root/reference and are skipped where it is absent (the GPU box)."""
 import numpy as np
